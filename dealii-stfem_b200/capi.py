@@ -1,0 +1,215 @@
+"""ctypes binding of the C ABI (include/stfem_b200.h) — the stub a maintainer of a Python
+harness would add.  Thin by design: numpy in, numpy out, no torch.
+
+The product path fails loudly when libstfem_b200.so is missing: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstfem_b200.so")
+
+F64, F32 = 0, 1
+MAX_BLOCKS = 16
+_NP = {F64: np.float64, F32: np.float32}
+
+
+class StfemError(RuntimeError):
+    pass
+
+
+class OpDesc(C.Structure):
+    _fields_ = [("degree", C.c_int), ("number_type", C.c_int), ("nb_rows", C.c_int), ("nb_cols", C.c_int),
+                ("Alpha", C.POINTER(C.c_double)), ("Beta", C.POINTER(C.c_double)),
+                ("laplace_coeff_cell", C.POINTER(C.c_double)), ("kernel_variant", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/stfem_b200.h declares: (restype, argtypes)
+_vp, _vpp = C.c_void_p, C.POINTER(C.c_void_p)
+SYMBOLS = {
+    "stfem_last_error": (C.c_char_p, []),
+    "stfem_version": (C.c_char_p, []),
+    "stfem_ctx_create": (C.c_int, [C.c_int, _vpp]),
+    "stfem_ctx_destroy": (C.c_int, [_vp]),
+    "stfem_ctx_synchronize": (C.c_int, [_vp]),
+    "stfem_ctx_stream": (_vp, [_vp]),
+    "stfem_ctx_launch_count": (C.c_longlong, [_vp]),
+    "stfem_dev_alloc": (C.c_int, [_vp, C.c_size_t, _vpp]),
+    "stfem_dev_free": (C.c_int, [_vp, _vp]),
+    "stfem_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "stfem_dev_download": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "stfem_dev_memset": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t]),
+    "stfem_host_alloc_pinned": (C.c_int, [C.c_size_t, _vpp]),
+    "stfem_host_free_pinned": (C.c_int, [_vp]),
+    "stfem_mesh_create": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.c_uint, _vpp]),
+    "stfem_mesh_destroy": (C.c_int, [_vp]),
+    "stfem_op_create": (C.c_int, [_vp, C.POINTER(OpDesc), _vpp]),
+    "stfem_op_destroy": (C.c_int, [_vp]),
+    "stfem_op_n_dofs_per_block": (C.c_longlong, [_vp]),
+    "stfem_op_n_blocks": (C.c_int, [_vp]),
+    "stfem_op_vmult": (C.c_int, [_vp, _vpp, _vpp, C.c_int]),
+    "stfem_op_vmult_slice_add": (C.c_int, [_vp, _vpp, _vp]),
+    "stfem_op_diagonal": (C.c_int, [_vp, _vpp]),
+    "stfem_op_vmult_host": (C.c_int, [_vp, _vpp, _vpp, C.c_int]),
+    "stfem_op_set_timing": (C.c_int, [_vp, C.c_int]),
+    "stfem_op_last_kernel_ms": (C.c_float, [_vp]),
+}
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built — no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StfemError("%s not found: run `python dealii-stfem_b200/build.py` (no CPU fallback exists)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise StfemError("stfem error %d: %s" % (rc, lib().stfem_last_error().decode()))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().stfem_ctx_create(device, C.byref(self.h)))
+
+    def synchronize(self):
+        check(lib().stfem_ctx_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib().stfem_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return lib().stfem_ctx_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().stfem_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class DeviceBlockVector:
+    """nb separate device arrays of N numbers (reference BlockVectorT, include/types.h:20-23)."""
+
+    def __init__(self, ctx, nb, n, number_type=F64):
+        self.ctx, self.nb, self.n, self.number_type = ctx, nb, n, number_type
+        self.dtype = _NP[number_type]
+        self.itemsize = np.dtype(self.dtype).itemsize
+        self.ptrs = (C.c_void_p * nb)()
+        for b in range(nb):
+            p = C.c_void_p()
+            check(lib().stfem_dev_alloc(ctx.h, n * self.itemsize, C.byref(p)))
+            self.ptrs[b] = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype).reshape(self.nb, self.n)
+        for b in range(self.nb):
+            check(lib().stfem_dev_upload(self.ctx.h, self.ptrs[b], arr[b].ctypes.data, self.n * self.itemsize))
+        return self
+
+    def download(self):
+        out = np.empty((self.nb, self.n), dtype=self.dtype)
+        for b in range(self.nb):
+            check(lib().stfem_dev_download(self.ctx.h, out[b].ctypes.data, self.ptrs[b], self.n * self.itemsize))
+        return out
+
+    def zero(self):
+        for b in range(self.nb):
+            check(lib().stfem_dev_memset(self.ctx.h, self.ptrs[b], 0, self.n * self.itemsize))
+
+    def free(self):
+        for b in range(self.nb):
+            if self.ptrs[b]:
+                lib().stfem_dev_free(self.ctx.h, self.ptrs[b])
+                self.ptrs[b] = None
+
+
+class Mesh:
+    def __init__(self, ctx, n_cells, lower=None, upper=None, vertices=None, dirichlet_faces=None):
+        self.ctx = ctx
+        self.dim = len(n_cells)
+        self.n_cells = [int(v) for v in n_cells]
+        n = (C.c_int * self.dim)(*self.n_cells)
+        lo = np.zeros(self.dim) if lower is None else np.asarray(lower, np.float64)
+        up = np.ones(self.dim) if upper is None else np.asarray(upper, np.float64)
+        vp = None
+        if vertices is not None:
+            self._v = np.ascontiguousarray(vertices, np.float64)
+            vp = _dptr(self._v)
+        mask = (0x3f if self.dim == 3 else 0xf) if dirichlet_faces is None else dirichlet_faces
+        self.h = C.c_void_p()
+        check(lib().stfem_mesh_create(ctx.h, self.dim, n, _dptr(lo), _dptr(up), vp, mask, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().stfem_mesh_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Operator:
+    """SystemMatrix<dim, Number, MatrixFreeOperatorScalar> of the reference (operators.h:516-663)."""
+
+    def __init__(self, mesh, degree, Alpha, Beta, number_type=F64, laplace_coeff_cell=None, variant=0):
+        self.mesh, self.ctx, self.number_type = mesh, mesh.ctx, number_type
+        A = np.ascontiguousarray(np.atleast_2d(Alpha), np.float64)
+        B = np.ascontiguousarray(np.atleast_2d(Beta), np.float64)
+        assert A.shape == B.shape
+        d = OpDesc()
+        d.degree, d.number_type, d.nb_rows, d.nb_cols = degree, number_type, A.shape[0], A.shape[1]
+        d.Alpha, d.Beta = _dptr(A), _dptr(B)
+        if laplace_coeff_cell is not None:
+            self._coef = np.ascontiguousarray(laplace_coeff_cell, np.float64)
+            d.laplace_coeff_cell = _dptr(self._coef)
+        d.kernel_variant = variant
+        self.h = C.c_void_p()
+        check(lib().stfem_op_create(mesh.h, C.byref(d), C.byref(self.h)))
+        self.nb_rows, self.nb_cols = A.shape
+        self.n = lib().stfem_op_n_dofs_per_block(self.h)
+
+    def new_vector(self, nb=None):
+        return DeviceBlockVector(self.ctx, self.nb_rows if nb is None else nb, self.n, self.number_type)
+
+    def vmult(self, dst, src, transpose=False):
+        check(lib().stfem_op_vmult(self.h, dst.ptrs, src.ptrs, 1 if transpose else 0))
+
+    def Tvmult(self, dst, src):
+        self.vmult(dst, src, True)
+
+    def vmult_slice_add(self, dst, src0):
+        check(lib().stfem_op_vmult_slice_add(self.h, dst.ptrs, src0.ptrs[0]))
+
+    def vmult_host(self, dst, src, transpose=False):
+        """dst, src: numpy [nb, N] (C-contiguous rows; pinned or pageable)."""
+        nb = self.nb_rows
+        dp = (C.c_void_p * nb)(*[dst[b].ctypes.data for b in range(nb)])
+        spp = (C.c_void_p * nb)(*[src[b].ctypes.data for b in range(nb)])
+        check(lib().stfem_op_vmult_host(self.h, dp, spp, 1 if transpose else 0))
+
+    def set_timing(self, on=True):
+        check(lib().stfem_op_set_timing(self.h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        return lib().stfem_op_last_kernel_ms(self.h)
+
+    def close(self):
+        if self.h:
+            lib().stfem_op_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,373 @@
+// C ABI: space-time operator (SystemMatrix + MatrixFreeOperator of the reference,
+// include/operators.h:516-663 and :967-1191).
+#include "basis_host.hpp"
+#include "common.hpp"
+#include "op.hpp"
+#include "st_vmult_generic.cuh"
+
+namespace stfem
+{
+  // ------------------------------------------------------------------ metric set-up kernel
+  // MappingQ1: J = dx/dxi from the 2^dim cell vertices; stores, per cell and
+  // quadrature point, the symmetric tensor J^-1 J^-T * det(J) * w_q and JxW = det(J) * w_q.
+  template <int DIM, typename T>
+  __global__ void metric_kernel(const double *__restrict__ vertices, int n0, int n1, int n2, int nq1,
+                                const double *__restrict__ xq, const double *__restrict__ wq, T *__restrict__ metric)
+  {
+    constexpr int NSYM = DIM * (DIM + 1) / 2;
+    const int     nq   = (DIM == 3) ? nq1 * nq1 * nq1 : nq1 * nq1;
+    const long long n_cells = (long long)n0 * n1 * ((DIM == 3) ? n2 : 1);
+    const long long gid     = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_cells * nq) return;
+    const long long cell = gid / nq;
+    const int       q    = (int)(gid % nq);
+    const int       qx = q % nq1, qy = (q / nq1) % nq1, qz = (DIM == 3) ? q / (nq1 * nq1) : 0;
+    const int       cx = (int)(cell % n0), cy = (int)((cell / n0) % n1), cz = (DIM == 3) ? (int)(cell / ((long long)n0 * n1)) : 0;
+    const double    xi[3] = {xq[qx], xq[qy], (DIM == 3) ? xq[qz] : 0.0};
+    double          J[DIM][DIM];
+    for (int a = 0; a < DIM; ++a)
+      for (int b = 0; b < DIM; ++b) J[a][b] = 0;
+    for (int v = 0; v < (1 << DIM); ++v)
+      {
+        const int vx = v & 1, vy = (v >> 1) & 1, vz = (v >> 2) & 1;
+        long long vid = (long long)(cx + vx) + (long long)(n0 + 1) * (cy + vy);
+        if (DIM == 3) vid += (long long)(n0 + 1) * (n1 + 1) * (cz + vz);
+        const double N[3]  = {vx ? xi[0] : 1 - xi[0], vy ? xi[1] : 1 - xi[1], vz ? xi[2] : 1 - xi[2]};
+        const double dN[3] = {vx ? 1.0 : -1.0, vy ? 1.0 : -1.0, vz ? 1.0 : -1.0};
+        for (int b = 0; b < DIM; ++b)
+          {
+            double s = dN[b];
+            for (int c = 0; c < DIM; ++c)
+              if (c != b) s *= N[c];
+            for (int a = 0; a < DIM; ++a) J[a][b] += vertices[vid * DIM + a] * s;
+          }
+      }
+    double det, inv[DIM][DIM];
+    if (DIM == 2)
+      {
+        det       = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        inv[0][0] = J[1][1] / det;
+        inv[0][1] = -J[0][1] / det;
+        inv[1][0] = -J[1][0] / det;
+        inv[1][1] = J[0][0] / det;
+      }
+    else
+      {
+        const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        det              = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+        inv[0][0]        = c00 / det;
+        inv[1][0]        = c01 / det;
+        inv[2][0]        = c02 / det;
+        inv[0][1]        = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+        inv[1][1]        = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+        inv[2][1]        = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+        inv[0][2]        = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+        inv[1][2]        = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+        inv[2][2]        = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+      }
+    const double w   = wq[qx] * wq[qy] * ((DIM == 3) ? wq[qz] : 1.0);
+    const double jxw = det * w;
+    T           *out = metric + (size_t)gid * (NSYM + 1);
+    int          s   = 0;
+    for (int a = 0; a < DIM; ++a)
+      for (int b = a; b < DIM; ++b)
+        {
+          double g = 0;
+          for (int c = 0; c < DIM; ++c) g += inv[a][c] * inv[b][c]; // (J^-1 J^-T)_ab, inv[a][c] = dxi_a/dx_c
+          out[s++] = (T)(g * jxw);
+        }
+    out[NSYM] = (T)jxw;
+  }
+
+  // ------------------------------------------------------------------ typed launchers
+  template <int DIM, int N1, typename T>
+  static int launch_generic(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst,
+                            const void *alpha, const void *beta)
+  {
+    stfem_mesh     *m = op->mesh;
+    VmultArgs<T, N1> a;
+    for (int q = 0; q < N1 * N1; ++q)
+      {
+        a.sh.S[q]  = (T)op->shape->S[q];
+        a.sh.Dc[q] = (T)op->shape->Dc[q];
+      }
+    for (int q = 0; q < N1; ++q) a.sh.w[q] = (T)op->shape->wq[q];
+    for (int d = 0; d < 3; ++d)
+      {
+        a.n[d]  = m->n[d];
+        a.np[d] = op->np[d];
+        a.h[d]  = (T)((m->upper[d] - m->lower[d]) / m->n[d]);
+      }
+    a.n_cells = m->n_cells;
+    a.nb_src  = nb_src;
+    a.nb_dst  = nb_dst;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
+      {
+        a.src[b] = b < nb_src ? (const T *)src[b] : nullptr;
+        a.dst[b] = b < nb_dst ? (T *)dst[b] : nullptr;
+      }
+    a.alpha      = (const T *)alpha;
+    a.beta       = (const T *)beta;
+    a.geom_mode  = m->cartesian ? 0 : 1;
+    a.metric     = (const T *)op->d_metric;
+    a.coeff_cell = (const T *)op->d_coeff;
+    a.dirichlet  = m->dirichlet;
+    a.nbmax      = nb_src > nb_dst ? nb_src : nb_dst;
+    constexpr int NP = (DIM == 3) ? N1 * N1 : N1;
+    constexpr int NC = (DIM == 3) ? N1 * N1 * N1 : N1 * N1;
+    int           cpc = 192 / (NP * a.nbmax);
+    if (cpc < 1) cpc = 1;
+    size_t per_slot = (size_t)(DIM + 2) * a.nbmax * NC * sizeof(T);
+    while (cpc > 1 && cpc * per_slot > 96 * 1024) --cpc;
+    a.cells_per_cta = cpc;
+    const size_t smem    = cpc * per_slot + 2 * (size_t)nb_src * nb_dst * sizeof(T);
+    const int    threads = cpc * NP * a.nbmax;
+    STFEM_REQUIRE(threads <= 1024, "st_vmult: %d threads per CTA exceed 1024 (degree %d, %d blocks)", threads,
+                  N1 - 1, a.nbmax);
+    STFEM_REQUIRE(smem <= 227 * 1024, "st_vmult: %zu bytes of shared memory exceed 227 KB", smem);
+    auto kern = st_vmult_generic_kernel<DIM, N1, T>;
+    if (smem > 48 * 1024)
+      STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (m->n_cells + cpc - 1) / cpc;
+    kern<<<(unsigned)grid, threads, smem, m->ctx->stream>>>(a);
+    m->ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
+  template <int DIM, typename T>
+  static int dispatch_degree(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst,
+                             const void *alpha, const void *beta)
+  {
+    switch (op->degree)
+      {
+        case 1: return launch_generic<DIM, 2, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
+        case 2: return launch_generic<DIM, 3, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
+        case 3: return launch_generic<DIM, 4, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
+        case 4: return launch_generic<DIM, 5, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
+        case 5: return launch_generic<DIM, 6, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
+        case 6: return launch_generic<DIM, 7, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
+        default: set_error("st_vmult: degree %d unsupported (1..6)", op->degree); return STFEM_ERR_UNSUPPORTED;
+      }
+  }
+
+  int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
+               const void *beta, bool zero_dst)
+  {
+    stfem_ctx *ctx = op->mesh->ctx;
+    STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (op->timing) STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const size_t bytes = (size_t)op->N * (op->number_type == STFEM_F64 ? 8 : 4);
+    if (zero_dst)
+      for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(dst[b], 0, bytes, ctx->stream));
+    int rc;
+    if (op->mesh->dim == 2)
+      rc = op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, dst, src, nb_src, nb_dst, alpha, beta) :
+                                          dispatch_degree<2, float>(op, dst, src, nb_src, nb_dst, alpha, beta);
+    else
+      rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, dst, src, nb_src, nb_dst, alpha, beta) :
+                                          dispatch_degree<3, float>(op, dst, src, nb_src, nb_dst, alpha, beta);
+    if (rc != STFEM_OK) return rc;
+    if (op->timing)
+      {
+        STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+        STFEM_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+        STFEM_CUDA_CHECK(cudaEventElapsedTime(&op->last_ms, ctx->ev0, ctx->ev1));
+      }
+    return STFEM_OK;
+  }
+
+  template <typename T>
+  static int upload_matrix(stfem_ctx *ctx, const std::vector<double> &M, void **d)
+  {
+    std::vector<T> tmp(M.begin(), M.end());
+    STFEM_CUDA_CHECK(cudaMalloc(d, tmp.size() * sizeof(T) + 16));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(*d, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return STFEM_OK;
+  }
+} // namespace stfem
+
+using namespace stfem;
+
+extern "C" {
+
+int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *out)
+{
+  STFEM_REQUIRE(mesh && desc && out, "stfem_op_create: null argument");
+  STFEM_REQUIRE(desc->degree >= 1 && desc->degree <= 6, "stfem_op_create: degree %d not in 1..6", desc->degree);
+  STFEM_REQUIRE(desc->number_type == STFEM_F64 || desc->number_type == STFEM_F32, "stfem_op_create: bad number_type");
+  STFEM_REQUIRE(desc->nb_rows >= 1 && desc->nb_rows <= STFEM_MAX_BLOCKS && desc->nb_cols >= 1 &&
+                  desc->nb_cols <= STFEM_MAX_BLOCKS,
+                "stfem_op_create: block counts %d x %d not in 1..%d", desc->nb_rows, desc->nb_cols, STFEM_MAX_BLOCKS);
+  STFEM_REQUIRE(desc->Alpha && desc->Beta, "stfem_op_create: Alpha/Beta null");
+  stfem_ctx *ctx = mesh->ctx;
+  STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
+  auto op         = std::make_unique<stfem_op>();
+  op->mesh        = mesh;
+  op->degree      = desc->degree;
+  op->number_type = desc->number_type;
+  op->nb_rows     = desc->nb_rows;
+  op->nb_cols     = desc->nb_cols;
+  op->variant     = desc->kernel_variant;
+  op->shape       = std::make_unique<ShapeHost>(desc->degree);
+  op->N           = 1;
+  for (int d = 0; d < 3; ++d)
+    {
+      op->np[d] = d < mesh->dim ? desc->degree * mesh->n[d] + 1 : 1;
+      op->N *= op->np[d];
+    }
+  const int nr = desc->nb_rows, nc = desc->nb_cols;
+  op->Alpha.assign(desc->Alpha, desc->Alpha + nr * nc);
+  op->Beta.assign(desc->Beta, desc->Beta + nr * nc);
+  std::vector<double> AT(nr * nc), BT(nr * nc);
+  for (int i = 0; i < nr; ++i)
+    for (int j = 0; j < nc; ++j)
+      {
+        AT[j * nr + i] = op->Alpha[i * nc + j];
+        BT[j * nr + i] = op->Beta[i * nc + j];
+      }
+  const bool f64 = desc->number_type == STFEM_F64;
+  if (f64)
+    {
+      STFEM_FORWARD(upload_matrix<double>(ctx, op->Alpha, &op->d_alpha));
+      STFEM_FORWARD(upload_matrix<double>(ctx, op->Beta, &op->d_beta));
+      STFEM_FORWARD(upload_matrix<double>(ctx, AT, &op->d_alphaT));
+      STFEM_FORWARD(upload_matrix<double>(ctx, BT, &op->d_betaT));
+    }
+  else
+    {
+      STFEM_FORWARD(upload_matrix<float>(ctx, op->Alpha, &op->d_alpha));
+      STFEM_FORWARD(upload_matrix<float>(ctx, op->Beta, &op->d_beta));
+      STFEM_FORWARD(upload_matrix<float>(ctx, AT, &op->d_alphaT));
+      STFEM_FORWARD(upload_matrix<float>(ctx, BT, &op->d_betaT));
+    }
+  if (desc->laplace_coeff_cell)
+    {
+      std::vector<double> c(desc->laplace_coeff_cell, desc->laplace_coeff_cell + mesh->n_cells);
+      if (f64)
+        STFEM_FORWARD(upload_matrix<double>(ctx, c, &op->d_coeff));
+      else
+        STFEM_FORWARD(upload_matrix<float>(ctx, c, &op->d_coeff));
+    }
+  if (!mesh->cartesian)
+    {
+      const int       n1   = op->degree + 1;
+      const int       nq   = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
+      const int       nsym = mesh->dim * (mesh->dim + 1) / 2;
+      const long long tot  = mesh->n_cells * nq;
+      const size_t    bytes = (size_t)tot * (nsym + 1) * (f64 ? 8 : 4);
+      STFEM_CUDA_CHECK(cudaMalloc(&op->d_metric, bytes));
+      double *d_xq = nullptr, *d_wq = nullptr;
+      STFEM_CUDA_CHECK(cudaMalloc(&d_xq, n1 * sizeof(double)));
+      STFEM_CUDA_CHECK(cudaMalloc(&d_wq, n1 * sizeof(double)));
+      STFEM_CUDA_CHECK(cudaMemcpyAsync(d_xq, op->shape->xq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      STFEM_CUDA_CHECK(cudaMemcpyAsync(d_wq, op->shape->wq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      const int       threads = 256;
+      const long long blocks  = (tot + threads - 1) / threads;
+      if (mesh->dim == 2)
+        {
+          if (f64)
+            metric_kernel<2, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, (double *)op->d_metric);
+          else
+            metric_kernel<2, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, (float *)op->d_metric);
+        }
+      else
+        {
+          if (f64)
+            metric_kernel<3, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, (double *)op->d_metric);
+          else
+            metric_kernel<3, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, (float *)op->d_metric);
+        }
+      ctx->launches++;
+      STFEM_CUDA_CHECK(cudaGetLastError());
+      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(d_xq);
+      cudaFree(d_wq);
+    }
+  *out = op.release();
+  return STFEM_OK;
+}
+
+int stfem_op_destroy(stfem_op_t op)
+{
+  if (!op) return STFEM_OK;
+  cudaSetDevice(op->mesh->ctx->device);
+  cudaStreamSynchronize(op->mesh->ctx->stream);
+  for (void *p : {op->d_alpha, op->d_beta, op->d_alphaT, op->d_betaT, op->d_metric, op->d_coeff})
+    if (p) cudaFree(p);
+  for (void *p : op->d_scratch)
+    if (p) cudaFree(p);
+  delete op;
+  return STFEM_OK;
+}
+
+long long stfem_op_n_dofs_per_block(stfem_op_t op) { return op ? op->N : 0; }
+int stfem_op_n_blocks(stfem_op_t op) { return op ? op->nb_rows : 0; }
+
+int stfem_op_vmult(stfem_op_t op, void *const *dst, const void *const *src, int transpose)
+{
+  STFEM_REQUIRE(op && dst && src, "stfem_op_vmult: null argument");
+  STFEM_REQUIRE(op->nb_rows == op->nb_cols, "stfem_op_vmult: operator is %d x %d blocks, not square (use vmult_slice_add)",
+                op->nb_rows, op->nb_cols);
+  for (int b = 0; b < op->nb_rows; ++b)
+    STFEM_REQUIRE(dst[b] && src[b] && dst[b] != src[b], "stfem_op_vmult: block %d null or aliased", b);
+  return op_apply(op, dst, src, op->nb_cols, op->nb_rows, transpose ? op->d_alphaT : op->d_alpha,
+                  transpose ? op->d_betaT : op->d_beta, true);
+}
+
+int stfem_op_vmult_slice_add(stfem_op_t op, void *const *dst, const void *src0)
+{
+  STFEM_REQUIRE(op && dst && src0, "stfem_op_vmult_slice_add: null argument");
+  STFEM_REQUIRE(op->nb_cols == 1, "stfem_op_vmult_slice_add: operator has %d block columns, expected 1", op->nb_cols);
+  const void *src[1] = {src0};
+  return op_apply(op, dst, src, 1, op->nb_rows, op->d_alpha, op->d_beta, false);
+}
+
+int stfem_op_diagonal(stfem_op_t, void *const *)
+{
+  set_error("stfem_op_diagonal: not implemented yet");
+  return STFEM_ERR_UNSUPPORTED;
+}
+
+int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const *src_host, int transpose)
+{
+  STFEM_REQUIRE(op && dst_host && src_host, "stfem_op_vmult_host: null argument");
+  STFEM_REQUIRE(op->nb_rows == op->nb_cols, "stfem_op_vmult_host: operator not square");
+  stfem_ctx   *ctx   = op->mesh->ctx;
+  const int    nb    = op->nb_rows;
+  const size_t bytes = (size_t)op->N * (op->number_type == STFEM_F64 ? 8 : 4);
+  STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (op->d_scratch.size() < (size_t)2 * nb)
+    {
+      for (void *p : op->d_scratch) cudaFree(p);
+      op->d_scratch.assign(2 * nb, nullptr);
+      for (auto &p : op->d_scratch) STFEM_CUDA_CHECK(cudaMalloc(&p, bytes));
+    }
+  std::vector<void *>       d(nb);
+  std::vector<const void *> s(nb);
+  for (int b = 0; b < nb; ++b)
+    {
+      d[b] = op->d_scratch[b];
+      s[b] = op->d_scratch[nb + b];
+      STFEM_CUDA_CHECK(cudaMemcpyAsync(op->d_scratch[nb + b], src_host[b], bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  STFEM_FORWARD(stfem_op_vmult(op, d.data(), s.data(), transpose));
+  for (int b = 0; b < nb; ++b)
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(dst_host[b], d[b], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return STFEM_OK;
+}
+
+int stfem_op_set_timing(stfem_op_t op, int enable)
+{
+  STFEM_REQUIRE(op, "null op");
+  op->timing = enable != 0;
+  return STFEM_OK;
+}
+
+float stfem_op_last_kernel_ms(stfem_op_t op) { return op ? op->last_ms : -1.f; }
+
+} // extern "C"

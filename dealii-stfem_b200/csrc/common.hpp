@@ -1,0 +1,72 @@
+// Shared host-side plumbing of the C ABI: error reporting, context, mesh, operator objects.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/stfem_b200.h"
+
+namespace stfem
+{
+  void        set_error(const char *fmt, ...);
+  const char *get_error();
+
+#define STFEM_CUDA_CHECK(expr)                                                                   \
+  do                                                                                             \
+    {                                                                                            \
+      cudaError_t err__ = (expr);                                                                \
+      if (err__ != cudaSuccess)                                                                  \
+        {                                                                                        \
+          stfem::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                    \
+                           cudaGetErrorString(err__));                                           \
+          return STFEM_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    }                                                                                            \
+  while (0)
+
+#define STFEM_REQUIRE(cond, ...)                                                                 \
+  do                                                                                             \
+    {                                                                                            \
+      if (!(cond))                                                                               \
+        {                                                                                        \
+          stfem::set_error(__VA_ARGS__);                                                         \
+          return STFEM_ERR_INVALID;                                                              \
+        }                                                                                        \
+    }                                                                                            \
+  while (0)
+
+#define STFEM_FORWARD(expr)                                                                      \
+  do                                                                                             \
+    {                                                                                            \
+      int rc__ = (expr);                                                                         \
+      if (rc__ != STFEM_OK) return rc__;                                                         \
+    }                                                                                            \
+  while (0)
+} // namespace stfem
+
+struct stfem_ctx
+{
+  int          device  = 0;
+  cudaStream_t stream  = nullptr;
+  long long    launches = 0;
+  int          sm_count = 0;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+};
+
+struct stfem_mesh
+{
+  stfem_ctx *ctx = nullptr;
+  int        dim = 0;
+  int        n[3] = {1, 1, 1};
+  double     lower[3] = {0, 0, 0}, upper[3] = {1, 1, 1};
+  long long  n_cells = 0;
+  bool       cartesian = true;
+  double    *d_vertices = nullptr; // device, (n+1)^dim * dim doubles, or null
+  std::vector<double> h_vertices;
+  unsigned   dirichlet = 0;
+};

@@ -1,0 +1,27 @@
+// The operator object behind stfem_op_t.
+#pragma once
+#include "basis_host.hpp"
+#include "common.hpp"
+
+struct stfem_op
+{
+  stfem_mesh *mesh = nullptr;
+  int         degree = 1, number_type = STFEM_F64, nb_rows = 1, nb_cols = 1, variant = 0;
+  int         np[3] = {1, 1, 1};
+  long long   N = 0; // spatial dofs per block
+  std::unique_ptr<stfem::ShapeHost> shape;
+  std::vector<double> Alpha, Beta; // host copies, row-major nb_rows x nb_cols
+  void *d_alpha = nullptr, *d_beta = nullptr, *d_alphaT = nullptr, *d_betaT = nullptr;
+  void *d_metric = nullptr; // general geometry: per cell, per q-point metric (+JxW)
+  void *d_coeff = nullptr;  // per-cell Laplace coefficient
+  std::vector<void *> d_scratch; // device staging for the host-buffer entry points
+  bool  timing = false;
+  float last_ms = 0.f;
+};
+
+namespace stfem
+{
+  // dst (+)= A src with explicit time matrices (device pointers in the operator's number type)
+  int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
+               const void *beta, bool zero_dst);
+} // namespace stfem

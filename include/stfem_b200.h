@@ -1,0 +1,118 @@
+/* stfem_b200.h — C ABI of the B200-native space-time FEM hot path.
+ *
+ * The reference (immaaane/dealii-stfem) has no FFI: its boundary is the duck-typed C++
+ * concept deal.II's solvers instantiate.  This header is the thin C layer
+ * under the C++ façade (dealii-stfem_b200/include/stfem/*.h) that mirrors those classes;
+ * every entry point names the reference interface it replaces.
+ *
+ * Conventions: opaque handles, int return codes (0 = STFEM_OK), no exceptions cross the
+ * boundary, stfem_last_error() gives the message of the last failing call on this thread.
+ * Block vectors keep the reference layout (include/types.h:20-23 of the reference): nb
+ * separate contiguous arrays of N spatial DoFs, lexicographic DoF numbering of the
+ * structured hex mesh (x fastest).  `number_type`: 0 = double, 1 = float.
+ * Device pointers are plain `void *` / `double *`; no torch types anywhere.
+ */
+#ifndef STFEM_B200_H
+#define STFEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STFEM_OK 0
+#define STFEM_ERR_INVALID 1
+#define STFEM_ERR_CUDA 2
+#define STFEM_ERR_UNSUPPORTED 3
+#define STFEM_ERR_NO_CONVERGENCE 4
+
+#define STFEM_F64 0
+#define STFEM_F32 1
+
+#define STFEM_MAX_BLOCKS 16
+
+typedef struct stfem_ctx *stfem_ctx_t;
+typedef struct stfem_mesh *stfem_mesh_t;
+typedef struct stfem_op *stfem_op_t;
+
+const char *stfem_last_error(void);
+const char *stfem_version(void);
+
+/* ---- context: one per GPU / per rank (reference: one MPI rank, operators.h:28-40) ---- */
+int stfem_ctx_create(int device, stfem_ctx_t *out);
+int stfem_ctx_destroy(stfem_ctx_t ctx);
+int stfem_ctx_synchronize(stfem_ctx_t ctx);
+/* the cudaStream_t all work of this context is enqueued on (as void*) */
+void *stfem_ctx_stream(stfem_ctx_t ctx);
+/* number of kernels this library launched on the context so far (bench "gpu_launches") */
+long long stfem_ctx_launch_count(stfem_ctx_t ctx);
+
+/* ---- device memory helpers (plain cudaMalloc/cudaMemcpyAsync on the context stream) ---- */
+int stfem_dev_alloc(stfem_ctx_t ctx, size_t bytes, void **out);
+int stfem_dev_free(stfem_ctx_t ctx, void *p);
+int stfem_dev_upload(stfem_ctx_t ctx, void *dst_dev, const void *src_host, size_t bytes);
+int stfem_dev_download(stfem_ctx_t ctx, void *dst_host, const void *src_dev, size_t bytes);
+int stfem_dev_memset(stfem_ctx_t ctx, void *dst_dev, int value, size_t bytes);
+int stfem_host_alloc_pinned(size_t bytes, void **out);
+int stfem_host_free_pinned(void *p);
+
+/* ---- mesh: GridGenerator::subdivided_hyper_rectangle + refine_global (+ distort_random),
+ *      reference tests/tp_01.cc:83-90.  n_cells[d] cells per direction after refinement.
+ *      vertices: NULL for a Cartesian box, else (n_cells[0]+1)*(n_cells[1]+1)*... points of
+ *      `dim` doubles, lexicographic (x fastest) — MappingQ1 geometry.
+ *      dirichlet_faces: bit (2*d+side) set = homogeneous Dirichlet on that face
+ *      (DoFTools::make_zero_boundary_constraints, tp_01.cc:99); 0x3f / 0xf = all faces. ---- */
+int stfem_mesh_create(stfem_ctx_t ctx, int dim, const int *n_cells, const double *lower,
+                      const double *upper, const double *vertices, unsigned dirichlet_faces,
+                      stfem_mesh_t *out);
+int stfem_mesh_destroy(stfem_mesh_t mesh);
+
+/* ---- space-time operator  A = Alpha (x) K + Beta (x) M
+ *      replaces SystemMatrix<dim,Number,MatrixFreeOperatorScalar> (reference
+ *      include/operators.h:516-663) together with its two MatrixFreeOperator members
+ *      K (laplace_scaling=1) and M (mass_scaling=1) (operators.h:967-1191, tp_01.cc:114-119).
+ *      Alpha, Beta: row-major nb_rows x nb_cols doubles (FullMatrix layout).  nb_cols == nb_rows
+ *      for the system matrix; nb_cols == 1 for the "slice" right-hand-side matrices
+ *      (operators.h:586-611).  laplace_coeff_cell: NULL or one coefficient per cell
+ *      (Coefficient<dim>, operators.h:870-965, is piecewise constant per coarse cell). ---- */
+typedef struct stfem_op_desc {
+  int degree;      /* FE_Q(degree) in space, QGauss(degree+1) */
+  int number_type; /* STFEM_F64 | STFEM_F32 */
+  int nb_rows;
+  int nb_cols;
+  const double *Alpha;
+  const double *Beta;
+  const double *laplace_coeff_cell; /* host pointer, n_cells values, may be NULL */
+  int kernel_variant;               /* 0 = default; >0 selects an implementation (tuning/tests) */
+} stfem_op_desc;
+
+int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *out);
+int stfem_op_destroy(stfem_op_t op);
+/* m(): operators.h:642-646 */
+long long stfem_op_n_dofs_per_block(stfem_op_t op);
+int stfem_op_n_blocks(stfem_op_t op);
+
+/* vmult / Tvmult (operators.h:536-583): dst = A src (transpose != 0: Alpha^T, Beta^T).
+ * dst, src: arrays of nb device pointers.  Constrained rows of dst are 0 (App. A.3). */
+int stfem_op_vmult(stfem_op_t op, void *const *dst, const void *const *src, int transpose);
+/* vmult_slice_add (operators.h:586-611): dst_j += Alpha(j,0) K src0 + Beta(j,0) M src0 */
+int stfem_op_vmult_slice_add(stfem_op_t op, void *const *dst, const void *src0);
+/* get_matrix_diagonal (operators.h:613-625): diag_i = Alpha(i,i) diag K + Beta(i,i) diag M */
+int stfem_op_diagonal(stfem_op_t op, void *const *diag);
+
+/* Same call with HOST buffers (nb arrays of N numbers of the operator's number type):
+ * copies src to the device, applies, copies dst back — the end-to-end path bench.py times. */
+int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const *src_host,
+                        int transpose);
+
+/* time of the last vmult kernel sequence on this operator, measured with CUDA events on the
+ * context stream (ms); enabled with stfem_op_set_timing(op, 1) */
+int stfem_op_set_timing(stfem_op_t op, int enable);
+float stfem_op_last_kernel_ms(stfem_op_t op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STFEM_B200_H */

@@ -1,0 +1,155 @@
+"""Parity of the CUDA space-time operator (through the C ABI) with the CPU oracle.
+
+Tolerances (BASELINE.json north_star): relative 1e-12 in FP64, 1e-5 in FP32 (multigrid levels).
+The oracle applies the reference's UNFUSED algorithm (operators.h:536-559); the kernel is fused.
+"""
+import numpy as np
+import pytest
+
+from oracle import fe_time as ft
+from oracle import spatial as S
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-12, 1: 1e-5}
+
+
+def _setup(dim, k, ref, distort, subdivisions=None, lower=None, upper=None):
+    sub = subdivisions or [1] * dim
+    mesh = S.Mesh(dim, sub, ref, lower=lower, upper=upper, distort=distort)
+    space = S.Space(mesh, k)
+    return mesh, space
+
+
+def _time_matrices(ttype, r, nts, tau=0.05):
+    w = ft.get_fe_time_weights(ttype, r, tau, nts)
+    return w[0], w[1], w[2], w[3]
+
+
+def _rand_block(nb, n, seed=42):
+    return np.stack([np.random.RandomState(seed + b).uniform(-1, 1, n) for b in range(nb)])
+
+
+def _gpu_op(ctx, mesh, k, A, B, number_type=0, coeff=None, variant=0):
+    import dealii_stfem_b200 as st
+    gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper,
+                 vertices=None if mesh.cartesian else mesh.vertices.reshape(-1, mesh.dim))
+    return gm, st.Operator(gm, k, A, B, number_type=number_type, laplace_coeff_cell=coeff, variant=variant)
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+CASES = [
+    # dim, k, ref, distort, ttype, r, nts
+    (2, 1, 2, 0.0, "DG", 0, 1),
+    (2, 2, 3, 0.0, "DG", 1, 1),      # config 1 family (Q2 x DG(1))
+    (2, 2, 2, 0.0, "DG", 1, 2),
+    (2, 3, 2, 0.15, "CGP", 2, 1),
+    (2, 5, 1, 0.1, "CGP", 4, 2),
+    (2, 6, 1, 0.0, "DG", 2, 1),
+    (3, 1, 2, 0.0, "DG", 1, 1),
+    (3, 2, 1, 0.2, "DG", 1, 1),
+    (3, 3, 1, 0.15, "DG", 2, 1),     # config 4 family (Q3 x DG(2), perturbed)
+    (3, 4, 1, 0.0, "CGP", 2, 1),     # config 2 family (Q4 x cG(2))
+    (3, 4, 1, 0.1, "DG", 1, 1),      # config 5 family (Q4 x DG(1))
+    (3, 3, 1, 0.0, "DG", 3, 4),      # 16 blocks (tf05-style, 4 steps at once)
+    (3, 5, 0, 0.1, "DG", 0, 1),
+]
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "d%d_k%d_r%d_p%g_%s%d_x%d" % c)
+def test_vmult_matches_oracle(ctx, case, number_type):
+    dim, k, ref, distort, ttype, r, nts = case
+    mesh, space = _setup(dim, k, ref, distort)
+    A, B, _, _ = _time_matrices(ttype, r, nts)
+    nb = A.shape[0]
+    dt = np.float64 if number_type == 0 else np.float32
+    K = S.MatrixFreeOperator(space, 0.0, 1.0)
+    M = S.MatrixFreeOperator(space, 1.0, 0.0)
+    sysm = S.SystemMatrix(K, M, A, B)
+    src = _rand_block(nb, space.n_dofs).astype(dt)
+    ref_dst = sysm.vmult(src.astype(np.float64))
+    gm, op = _gpu_op(ctx, mesh, k, A, B, number_type)
+    d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+    op.vmult(d_dst, d_src)
+    out = d_dst.download()
+    assert out.dtype == dt
+    assert _rel(out.astype(np.float64), ref_dst) < TOL[number_type]
+    # constrained rows are exactly zero
+    assert np.all(out[:, space.constrained] == 0)
+    # Tvmult
+    ref_t = sysm.Tvmult(src.astype(np.float64))
+    op.Tvmult(d_dst, d_src)
+    assert _rel(d_dst.download().astype(np.float64), ref_t) < TOL[number_type]
+    for v in (d_src, d_dst):
+        v.free()
+    op.close()
+    gm.close()
+
+
+@pytest.mark.parametrize("dim,k", [(2, 2), (3, 3)])
+def test_vmult_slice_add(ctx, dim, k):
+    mesh, space = _setup(dim, k, 1, 0.1)
+    _, _, G, Z = _time_matrices("CGP", 3, 1)
+    K = S.MatrixFreeOperator(space, 0.0, 1.0)
+    M = S.MatrixFreeOperator(space, 1.0, 0.0)
+    sysm = S.SystemMatrix(K, M, G, Z)
+    nb = G.shape[0]
+    src0 = _rand_block(1, space.n_dofs, seed=7)
+    dst0 = _rand_block(nb, space.n_dofs, seed=9)
+    dst0[:, space.constrained] = 0
+    ref_dst = sysm.vmult_slice_add(dst0.copy(), src0[0])
+    gm, op = _gpu_op(ctx, mesh, k, G, Z)
+    d_src = op.new_vector(1).upload(src0)
+    d_dst = op.new_vector(nb).upload(dst0)
+    op.vmult_slice_add(d_dst, d_src)
+    assert _rel(d_dst.download(), ref_dst) < 1e-12
+    d_src.free(); d_dst.free(); op.close(); gm.close()
+
+
+def test_heterogeneous_coefficient_perturbed_mesh(ctx):
+    """Config 4: [-1,1]^3, subdivisions 5, Coefficient<dim> on K only (tp_01.cc:118-119)."""
+    dim, k = 3, 3
+    mesh, space = _setup(dim, k, 0, 0.15, subdivisions=[5, 5, 5], lower=[-1, -1, -1], upper=[1, 1, 1])
+    coef = S.Coefficient(dim, [5, 5, 5], [-1, -1, -1], [1, 1, 1], distort_coeff=0.6)
+    A, B, _, _ = _time_matrices("DG", 2, 1)
+    K = S.MatrixFreeOperator(space, 0.0, 1.0)
+    K.evaluate_coefficient(coef)
+    M = S.MatrixFreeOperator(space, 1.0, 0.0)
+    # piecewise constant per cell on this mesh: one value per cell is the whole table
+    cc = K.laplace_coeff
+    assert np.all(cc == cc[:, :1])
+    sysm = S.SystemMatrix(K, M, A, B)
+    src = _rand_block(3, space.n_dofs)
+    ref_dst = sysm.vmult(src)
+    gm, op = _gpu_op(ctx, mesh, k, A, B, coeff=cc[:, 0])
+    d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+    op.vmult(d_dst, d_src)
+    assert _rel(d_dst.download(), ref_dst) < 1e-12
+    d_src.free(); d_dst.free(); op.close(); gm.close()
+
+
+def test_linearity_and_symmetry_large(ctx):
+    """Size-independent properties at a size the oracle does not reach: A(ax+by) = aAx + bAy and
+    <Ax, y> = <x, A^T y> on a 48^3 Q4 mesh (1.4e7 space-time DoFs)."""
+    import dealii_stfem_b200 as st
+    A, B, _, _ = _time_matrices("CGP", 2, 1)
+    gm = st.Mesh(ctx, [48, 48, 48])
+    op = st.Operator(gm, 4, A, B)
+    n, nb = op.n, 2
+    x, y = _rand_block(nb, n, 1), _rand_block(nb, n, 5)
+    dx, dy, dz, dr = (op.new_vector() for _ in range(4))
+    dx.upload(x); dy.upload(y); dz.upload(2.0 * x - 3.0 * y)
+    op.vmult(dr, dx); Ax = dr.download()
+    op.vmult(dr, dy); Ay = dr.download()
+    op.vmult(dr, dz); Az = dr.download()
+    assert _rel(Az, 2.0 * Ax - 3.0 * Ay) < 1e-12
+    op.Tvmult(dr, dy); ATy = dr.download()
+    lhs, rhs = np.vdot(Ax, y), np.vdot(x, ATy)   # y, x include boundary entries: rows/cols are zero there
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), np.linalg.norm(Ax) * np.linalg.norm(y) * 1e-3)
+    for v in (dx, dy, dz, dr):
+        v.free()
+    op.close(); gm.close()
