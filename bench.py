@@ -1,0 +1,263 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the space-time operator hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one application of the fused space-time operator  dst = (Alpha (x) K + Beta (x) M) src
+(reference SystemMatrix::vmult, include/operators.h:536-559) over the whole block vector.
+Workload at N=1 = BASELINE.json configs[1]: 3D heat, Q4 space x cG(2) time, 96^3 cells
+(subdivisions 3, refinement 5), 385^3 spatial DoFs x 2 time blocks = 1.14e8 space-time DoFs, FP64.
+For N>1 every rank owns one such brick (weak scaling, box partition of the mesh).
+
+Prints ONE JSON line (rank 0).  `value` = space-time DoFs/s with inputs resident in HBM (CUDA events on
+the library's stream, max over ranks); `e2e` = the same metric through the C-ABI entry point with
+pinned HOST buffers (H2D + kernel + D2H inside the timed region); `roofline`, `cpu_baseline`,
+`clocks`, `gpu_launches` as the contract asks.  torch is used for torch.distributed plumbing only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "space-time DoFs/s, operator vmult (3D heat, Q4 x cG(2), FP64)"
+UNIT = "DoFs/s"
+DEGREE, TTYPE, TDEG = 4, "CGP", 2
+N_CELLS_FULL = 96            # per direction: subdivisions 3, refinement 5
+CPU_SAMPLE_CELLS = 48        # bounded CPU sample of the same workload (1/8 of the cells)
+BYTES_PER_DOF = 16           # FP64: read src once + write dst once
+
+
+def time_weights():
+    """Alpha, Beta of cG(2) for tau = 2^-6 (tests/tp_01.cc:106-109 with refinement 5)."""
+    from dealii_stfem_b200 import fe_time_host
+    return fe_time_host.get_fe_time_weights(TTYPE, TDEG, 2.0 ** -6, 1)[:2]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md 'clocks' recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(n_cells, steps, warmup):
+    """The reference's CPU algorithm (unfused 2*nb cell loops + axpys, operators.h:536-559) through
+    oracle/cpu_ref.cpp on all host threads.  Returns (DoFs/s, ms per step, threads)."""
+    from oracle import cpu_ref, fe_time as oft, spatial as osp
+    A, B = oft.get_fe_time_weights(TTYPE, TDEG, 2.0 ** -6, 1)[:2]
+    mesh = osp.Mesh(3, [n_cells] * 3, 0)
+    space = osp.Space(mesh, DEGREE)
+    nb = A.shape[0]
+    src = np.sin(0.1 * np.arange(space.n_dofs)[None, :] + np.arange(nb)[:, None])
+    threads = cpu_ref.max_threads()
+    for _ in range(warmup):
+        cpu_ref.system_vmult(space, A, B, src)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_ref.system_vmult(space, A, B, src)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return nb * space.n_dofs / dt, dt * 1e3, threads, nb * space.n_dofs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=N_CELLS_FULL, help="cells per direction per GPU (default 96)")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, ms, threads, ndofs = cpu_reference_run(CPU_SAMPLE_CELLS, args.steps, args.warmup)
+        sample = "%d^3-cell Q4 x cG(2) brick (%.3g space-time DoFs) per step, all host threads" % (CPU_SAMPLE_CELLS, ndofs)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "3D heat Q4 x cG(2) operator vmult; CPU arm runs the reference's unfused "
+                                       "algorithm (oracle/cpu_ref.cpp, the reference needs deal.II and cannot be built)",
+                           "sample": sample},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    import dealii_stfem_b200 as st
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = st.Context(dev)
+    A, B = time_weights()
+    n = args.cells
+    mesh = st.Mesh(ctx, [n, n, n])
+    op = st.Operator(mesh, DEGREE, A, B, number_type=st.F64, variant=args.variant)
+    nb = op.nb_rows
+    dofs_rank = op.n * nb
+    x, y = op.new_vector(), op.new_vector()
+    hx, px = st.capi.pinned_array((nb, op.n), np.float64)
+    hy, py = st.capi.pinned_array((nb, op.n), np.float64)
+    hx[:] = np.sin(0.1 * np.arange(op.n)[None, :] + np.arange(nb)[:, None])      # SURVEY §8d synthetic input
+    x.upload(hx)
+
+    # device-resident timing
+    for _ in range(warmup):
+        op.vmult(y, x)
+    barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    launches0 = ctx.launches
+    ctx.timer_start()
+    for _ in range(args.steps):
+        op.vmult(y, x)
+    ms_total = ctx.timer_stop()
+    launches = ctx.launches - launches0
+    barrier()
+    clocks = sampler.stop()
+    # kernel-only duration (CUDA events around each launch, same stream), for the roofline
+    op.set_timing(True)
+    kms = []
+    for _ in range(min(args.steps, 10)):
+        op.vmult(y, x)
+        kms.append(op.last_kernel_ms())
+    op.set_timing(False)
+    kernel_ms = float(np.mean(kms))
+
+    # end-to-end through the host-buffer entry point
+    e2e_steps = max(3, min(args.steps, 5))
+    op.vmult_host(hy, hx)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        op.vmult_host(hy, hx)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    checksum = float(np.abs(hy).sum())
+
+    t = torch.tensor([ms_total, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kernel_ms = (float(v) for v in t.tolist())
+    ms_step = ms_total / args.steps
+    total_dofs = dofs_rank * world
+    value = total_dofs / (ms_step * 1e-3)
+    peak, peak_src = measured_peak()
+    achieved = dofs_rank * BYTES_PER_DOF / (kernel_ms * 1e-3) / 1e9
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: 3D heat, Q4 x cG(2), %d^3 cells per GPU, %d spatial DoFs x %d time blocks "
+                                   "= %.4g space-time DoFs per GPU; one step = one fused operator vmult" % (n, op.n, nb, dofs_rank),
+                       "l2": "inputs+outputs %.0f MB per step, larger than the 126 MB L2" % (2 * dofs_rank * 8 / 1e6),
+                       "parallelism": "box partition, %d independent brick(s); halo exchange not in this timing" % world,
+                       "kernel_variant": args.variant, "checksum": checksum},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "note": "algorithmic bytes = 16 B per space-time DoF; FP64 st_vmult is FP64-pipe bound "
+                                 "(~150 DFMA per DoF), see DESIGN.md"},
+            "e2e": {"value": total_dofs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(dofs_rank * 8), "d2h_bytes_per_step": int(dofs_rank * 8)},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, ms, threads, ndofs = cpu_reference_run(CPU_SAMPLE_CELLS, 3, 1)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d^3-cell brick of the same workload (%.3g space-time DoFs), 3 applications "
+                                          "of the reference's unfused algorithm (oracle/cpu_ref.cpp)" % (CPU_SAMPLE_CELLS, ndofs)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for v in (x, y):
+        v.free()
+    st.capi.free_pinned(px)
+    st.capi.free_pinned(py)
+    op.close()
+    mesh.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

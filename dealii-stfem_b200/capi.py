@@ -23,13 +23,14 @@ class StfemError(RuntimeError):
 class OpDesc(C.Structure):
     _fields_ = [("degree", C.c_int), ("number_type", C.c_int), ("nb_rows", C.c_int), ("nb_cols", C.c_int),
                 ("Alpha", C.POINTER(C.c_double)), ("Beta", C.POINTER(C.c_double)),
-                ("laplace_coeff_cell", C.POINTER(C.c_double)), ("kernel_variant", C.c_int)]
+                ("laplace_coeff_cell", C.POINTER(C.c_double)), ("laplace_coeff_q", C.POINTER(C.c_double)),
+                ("kernel_variant", C.c_int)]
 
 
 _lib = None
 
 # every symbol include/stfem_b200.h declares: (restype, argtypes)
-_vp, _vpp = C.c_void_p, C.POINTER(C.c_void_p)
+_vp, _vpp, _dp = C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double)
 SYMBOLS = {
     "stfem_last_error": (C.c_char_p, []),
     "stfem_version": (C.c_char_p, []),
@@ -38,6 +39,8 @@ SYMBOLS = {
     "stfem_ctx_synchronize": (C.c_int, [_vp]),
     "stfem_ctx_stream": (_vp, [_vp]),
     "stfem_ctx_launch_count": (C.c_longlong, [_vp]),
+    "stfem_ctx_timer_start": (C.c_int, [_vp]),
+    "stfem_ctx_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "stfem_dev_alloc": (C.c_int, [_vp, C.c_size_t, _vpp]),
     "stfem_dev_free": (C.c_int, [_vp, _vp]),
     "stfem_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
@@ -58,6 +61,15 @@ SYMBOLS = {
     "stfem_op_vmult_host": (C.c_int, [_vp, _vpp, _vpp, C.c_int]),
     "stfem_op_set_timing": (C.c_int, [_vp, C.c_int]),
     "stfem_op_last_kernel_ms": (C.c_float, [_vp]),
+    "stfem_fe_time_n_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "stfem_fe_time_weights": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int] + [_dp] * 4),
+    "stfem_fe_time_weights_wave": (C.c_int, [C.c_int, C.c_int] + [_dp] * 4 + [C.c_int] + [_dp] * 5),
+    "stfem_time_transfer_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int,
+                                             C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "stfem_poly_mg_sequence": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "stfem_mg_sequence": (C.c_int, [C.c_int] * 5 + [C.c_char] + [C.c_int] * 4 + [C.c_char_p, C.c_int]),
+    "stfem_precondition_stmg_types": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "stfem_quadrature_rule": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
 }
 
 
@@ -100,10 +112,32 @@ class Context:
     def launches(self):
         return lib().stfem_ctx_launch_count(self.h)
 
+    def timer_start(self):
+        check(lib().stfem_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().stfem_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def close(self):
         if self.h:
             lib().stfem_ctx_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def pinned_array(shape, dtype):
+    """numpy array backed by cudaMallocHost memory (kept alive by the returned array's base)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(lib().stfem_host_alloc_pinned(n, C.byref(p)))
+    buf = (C.c_byte * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, p
+
+
+def free_pinned(p):
+    lib().stfem_host_free_pinned(p)
 
 
 class DeviceBlockVector:
@@ -167,7 +201,8 @@ class Mesh:
 class Operator:
     """SystemMatrix<dim, Number, MatrixFreeOperatorScalar> of the reference (operators.h:516-663)."""
 
-    def __init__(self, mesh, degree, Alpha, Beta, number_type=F64, laplace_coeff_cell=None, variant=0):
+    def __init__(self, mesh, degree, Alpha, Beta, number_type=F64, laplace_coeff_cell=None, laplace_coeff_q=None,
+                 variant=0):
         self.mesh, self.ctx, self.number_type = mesh, mesh.ctx, number_type
         A = np.ascontiguousarray(np.atleast_2d(Alpha), np.float64)
         B = np.ascontiguousarray(np.atleast_2d(Beta), np.float64)
@@ -178,6 +213,9 @@ class Operator:
         if laplace_coeff_cell is not None:
             self._coef = np.ascontiguousarray(laplace_coeff_cell, np.float64)
             d.laplace_coeff_cell = _dptr(self._coef)
+        if laplace_coeff_q is not None:
+            self._coefq = np.ascontiguousarray(laplace_coeff_q, np.float64)
+            d.laplace_coeff_q = _dptr(self._coefq)
         d.kernel_variant = variant
         self.h = C.c_void_p()
         check(lib().stfem_op_create(mesh.h, C.byref(d), C.byref(self.h)))

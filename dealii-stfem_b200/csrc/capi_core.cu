@@ -33,6 +33,8 @@ int stfem_ctx_create(int device, stfem_ctx_t *out)
   STFEM_CUDA_CHECK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   STFEM_CUDA_CHECK(cudaEventCreate(&c->ev0));
   STFEM_CUDA_CHECK(cudaEventCreate(&c->ev1));
+  STFEM_CUDA_CHECK(cudaEventCreate(&c->tm0));
+  STFEM_CUDA_CHECK(cudaEventCreate(&c->tm1));
   *out = c;
   return STFEM_OK;
 }
@@ -44,6 +46,8 @@ int stfem_ctx_destroy(stfem_ctx_t ctx)
   cudaStreamSynchronize(ctx->stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->tm0);
+  cudaEventDestroy(ctx->tm1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return STFEM_OK;
@@ -53,6 +57,22 @@ int stfem_ctx_synchronize(stfem_ctx_t ctx)
 {
   STFEM_REQUIRE(ctx, "null context");
   STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return STFEM_OK;
+}
+
+int stfem_ctx_timer_start(stfem_ctx_t ctx)
+{
+  STFEM_REQUIRE(ctx, "null context");
+  STFEM_CUDA_CHECK(cudaEventRecord(ctx->tm0, ctx->stream));
+  return STFEM_OK;
+}
+
+int stfem_ctx_timer_stop(stfem_ctx_t ctx, float *ms)
+{
+  STFEM_REQUIRE(ctx && ms, "null argument");
+  STFEM_CUDA_CHECK(cudaEventRecord(ctx->tm1, ctx->stream));
+  STFEM_CUDA_CHECK(cudaEventSynchronize(ctx->tm1));
+  STFEM_CUDA_CHECK(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
   return STFEM_OK;
 }
 

@@ -12,7 +12,8 @@ namespace stfem
   // quadrature point, the symmetric tensor J^-1 J^-T * det(J) * w_q and JxW = det(J) * w_q.
   template <int DIM, typename T>
   __global__ void metric_kernel(const double *__restrict__ vertices, int n0, int n1, int n2, int nq1,
-                                const double *__restrict__ xq, const double *__restrict__ wq, T *__restrict__ metric)
+                                const double *__restrict__ xq, const double *__restrict__ wq, const double *__restrict__ coeff_q,
+                                T *__restrict__ metric)
   {
     constexpr int NSYM = DIM * (DIM + 1) / 2;
     const int     nq   = (DIM == 3) ? nq1 * nq1 * nq1 : nq1 * nq1;
@@ -69,6 +70,7 @@ namespace stfem
       }
     const double w   = wq[qx] * wq[qy] * ((DIM == 3) ? wq[qz] : 1.0);
     const double jxw = det * w;
+    const double cq  = coeff_q ? coeff_q[gid] : 1.0;
     T           *out = metric + (size_t)gid * (NSYM + 1);
     int          s   = 0;
     for (int a = 0; a < DIM; ++a)
@@ -76,9 +78,32 @@ namespace stfem
         {
           double g = 0;
           for (int c = 0; c < DIM; ++c) g += inv[a][c] * inv[b][c]; // (J^-1 J^-T)_ab, inv[a][c] = dxi_a/dx_c
-          out[s++] = (T)(g * jxw);
+          out[s++] = (T)(cq * g * jxw);
         }
     out[NSYM] = (T)jxw;
+  }
+
+  // uniform vertex grid for Cartesian meshes that need the general metric path (per-q coefficients)
+  static int mesh_ensure_vertices(stfem_mesh *m)
+  {
+    if (m->d_vertices) return STFEM_OK;
+    size_t nv = 1;
+    for (int d = 0; d < m->dim; ++d) nv *= (size_t)m->n[d] + 1;
+    m->h_vertices.resize(nv * m->dim);
+    size_t v = 0;
+    for (int iz = 0; iz <= (m->dim == 3 ? m->n[2] : 0); ++iz)
+      for (int iy = 0; iy <= m->n[1]; ++iy)
+        for (int ix = 0; ix <= m->n[0]; ++ix, ++v)
+          {
+            const int idx[3] = {ix, iy, iz};
+            for (int d = 0; d < m->dim; ++d)
+              m->h_vertices[v * m->dim + d] = m->lower[d] + (m->upper[d] - m->lower[d]) * idx[d] / m->n[d];
+          }
+    STFEM_CUDA_CHECK(cudaMalloc(&m->d_vertices, nv * m->dim * sizeof(double)));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(m->d_vertices, m->h_vertices.data(), nv * m->dim * sizeof(double),
+                                     cudaMemcpyHostToDevice, m->ctx->stream));
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(m->ctx->stream));
+    return STFEM_OK;
   }
 
   // ------------------------------------------------------------------ typed launchers
@@ -110,7 +135,7 @@ namespace stfem
       }
     a.alpha      = (const T *)alpha;
     a.beta       = (const T *)beta;
-    a.geom_mode  = m->cartesian ? 0 : 1;
+    a.geom_mode  = op->d_metric ? 1 : 0;
     a.metric     = (const T *)op->d_metric;
     a.coeff_cell = (const T *)op->d_coeff;
     a.dirichlet  = m->dirichlet;
@@ -252,15 +277,21 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
       else
         STFEM_FORWARD(upload_matrix<float>(ctx, c, &op->d_coeff));
     }
-  if (!mesh->cartesian)
+  if (!mesh->cartesian || desc->laplace_coeff_q)
     {
+      STFEM_FORWARD(mesh_ensure_vertices(mesh));
       const int       n1   = op->degree + 1;
       const int       nq   = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
       const int       nsym = mesh->dim * (mesh->dim + 1) / 2;
       const long long tot  = mesh->n_cells * nq;
       const size_t    bytes = (size_t)tot * (nsym + 1) * (f64 ? 8 : 4);
       STFEM_CUDA_CHECK(cudaMalloc(&op->d_metric, bytes));
-      double *d_xq = nullptr, *d_wq = nullptr;
+      double *d_xq = nullptr, *d_wq = nullptr, *d_cq = nullptr;
+      if (desc->laplace_coeff_q)
+        {
+          STFEM_CUDA_CHECK(cudaMalloc(&d_cq, (size_t)tot * sizeof(double)));
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(d_cq, desc->laplace_coeff_q, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        }
       STFEM_CUDA_CHECK(cudaMalloc(&d_xq, n1 * sizeof(double)));
       STFEM_CUDA_CHECK(cudaMalloc(&d_wq, n1 * sizeof(double)));
       STFEM_CUDA_CHECK(cudaMemcpyAsync(d_xq, op->shape->xq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -270,22 +301,23 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
       if (mesh->dim == 2)
         {
           if (f64)
-            metric_kernel<2, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, (double *)op->d_metric);
+            metric_kernel<2, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, d_cq, (double *)op->d_metric);
           else
-            metric_kernel<2, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, (float *)op->d_metric);
+            metric_kernel<2, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, d_cq, (float *)op->d_metric);
         }
       else
         {
           if (f64)
-            metric_kernel<3, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, (double *)op->d_metric);
+            metric_kernel<3, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, d_cq, (double *)op->d_metric);
           else
-            metric_kernel<3, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, (float *)op->d_metric);
+            metric_kernel<3, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, d_cq, (float *)op->d_metric);
         }
       ctx->launches++;
       STFEM_CUDA_CHECK(cudaGetLastError());
       STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       cudaFree(d_xq);
       cudaFree(d_wq);
+      if (d_cq) cudaFree(d_cq);
     }
   *out = op.release();
   return STFEM_OK;

@@ -55,7 +55,8 @@ struct stfem_ctx
   cudaStream_t stream  = nullptr;
   long long    launches = 0;
   int          sm_count = 0;
-  cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t  ev0 = nullptr, ev1 = nullptr; // per-operator kernel timing
+  cudaEvent_t  tm0 = nullptr, tm1 = nullptr; // stfem_ctx_timer_*
 };
 
 struct stfem_mesh

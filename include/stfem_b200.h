@@ -48,6 +48,10 @@ int stfem_ctx_synchronize(stfem_ctx_t ctx);
 void *stfem_ctx_stream(stfem_ctx_t ctx);
 /* number of kernels this library launched on the context so far (bench "gpu_launches") */
 long long stfem_ctx_launch_count(stfem_ctx_t ctx);
+/* CUDA-event stopwatch on the context stream: start records an event, stop records a second one,
+ * synchronises on it and returns the elapsed device time in ms */
+int stfem_ctx_timer_start(stfem_ctx_t ctx);
+int stfem_ctx_timer_stop(stfem_ctx_t ctx, float *ms);
 
 /* ---- device memory helpers (plain cudaMalloc/cudaMemcpyAsync on the context stream) ---- */
 int stfem_dev_alloc(stfem_ctx_t ctx, size_t bytes, void **out);
@@ -85,6 +89,9 @@ typedef struct stfem_op_desc {
   const double *Alpha;
   const double *Beta;
   const double *laplace_coeff_cell; /* host pointer, n_cells values, may be NULL */
+  const double *laplace_coeff_q;    /* host pointer, n_cells * (degree+1)^dim values (cell-major, q-points
+                                       lexicographic) = the reference's Table [cell][q]
+                                       (operators.h:1060-1087, 1185-1186); may be NULL */
   int kernel_variant;               /* 0 = default; >0 selects an implementation (tuning/tests) */
 } stfem_op_desc;
 
@@ -111,6 +118,35 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
  * context stream (ms); enabled with stfem_op_set_timing(op, 1) */
 int stfem_op_set_timing(stfem_op_t op, int enable);
 float stfem_op_last_kernel_ms(stfem_op_t op);
+
+/* ---- host-side time algebra (no GPU): reference include/fe_time.h, include/fe_time.cc.
+ *      type: 1 = CGP, 2 = DG (enum TimeStepType, fe_time.h:18-23).  All matrices row-major doubles. ---- */
+int stfem_fe_time_n_blocks(int type, int r, int n_timesteps_at_once);
+/* get_fe_time_weights (fe_time.h:351-409): Alpha*tau, Beta (nb x nb), Gamma, Zeta (nb x 1) */
+int stfem_fe_time_weights(int type, int r, double tau, int n_timesteps_at_once, double *Alpha, double *Beta,
+                          double *Gamma, double *Zeta);
+/* get_fe_time_weights_wave (fe_time.h:157-305): inputs nd x nd / nd x 1 single-step matrices,
+ * outputs (nd*nts)^2, (nd*nts)^2 and three (nd*nts) x 1 */
+int stfem_fe_time_weights_wave(int type, int nd, const double *Alpha, const double *Beta, const double *Gamma,
+                               const double *Zeta, int n_timesteps_at_once, double *lhs_uK, double *lhs_uM,
+                               double *rhs_uK, double *rhs_uM, double *rhs_vM);
+/* kind 0: get_time_projection_matrix(type, r_src=a, r_dst=b, nts)   (fe_time.h:749-805)
+ * kind 1: get_time_prolongation_matrix(type, r=a, nts)              (fe_time.h:807-851)
+ * kind 2: get_time_restriction_matrix(type, r=a, nts)               (fe_time.h:853-898)
+ * out may be NULL to query rows/cols. */
+int stfem_time_transfer_matrix(int kind, int type, int a, int b, int n_timesteps_at_once, double *out, int capacity,
+                               int *rows, int *cols);
+/* get_poly_mg_sequence (fe_time.cc:40-56); p_sequence: 0 bisect, 1 decrease_by_one, 2 go_to_one */
+int stfem_poly_mg_sequence(int k_max, int k_min, int p_sequence, int *out, int capacity, int *count);
+/* get_mg_sequence (fe_time.cc:58-127): level types 't','k','h','p' coarse -> fine, NUL-terminated.
+ * coarsening_type: 0 space_or_time, 1 space_and_time (types.h:103-107) */
+int stfem_mg_sequence(int n_sp_lvl, int n_k_seq, int n_p_seq, int n_timesteps_at_once, int n_timesteps_at_once_min,
+                      char lower_lvl, int coarsening_type, int time_before_space, int use_p_multigrid_space,
+                      int zip_from_back, char *out, int capacity);
+/* get_precondition_stmg_types (fe_time.cc:129-150): out has strlen(seq)+1 entries */
+int stfem_precondition_stmg_types(const char *seq, int coarsening_type, int time_before_space, int smoother, int *out);
+/* 1D rules on [0,1]: kind 0 QGauss, 1 QGaussLobatto, 2 QGaussRadau(right) */
+int stfem_quadrature_rule(int kind, int n, double *x, double *w);
 
 #ifdef __cplusplus
 }

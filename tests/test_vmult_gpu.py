@@ -30,11 +30,12 @@ def _rand_block(nb, n, seed=42):
     return np.stack([np.random.RandomState(seed + b).uniform(-1, 1, n) for b in range(nb)])
 
 
-def _gpu_op(ctx, mesh, k, A, B, number_type=0, coeff=None, variant=0):
+def _gpu_op(ctx, mesh, k, A, B, number_type=0, coeff=None, coeff_q=None, variant=0):
     import dealii_stfem_b200 as st
     gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper,
                  vertices=None if mesh.cartesian else mesh.vertices.reshape(-1, mesh.dim))
-    return gm, st.Operator(gm, k, A, B, number_type=number_type, laplace_coeff_cell=coeff, variant=variant)
+    return gm, st.Operator(gm, k, A, B, number_type=number_type, laplace_coeff_cell=coeff,
+                           laplace_coeff_q=coeff_q, variant=variant)
 
 
 def _rel(a, b):
@@ -119,13 +120,11 @@ def test_heterogeneous_coefficient_perturbed_mesh(ctx):
     K = S.MatrixFreeOperator(space, 0.0, 1.0)
     K.evaluate_coefficient(coef)
     M = S.MatrixFreeOperator(space, 1.0, 0.0)
-    # piecewise constant per cell on this mesh: one value per cell is the whole table
-    cc = K.laplace_coeff
-    assert np.all(cc == cc[:, :1])
+    cc = K.laplace_coeff        # Table [cell][q] like operators.h:1185-1186
     sysm = S.SystemMatrix(K, M, A, B)
     src = _rand_block(3, space.n_dofs)
     ref_dst = sysm.vmult(src)
-    gm, op = _gpu_op(ctx, mesh, k, A, B, coeff=cc[:, 0])
+    gm, op = _gpu_op(ctx, mesh, k, A, B, coeff_q=cc)
     d_src, d_dst = op.new_vector().upload(src), op.new_vector()
     op.vmult(d_dst, d_src)
     assert _rel(d_dst.download(), ref_dst) < 1e-12
@@ -153,3 +152,25 @@ def test_linearity_and_symmetry_large(ctx):
     for v in (dx, dy, dz, dr):
         v.free()
     op.close(); gm.close()
+
+
+def test_per_cell_coefficient_cartesian(ctx):
+    """Coefficient<dim> is constant per cell on the unperturbed practical mesh: the per-cell path."""
+    dim, k = 3, 2
+    mesh, space = _setup(dim, k, 1, 0.0, subdivisions=[5, 5, 5], lower=[-1, -1, -1], upper=[1, 1, 1])
+    coef = S.Coefficient(dim, [5, 5, 5], [-1, -1, -1], [1, 1, 1], distort_coeff=0.5)
+    A, B, _, _ = _time_matrices("DG", 1, 2)
+    K = S.MatrixFreeOperator(space, 0.0, 1.0)
+    K.evaluate_coefficient(coef)
+    M = S.MatrixFreeOperator(space, 1.0, 0.0)
+    cc = K.laplace_coeff
+    assert np.all(cc == cc[:, :1])
+    sysm = S.SystemMatrix(K, M, A, B)
+    src = _rand_block(4, space.n_dofs)
+    ref_dst = sysm.vmult(src)
+    for kw in (dict(coeff=cc[:, 0]), dict(coeff_q=cc)):
+        gm, op = _gpu_op(ctx, mesh, k, A, B, **kw)
+        d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+        op.vmult(d_dst, d_src)
+        assert _rel(d_dst.download(), ref_dst) < 1e-12
+        d_src.free(); d_dst.free(); op.close(); gm.close()
