@@ -61,6 +61,16 @@ SYMBOLS = {
     "stfem_op_vmult_host": (C.c_int, [_vp, _vpp, _vpp, C.c_int]),
     "stfem_op_set_timing": (C.c_int, [_vp, C.c_int]),
     "stfem_op_last_kernel_ms": (C.c_float, [_vp]),
+    "stfem_mg_create": (C.c_int, [_vp, _vp, _vpp]),
+    "stfem_mg_destroy": (C.c_int, [_vp]),
+    "stfem_mg_n_levels": (C.c_int, [_vp]),
+    "stfem_mg_vmult": (C.c_int, [_vp, _vpp, _vpp]),
+    "stfem_mg_level_apply": (C.c_int, [_vp, C.c_int, C.c_int, _vpp, _vpp]),
+    "stfem_mg_level_info": (C.c_int, [_vp, C.c_int, _dp]),
+    "stfem_solver_create": (C.c_int, [_vpp]),
+    "stfem_solver_destroy": (C.c_int, [_vp]),
+    "stfem_fgmres_solve": (C.c_int, [_vp, _vp, _vp, _vpp, _vpp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                     C.POINTER(C.c_int), _dp, _dp]),
     "stfem_fe_time_n_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "stfem_fe_time_weights": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int] + [_dp] * 4),
     "stfem_fe_time_weights_wave": (C.c_int, [C.c_int, C.c_int] + [_dp] * 4 + [C.c_int] + [_dp] * 5),
@@ -250,4 +260,81 @@ class Operator:
     def close(self):
         if self.h:
             lib().stfem_op_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class MgDesc(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("level_ops", C.POINTER(C.c_void_p)), ("mg_type_level", C.c_char_p),
+                ("smoother_types", C.POINTER(C.c_int)), ("time_type", C.c_int), ("n_timesteps_at_once", C.c_int),
+                ("poly_time_sequence", C.POINTER(C.c_int)), ("n_poly_time", C.c_int), ("smoothing_steps", C.c_int),
+                ("relaxation", C.c_double), ("smoothing_range", C.c_double), ("eig_n_iterations", C.c_int),
+                ("variable", C.c_int), ("restrict_is_transpose_prolongate", C.c_int)]
+
+
+class Multigrid:
+    """GMG of the reference (include/stmg.h:1047-1344) on a list of level Operators (coarse -> fine)."""
+
+    def __init__(self, ctx, level_ops, mg_type_level, smoother_types, time_type, n_timesteps_at_once, poly_time_sequence,
+                 smoothing_steps=1, relaxation=0.0, smoothing_range=1.0, eig_n_iterations=20, variable=True,
+                 restrict_is_transpose_prolongate=True):
+        self.ctx, self.ops = ctx, list(level_ops)
+        nl = len(self.ops)
+        d = MgDesc()
+        d.n_levels = nl
+        self._ops = (C.c_void_p * nl)(*[o.h.value for o in self.ops])
+        d.level_ops = self._ops
+        self._types = "".join(mg_type_level).encode()
+        d.mg_type_level = self._types
+        self._sm = (C.c_int * nl)(*smoother_types)
+        d.smoother_types = self._sm
+        d.time_type = {"CGP": 1, "DG": 2}[time_type]
+        d.n_timesteps_at_once = n_timesteps_at_once
+        self._poly = (C.c_int * len(poly_time_sequence))(*poly_time_sequence)
+        d.poly_time_sequence, d.n_poly_time = self._poly, len(poly_time_sequence)
+        d.smoothing_steps, d.relaxation, d.smoothing_range = smoothing_steps, relaxation, smoothing_range
+        d.eig_n_iterations, d.variable = eig_n_iterations, int(variable)
+        d.restrict_is_transpose_prolongate = int(restrict_is_transpose_prolongate)
+        self.h = C.c_void_p()
+        check(lib().stfem_mg_create(ctx.h, C.byref(d), C.byref(self.h)))
+
+    @property
+    def n_levels(self):
+        return lib().stfem_mg_n_levels(self.h)
+
+    def vmult(self, dst, src):
+        check(lib().stfem_mg_vmult(self.h, dst.ptrs, src.ptrs))
+
+    def level_apply(self, level, what, dst, src):
+        check(lib().stfem_mg_level_apply(self.h, level, what, dst.ptrs, src.ptrs))
+
+    def level_info(self, level):
+        out = np.zeros(10)
+        check(lib().stfem_mg_level_info(self.h, level, _dptr(out)))
+        keys = ["smoother", "lambda", "omega", "theta", "delta", "steps", "N", "blocks", "patch_matrices", "patch_bytes"]
+        return dict(zip(keys, out))
+
+    def close(self):
+        if self.h:
+            lib().stfem_mg_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Fgmres:
+    """SolverFGMRES + ReductionControl as configured by the reference (time_integrators.h:56-59)."""
+
+    def __init__(self):
+        self.h = C.c_void_p()
+        check(lib().stfem_solver_create(C.byref(self.h)))
+
+    def solve(self, A, x, b, M=None, max_basis=100, max_iter=200, abstol=1e-12, reduce=1e-12):
+        it, r0, r1 = C.c_int(), C.c_double(), C.c_double()
+        rc = lib().stfem_fgmres_solve(self.h, A.h, M.h if M is not None else None, x.ptrs, b.ptrs, max_basis, max_iter,
+                                      abstol, reduce, C.byref(it), C.byref(r0), C.byref(r1))
+        self.iterations, self.initial_residual, self.final_residual = it.value, r0.value, r1.value
+        check(rc)
+        return it.value
+
+    def close(self):
+        if self.h:
+            lib().stfem_solver_destroy(self.h)
             self.h = C.c_void_p()

@@ -106,6 +106,51 @@ namespace stfem
     return STFEM_OK;
   }
 
+  // per cell / q-point metric of the operator's mesh in precision T (per-q coefficient folded in)
+  template <typename T>
+  static int compute_metric(stfem_op *op, void **out)
+  {
+    stfem_mesh *mesh = op->mesh;
+    stfem_ctx  *ctx  = mesh->ctx;
+    STFEM_FORWARD(mesh_ensure_vertices(mesh));
+    const int       n1   = op->degree + 1;
+    const int       nq   = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    const int       nsym = mesh->dim * (mesh->dim + 1) / 2;
+    const long long tot  = mesh->n_cells * nq;
+    STFEM_CUDA_CHECK(cudaMalloc(out, (size_t)tot * (nsym + 1) * sizeof(T)));
+    double *d_xq = nullptr, *d_wq = nullptr, *d_cq = nullptr;
+    if (!op->h_coeff_q.empty())
+      {
+        STFEM_CUDA_CHECK(cudaMalloc(&d_cq, (size_t)tot * sizeof(double)));
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_cq, op->h_coeff_q.data(), (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      }
+    STFEM_CUDA_CHECK(cudaMalloc(&d_xq, n1 * sizeof(double)));
+    STFEM_CUDA_CHECK(cudaMalloc(&d_wq, n1 * sizeof(double)));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(d_xq, op->shape->xq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(d_wq, op->shape->wq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const int       threads = 256;
+    const long long blocks  = (tot + threads - 1) / threads;
+    if (mesh->dim == 2)
+      metric_kernel<2, T><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, d_cq, (T *)*out);
+    else
+      metric_kernel<3, T><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, d_cq, (T *)*out);
+    ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_xq);
+    cudaFree(d_wq);
+    if (d_cq) cudaFree(d_cq);
+    return STFEM_OK;
+  }
+
+  int metric_double(stfem_op *op, double **out)
+  {
+    void *p  = nullptr;
+    int   rc = compute_metric<double>(op, &p);
+    *out     = (double *)p;
+    return rc;
+  }
+
   // ------------------------------------------------------------------ typed launchers
   template <int DIM, int N1, typename T>
   static int launch_generic(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst,
@@ -271,53 +316,21 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
     }
   if (desc->laplace_coeff_cell)
     {
-      std::vector<double> c(desc->laplace_coeff_cell, desc->laplace_coeff_cell + mesh->n_cells);
+      op->h_coeff_cell.assign(desc->laplace_coeff_cell, desc->laplace_coeff_cell + mesh->n_cells);
       if (f64)
-        STFEM_FORWARD(upload_matrix<double>(ctx, c, &op->d_coeff));
+        STFEM_FORWARD(upload_matrix<double>(ctx, op->h_coeff_cell, &op->d_coeff));
       else
-        STFEM_FORWARD(upload_matrix<float>(ctx, c, &op->d_coeff));
+        STFEM_FORWARD(upload_matrix<float>(ctx, op->h_coeff_cell, &op->d_coeff));
     }
   if (!mesh->cartesian || desc->laplace_coeff_q)
     {
-      STFEM_FORWARD(mesh_ensure_vertices(mesh));
-      const int       n1   = op->degree + 1;
-      const int       nq   = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
-      const int       nsym = mesh->dim * (mesh->dim + 1) / 2;
-      const long long tot  = mesh->n_cells * nq;
-      const size_t    bytes = (size_t)tot * (nsym + 1) * (f64 ? 8 : 4);
-      STFEM_CUDA_CHECK(cudaMalloc(&op->d_metric, bytes));
-      double *d_xq = nullptr, *d_wq = nullptr, *d_cq = nullptr;
-      if (desc->laplace_coeff_q)
-        {
-          STFEM_CUDA_CHECK(cudaMalloc(&d_cq, (size_t)tot * sizeof(double)));
-          STFEM_CUDA_CHECK(cudaMemcpyAsync(d_cq, desc->laplace_coeff_q, (size_t)tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        }
-      STFEM_CUDA_CHECK(cudaMalloc(&d_xq, n1 * sizeof(double)));
-      STFEM_CUDA_CHECK(cudaMalloc(&d_wq, n1 * sizeof(double)));
-      STFEM_CUDA_CHECK(cudaMemcpyAsync(d_xq, op->shape->xq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      STFEM_CUDA_CHECK(cudaMemcpyAsync(d_wq, op->shape->wq.data(), n1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      const int       threads = 256;
-      const long long blocks  = (tot + threads - 1) / threads;
-      if (mesh->dim == 2)
-        {
-          if (f64)
-            metric_kernel<2, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, d_cq, (double *)op->d_metric);
-          else
-            metric_kernel<2, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], 1, n1, d_xq, d_wq, d_cq, (float *)op->d_metric);
-        }
+      const int n1 = op->degree + 1;
+      const int nq = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
+      if (desc->laplace_coeff_q) op->h_coeff_q.assign(desc->laplace_coeff_q, desc->laplace_coeff_q + mesh->n_cells * nq);
+      if (f64)
+        STFEM_FORWARD(compute_metric<double>(op.get(), &op->d_metric));
       else
-        {
-          if (f64)
-            metric_kernel<3, double><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, d_cq, (double *)op->d_metric);
-          else
-            metric_kernel<3, float><<<(unsigned)blocks, threads, 0, ctx->stream>>>(mesh->d_vertices, mesh->n[0], mesh->n[1], mesh->n[2], n1, d_xq, d_wq, d_cq, (float *)op->d_metric);
-        }
-      ctx->launches++;
-      STFEM_CUDA_CHECK(cudaGetLastError());
-      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(d_xq);
-      cudaFree(d_wq);
-      if (d_cq) cudaFree(d_cq);
+        STFEM_FORWARD(compute_metric<float>(op.get(), &op->d_metric));
     }
   *out = op.release();
   return STFEM_OK;

@@ -1,0 +1,570 @@
+// Space-time multigrid V-cycle and FGMRES, host drivers over the device kernels.
+// Replaces, for the reference's hot path:
+//   GMG                               include/stmg.h:1047-1344   (reinit :1193-1329, vmult :1331-1344)
+//   PreconditionSTMG                  include/stmg.h:968-1045    (Identity | Relaxation<Vanka> | Chebyshev<Vanka>)
+//   STMGTransferBlockMatrixFree       include/stmg.h:304-458
+//   deal.II Multigrid::level_v_step, MGSmootherPrecondition, MGCoarseGridApplySmoother,
+//   PreconditionRelaxation / PreconditionChebyshev with power-iteration estimate   
+//   deal.II SolverFGMRES + ReductionControl  (include/time_integrators.h:56-59, 315)
+#pragma once
+#include <cmath>
+#include <memory>
+
+#include "fe_time.hpp"
+#include "op.hpp"
+#include "transfer.cuh"
+#include "vanka.cuh"
+#include "vec.cuh"
+
+namespace stfem
+{
+  template <typename T>
+  __global__ void k_initial_guess(long long n, int nb, T *__restrict__ v)
+  {
+    // deal.II set_initial_guess: (i mod 11) minus its mean, per block
+    const long long full = n / 11, rem = n % 11;
+    const double    mean = (double)(full * 55 + rem * (rem - 1) / 2) / (double)n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * nb; i += (long long)gridDim.x * blockDim.x)
+      v[i] = (T)((double)((i % n) % 11) - mean);
+  }
+
+  template <typename T>
+  struct MGLevel
+  {
+    stfem_op                 *op = nullptr;
+    int                       smoother = 1; // 0 identity, 1 relaxation, 2 chebyshev
+    std::unique_ptr<Vanka<T>> vanka;
+    double                    omega = 1.0, theta = 1.0, delta = 0.0, lambda = 1.0;
+    char                      ttype = 0; // transfer from level-1: 'h','p','k','t'
+    SpaceTransfer<T>          st;
+    TimeTransfer<T>           tt;
+    BlockVec<T>               sol, defect, t, r, d, d2;
+    int                       steps = 1;
+  };
+
+  struct MGOptions
+  {
+    int    smoothing_steps = 1;
+    double relaxation = 0.0, smoothing_range = 1.0;
+    int    eig_n_iterations = 20;
+    bool   variable = true, restrict_is_transpose_prolongate = true;
+  };
+
+  struct MGBase
+  {
+    virtual ~MGBase() = default;
+    virtual int vmult(void *const *dst, const void *const *src) = 0; // double block pointers (finest level)
+    virtual int level_apply(int level, int what, void *const *dst, const void *const *src) = 0;
+    virtual int level_info(int level, double *out) = 0;
+    virtual int n_levels() const = 0;
+    stfem_ctx *ctx = nullptr;
+  };
+
+  template <typename T>
+  struct Multigrid : MGBase
+  {
+    std::vector<MGLevel<T>> L;
+    MGOptions               opt;
+    DotScratch              sc;
+    BlockVec<double>        src64, dst64; // staging when T == float or the caller's blocks are not contiguous
+
+    int n_levels() const override { return (int)L.size(); }
+
+    int A(int l, BlockVec<T> &dst, const BlockVec<T> &src)
+    {
+      stfem_op *op = L[l].op;
+      return op_apply(op, dst.block_ptrs(), src.cblock_ptrs(), op->nb_cols, op->nb_rows, op->d_alpha, op->d_beta, true);
+    }
+
+    // PreconditionSTMG::vmult(dst, src)   (stmg.h:1018-1023)
+    int smoother_vmult(int l, BlockVec<T> &dst, const BlockVec<T> &src)
+    {
+      MGLevel<T> &lv = L[l];
+      if (lv.smoother == 0) return v_copy(dst, src);
+      if (lv.smoother == 1)
+        {
+          // PreconditionRelaxation: x = w P^-1 b ; n_it-1 times x += w P^-1 (b - A x)
+          STFEM_FORWARD(lv.vanka->vmult(dst, src));
+          v_scale(dst, (T)lv.omega);
+          for (int it = 1; it < opt.smoothing_steps; ++it)
+            {
+              STFEM_FORWARD(A(l, lv.d2, dst));
+              v_sadd(lv.d2, (T)-1, (T)1, src); // d2 = b - A x
+              STFEM_FORWARD(lv.vanka->vmult(lv.t, lv.d2));
+              v_axpy(dst, (T)lv.omega, lv.t);
+            }
+          return STFEM_OK;
+        }
+      // Chebyshev of degree smoothing_steps, zero start vector
+      const double th = lv.theta, de = lv.delta;
+      STFEM_FORWARD(lv.vanka->vmult(lv.d2, src));
+      v_scale(lv.d2, (T)(1.0 / th)); // d
+      STFEM_FORWARD(v_copy(dst, lv.d2));
+      if (opt.smoothing_steps < 2) return STFEM_OK;
+      const bool   fin = de != 0.0;
+      const double sigma = fin ? th / de : 0.0;
+      double       rho_old = fin ? 1.0 / sigma : 0.0;
+      for (int it = 1; it < opt.smoothing_steps; ++it)
+        {
+          const double rho = fin ? 1.0 / (2.0 * sigma - rho_old) : 0.0;
+          STFEM_FORWARD(A(l, lv.t, dst));
+          v_sadd(lv.t, (T)-1, (T)1, src); // r = b - A x
+          // d = rho*rho_old*d + (2 rho/delta) P^-1 r   (delta = 0: plain Richardson with 1/theta)
+          BlockVec<T> &pr = lv.sol; // scratch: only used outside the V-cycle recursion of this level's smoother
+          (void)pr;
+          STFEM_FORWARD(lv.vanka->vmult(lv.r, lv.t));
+          v_sadd(lv.d2, (T)(rho * rho_old), (T)(fin ? 2.0 * rho / de : 1.0 / th), lv.r);
+          v_axpy(dst, (T)1, lv.d2);
+          rho_old = rho;
+        }
+      return STFEM_OK;
+    }
+
+    // MGSmootherPrecondition::apply: u = P b, then steps-1 times u += P (b - A u)
+    int mg_apply(int l, BlockVec<T> &u, const BlockVec<T> &rhs)
+    {
+      MGLevel<T> &lv = L[l];
+      STFEM_FORWARD(smoother_vmult(l, u, rhs));
+      for (int s = 1; s < lv.steps; ++s) STFEM_FORWARD(smooth_step(l, u, rhs));
+      return STFEM_OK;
+    }
+    int smooth_step(int l, BlockVec<T> &u, const BlockVec<T> &rhs)
+    {
+      MGLevel<T> &lv = L[l];
+      STFEM_FORWARD(A(l, lv.r, u));
+      v_sadd(lv.r, (T)-1, (T)1, rhs);
+      // the smoother uses lv.t/lv.d2/lv.r as scratch: keep the residual in lv.d
+      STFEM_FORWARD(v_copy(lv.d, lv.r));
+      BlockVec<T> &corr = lv.t;
+      if (lv.smoother == 0)
+        {
+          v_axpy(u, (T)1, lv.d);
+          return STFEM_OK;
+        }
+      // result of the smoother must not alias its scratch: smoother_vmult writes dst first into `corr2`
+      STFEM_FORWARD(smoother_vmult_into(l, corr, lv.d));
+      v_axpy(u, (T)1, corr);
+      return STFEM_OK;
+    }
+    // smoother_vmult with dst = lv.t: for relaxation steps>1 and Chebyshev the scratch lv.t is needed, use lv.sol2
+    int smoother_vmult_into(int l, BlockVec<T> &dst, const BlockVec<T> &src)
+    {
+      MGLevel<T> &lv = L[l];
+      if (lv.smoother != 0 && opt.smoothing_steps > 1)
+        {
+          // dst aliases lv.t which the multi-step smoothers use: go through a private buffer
+          if (tmp_multi.size() <= (size_t)l) tmp_multi.resize(L.size());
+          if (!tmp_multi[l].d) STFEM_FORWARD(tmp_multi[l].alloc(ctx, src.nb, src.n));
+          STFEM_FORWARD(smoother_vmult(l, tmp_multi[l], src));
+          return v_copy(dst, tmp_multi[l]);
+        }
+      return smoother_vmult(l, dst, src);
+    }
+    std::vector<BlockVec<T>> tmp_multi;
+
+    // Multigrid::level_v_step; defect in L[l].defect, result in L[l].sol
+    int v_step(int l)
+    {
+      MGLevel<T> &lv = L[l];
+      if (l == 0) return mg_apply(0, lv.sol, lv.defect);
+      STFEM_FORWARD(mg_apply(l, lv.sol, lv.defect));
+      // t = defect - A sol
+      {
+        BlockVec<T> &res = lv.d;
+        STFEM_FORWARD(A(l, res, lv.sol));
+        v_sadd(res, (T)-1, (T)1, lv.defect);
+        MGLevel<T> &lc = L[l - 1];
+        STFEM_FORWARD(lc.defect.zero());
+        if (lv.ttype == 'h' || lv.ttype == 'p')
+          STFEM_FORWARD(lv.st.restrict_and_add(lc.defect, res));
+        else
+          lv.tt.restrict_and_add(lc.defect, res);
+      }
+      STFEM_FORWARD(v_step(l - 1));
+      {
+        MGLevel<T> &lc = L[l - 1];
+        if (lv.ttype == 'h' || lv.ttype == 'p')
+          STFEM_FORWARD(lv.st.prolongate_and_add(lv.sol, lc.sol));
+        else
+          lv.tt.prolongate_and_add(lv.sol, lc.sol);
+      }
+      for (int s = 0; s < lv.steps; ++s) STFEM_FORWARD(smooth_step(l, lv.sol, lv.defect));
+      return STFEM_OK;
+    }
+
+    int estimate(int l)
+    {
+      MGLevel<T> &lv = L[l];
+      if (lv.smoother == 0) return STFEM_OK;
+      if (lv.smoother == 1 && opt.relaxation != 0.0)
+        {
+          lv.omega = opt.relaxation;
+          return STFEM_OK;
+        }
+      // power iteration on P^-1 A (A.7)
+      BlockVec<T> &v = lv.sol, &w = lv.defect, &tmp = lv.t;
+      k_initial_guess<T><<<grid_for(ctx, v.size(), 256), 256, 0, ctx->stream>>>(v.n, v.nb, v.d);
+      ctx->launches++;
+      double nrm2 = 0, lam = 1.0;
+      STFEM_FORWARD(v_dot(sc, v, v, &nrm2));
+      if (nrm2 > 0)
+        {
+          v_scale(v, (T)(1.0 / std::sqrt(nrm2)));
+          for (int it = 0; it < opt.eig_n_iterations; ++it)
+            {
+              STFEM_FORWARD(A(l, tmp, v));
+              STFEM_FORWARD(lv.vanka->vmult(w, tmp));
+              double                           out[2];
+              std::vector<const BlockVec<T> *> V{&v, &w};
+              STFEM_FORWARD(v_multi_dot(sc, w, V, out));
+              lam = out[0];
+              const double nw = std::sqrt(out[1]);
+              if (!(nw > 0) || !std::isfinite(nw))
+                {
+                  lam = 1.0; // guard: start vector in the kernel of A (1-cell coarse levels)
+                  break;
+                }
+              STFEM_FORWARD(v_copy(v, w));
+              v_scale(v, (T)(1.0 / nw));
+            }
+        }
+      lv.lambda = lam;
+      const double lmax = 1.2 * lam;
+      const double rng  = opt.smoothing_range;
+      const double lmin = rng > 1.0 ? lam / rng : lam;
+      const double alpha = rng > 1.0 ? lmax / rng : std::min(0.9 * lmax, lmin);
+      if (lv.smoother == 1)
+        lv.omega = 2.0 / (alpha + lmax);
+      else
+        {
+          lv.theta = 0.5 * (lmax + alpha);
+          lv.delta = 0.5 * (lmax - alpha);
+        }
+      return STFEM_OK;
+    }
+
+    int init(stfem_ctx *c, const std::vector<stfem_op *> &ops, const std::string &types, const std::vector<int> &smoothers, int time_type,
+             int nts, const std::vector<int> &poly_time, const MGOptions &o)
+    {
+      ctx = c; opt = o;
+      const int nl = (int)ops.size();
+      STFEM_REQUIRE(nl >= 1 && (int)types.size() == nl - 1 && (int)smoothers.size() == nl, "mg: inconsistent level description");
+      L.resize(nl);
+      // block structure per level (get_blk_indices, stmg.h:460-501)
+      std::vector<int> lv_nts(nl), lv_nd(nl);
+      {
+        int p = (int)poly_time.size() - 1, n = nts;
+        for (int i = nl - 1; i >= 1; --i)
+          {
+            STFEM_REQUIRE(p >= 0, "mg: poly_time_sequence too short for the number of k levels");
+            lv_nts[i] = n;
+            lv_nd[i]  = time_type == DG ? poly_time[p] + 1 : poly_time[p];
+            if (types[i - 1] == 'k') --p;
+            else if (types[i - 1] == 't') n /= 2;
+          }
+        STFEM_REQUIRE(p >= 0, "mg: poly_time_sequence too short");
+        lv_nts[0] = n;
+        lv_nd[0]  = time_type == DG ? poly_time[p] + 1 : poly_time[p];
+      }
+      for (int l = 0; l < nl; ++l)
+        {
+          MGLevel<T> &lv = L[l];
+          lv.op       = ops[l];
+          lv.smoother = smoothers[l];
+          lv.steps    = opt.variable ? (1 << (nl - 1 - l)) : 1;
+          STFEM_REQUIRE(lv.op->nb_rows == lv_nts[l] * lv_nd[l], "mg: level %d operator has %d blocks, level structure says %d x %d", l,
+                        lv.op->nb_rows, lv_nts[l], lv_nd[l]);
+          const int nb = lv.op->nb_rows;
+          for (BlockVec<T> *v : {&lv.sol, &lv.defect, &lv.t, &lv.r, &lv.d, &lv.d2}) STFEM_FORWARD(v->alloc(ctx, nb, lv.op->N));
+          if (lv.smoother != 0)
+            {
+              lv.vanka = std::make_unique<Vanka<T>>();
+              STFEM_FORWARD(lv.vanka->setup(lv.op));
+            }
+          if (l > 0)
+            {
+              lv.ttype = types[l - 1];
+              stfem_op *oc = ops[l - 1];
+              if (lv.ttype == 'h' || lv.ttype == 'p')
+                {
+                  STFEM_REQUIRE(oc->nb_rows == nb, "mg: space transfer between levels with different block counts");
+                  STFEM_FORWARD(lv.st.init(ctx, lv.op->mesh->dim, oc->mesh->n, oc->degree, lv.op->mesh->n, lv.op->degree, lv.op->mesh->dirichlet));
+                }
+              else
+                {
+                  STFEM_REQUIRE(oc->N == lv.op->N, "mg: time transfer between levels with different spatial size");
+                  STFEM_FORWARD(lv.tt.init(time_type, lv_nts[l], lv_nd[l], lv_nts[l - 1], lv_nd[l - 1], opt.restrict_is_transpose_prolongate, lv.ttype));
+                }
+            }
+        }
+      for (int l = 0; l < nl; ++l) STFEM_FORWARD(estimate(l));
+      return STFEM_OK;
+    }
+
+    int stage_in(BlockVec<T> &dst, const void *const *src, int nb, long long n)
+    {
+      if (std::is_same<T, double>::value)
+        {
+          for (int b = 0; b < nb; ++b)
+            STFEM_CUDA_CHECK(cudaMemcpyAsync((char *)dst.d + sizeof(T) * (size_t)b * n, src[b], sizeof(T) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+          return STFEM_OK;
+        }
+      if (!src64.d) STFEM_FORWARD(src64.alloc(ctx, nb, n));
+      for (int b = 0; b < nb; ++b)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(src64.d + (size_t)b * n, src[b], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      k_convert<T, double><<<grid_for(ctx, dst.size(), 256), 256, 0, ctx->stream>>>(dst.size(), src64.d, dst.d);
+      ctx->launches++;
+      return STFEM_OK;
+    }
+    int stage_out(void *const *dst, const BlockVec<T> &src, int nb, long long n)
+    {
+      if (std::is_same<T, double>::value)
+        {
+          for (int b = 0; b < nb; ++b)
+            STFEM_CUDA_CHECK(cudaMemcpyAsync(dst[b], (const char *)src.d + sizeof(T) * (size_t)b * n, sizeof(T) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+          return STFEM_OK;
+        }
+      if (!dst64.d) STFEM_FORWARD(dst64.alloc(ctx, nb, n));
+      k_convert<double, T><<<grid_for(ctx, src.size(), 256), 256, 0, ctx->stream>>>(src.size(), src.d, dst64.d);
+      ctx->launches++;
+      for (int b = 0; b < nb; ++b)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(dst[b], dst64.d + (size_t)b * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      return STFEM_OK;
+    }
+
+    // GMG::vmult (stmg.h:1331-1344): double in, one V-cycle in level precision, double out
+    int vmult(void *const *dst, const void *const *src) override
+    {
+      MGLevel<T> &top = L.back();
+      STFEM_FORWARD(stage_in(top.defect, src, top.op->nb_rows, top.op->N));
+      STFEM_FORWARD(v_step((int)L.size() - 1));
+      return stage_out(dst, top.sol, top.op->nb_rows, top.op->N);
+    }
+
+    // unit-test hooks; vectors in LEVEL precision, given as block pointers
+    int level_apply(int l, int what, void *const *dst, const void *const *src) override
+    {
+      STFEM_REQUIRE(l >= 0 && l < (int)L.size(), "mg level %d out of range", l);
+      MGLevel<T> &lv = L[l];
+      auto load = [&](BlockVec<T> &v, const void *const *p) -> int {
+        for (int b = 0; b < v.nb; ++b)
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(v.d + (size_t)b * v.n, p[b], sizeof(T) * v.n, cudaMemcpyDeviceToDevice, ctx->stream));
+        return STFEM_OK;
+      };
+      auto store = [&](void *const *p, const BlockVec<T> &v) -> int {
+        for (int b = 0; b < v.nb; ++b)
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(p[b], v.d + (size_t)b * v.n, sizeof(T) * v.n, cudaMemcpyDeviceToDevice, ctx->stream));
+        return STFEM_OK;
+      };
+      switch (what)
+        {
+          case 0: // Vanka
+            STFEM_REQUIRE(lv.vanka, "level %d has no Vanka smoother", l);
+            STFEM_FORWARD(load(lv.defect, src));
+            STFEM_FORWARD(lv.vanka->vmult(lv.sol, lv.defect));
+            return store(dst, lv.sol);
+          case 1: // PreconditionSTMG::vmult
+            STFEM_FORWARD(load(lv.defect, src));
+            STFEM_FORWARD(smoother_vmult(l, lv.sol, lv.defect));
+            return store(dst, lv.sol);
+          case 2: // restrict level l -> l-1 (dst zeroed)
+            STFEM_REQUIRE(l > 0, "no coarser level");
+            STFEM_FORWARD(load(lv.d, src));
+            STFEM_FORWARD(L[l - 1].defect.zero());
+            if (lv.ttype == 'h' || lv.ttype == 'p') STFEM_FORWARD(lv.st.restrict_and_add(L[l - 1].defect, lv.d));
+            else lv.tt.restrict_and_add(L[l - 1].defect, lv.d);
+            return store(dst, L[l - 1].defect);
+          case 3: // prolongate level l-1 -> l (dst zeroed)
+            STFEM_REQUIRE(l > 0, "no coarser level");
+            STFEM_FORWARD(load(L[l - 1].sol, src));
+            STFEM_FORWARD(lv.sol.zero());
+            if (lv.ttype == 'h' || lv.ttype == 'p') STFEM_FORWARD(lv.st.prolongate_and_add(lv.sol, L[l - 1].sol));
+            else lv.tt.prolongate_and_add(lv.sol, L[l - 1].sol);
+            return store(dst, lv.sol);
+          case 4: // level operator
+            STFEM_FORWARD(load(lv.defect, src));
+            STFEM_FORWARD(A(l, lv.sol, lv.defect));
+            return store(dst, lv.sol);
+          case 5: // one V-cycle starting at this level (defect -> correction)
+            STFEM_FORWARD(load(lv.defect, src));
+            STFEM_FORWARD(v_step(l));
+            return store(dst, lv.sol);
+          default: set_error("mg level_apply: unknown operation %d", what); return STFEM_ERR_INVALID;
+        }
+    }
+
+    int level_info(int l, double *out) override
+    {
+      STFEM_REQUIRE(l >= 0 && l < (int)L.size() && out, "mg level_info: bad arguments");
+      MGLevel<T> &lv = L[l];
+      out[0] = lv.smoother; out[1] = lv.lambda; out[2] = lv.omega; out[3] = lv.theta; out[4] = lv.delta; out[5] = lv.steps;
+      out[6] = (double)lv.op->N; out[7] = lv.op->nb_rows; out[8] = lv.vanka ? (double)lv.vanka->n_mat : 0.0;
+      out[9] = lv.vanka ? (double)lv.vanka->bytes : 0.0;
+      return STFEM_OK;
+    }
+  };
+
+  // ------------------------------------------------------------------ FGMRES (double)
+  struct FgmresResult { int iterations = 0; double initial_residual = 0, final_residual = 0; bool converged = false; };
+
+  struct Fgmres
+  {
+    stfem_ctx                     *ctx = nullptr;
+    std::vector<BlockVec<double>>  V, Z;
+    BlockVec<double>               x, b, w;
+    DotScratch                     sc;
+
+    int ensure(std::vector<BlockVec<double>> &a, size_t i, int nb, long long n)
+    {
+      while (a.size() <= i) a.emplace_back();
+      if (!a[i].d || a[i].nb != nb || a[i].n != n) STFEM_FORWARD(a[i].alloc(ctx, nb, n));
+      return STFEM_OK;
+    }
+
+    // right-preconditioned flexible GMRES(max_basis), ReductionControl(max_iter, abstol, reduce)
+    int solve(stfem_op *A, MGBase *M, void *const *x_blocks, const void *const *b_blocks, int max_basis, int max_iter, double abstol,
+              double reduce, FgmresResult &res)
+    {
+      ctx = A->mesh->ctx;
+      const int       nb = A->nb_rows;
+      const long long n  = A->N;
+      STFEM_REQUIRE(A->number_type == STFEM_F64, "fgmres: the outer operator must be double precision");
+      if (!x.d || x.nb != nb || x.n != n)
+        {
+          STFEM_FORWARD(x.alloc(ctx, nb, n));
+          STFEM_FORWARD(b.alloc(ctx, nb, n));
+          STFEM_FORWARD(w.alloc(ctx, nb, n));
+        }
+      for (int k = 0; k < nb; ++k)
+        {
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(x.d + (size_t)k * n, x_blocks[k], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(b.d + (size_t)k * n, b_blocks[k], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+      auto apply_A = [&](BlockVec<double> &dst, const BlockVec<double> &src) {
+        return op_apply(A, dst.block_ptrs(), src.cblock_ptrs(), nb, nb, A->d_alpha, A->d_beta, true);
+      };
+      res = FgmresResult();
+      double tol = 0;
+      bool   first = true;
+      std::vector<double> H((size_t)(max_basis + 1) * max_basis), g(max_basis + 1), cs(max_basis), sn(max_basis), h(max_basis + 2);
+      auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * max_basis + j]; };
+      while (true)
+        {
+          // r = b - A x
+          STFEM_FORWARD(ensure(V, 0, nb, n));
+          STFEM_FORWARD(apply_A(V[0], x));
+          v_sadd(V[0], -1.0, 1.0, b);
+          double beta2 = 0;
+          STFEM_FORWARD(v_dot(sc, V[0], V[0], &beta2));
+          const double beta = std::sqrt(beta2);
+          if (!std::isfinite(beta))
+            {
+              set_error("fgmres: residual is not finite");
+              return STFEM_ERR_NO_CONVERGENCE;
+            }
+          if (first)
+            {
+              res.initial_residual = beta;
+              res.final_residual   = beta;
+              tol                  = std::max(abstol, reduce * beta);
+              first                = false;
+              if (beta <= tol)
+                {
+                  res.converged = true;
+                  break;
+                }
+            }
+          v_scale(V[0], 1.0 / beta);
+          std::fill(H.begin(), H.end(), 0.0);
+          std::fill(g.begin(), g.end(), 0.0);
+          g[0]       = beta;
+          int  jdone = 0;
+          bool stop  = false;
+          for (int j = 0; j < max_basis; ++j)
+            {
+              STFEM_FORWARD(ensure(Z, j, nb, n));
+              STFEM_FORWARD(ensure(V, j + 1, nb, n));
+              if (M)
+                STFEM_FORWARD(M->vmult(Z[j].block_ptrs(), V[j].cblock_ptrs()));
+              else
+                STFEM_FORWARD(v_copy(Z[j], V[j]));
+              STFEM_FORWARD(apply_A(w, Z[j]));
+              // classical Gram-Schmidt, one re-orthogonalisation pass; every pass = one fused multi-dot
+              // (all h_ij and ||w||^2 in one sweep over w) and one fused multi-axpy
+              std::vector<const BlockVec<double> *> basis;
+              for (int i = 0; i <= j; ++i) basis.push_back(&V[i]);
+              double wnorm2 = 0;
+              for (int pass = 0; pass < 2; ++pass)
+                {
+                  std::vector<const BlockVec<double> *> q = basis;
+                  q.push_back(&w);
+                  STFEM_FORWARD(v_multi_dot(sc, w, q, h.data()));
+                  std::vector<double> c(j + 1);
+                  double              sub = 0;
+                  for (int i = 0; i <= j; ++i)
+                    {
+                      c[i] = -h[i];
+                      Hm(i, j) += h[i];
+                      sub += h[i] * h[i];
+                    }
+                  v_multi_axpy(w, basis, c.data());
+                  wnorm2 = h[j + 1] - sub;
+                }
+              // the subtraction above loses accuracy when w is almost in the span: recompute the norm
+              STFEM_FORWARD(v_dot(sc, w, w, &wnorm2));
+              const double hn = std::sqrt(std::max(wnorm2, 0.0));
+              Hm(j + 1, j)    = hn;
+              if (hn != 0.0)
+                {
+                  STFEM_FORWARD(v_copy(V[j + 1], w));
+                  v_scale(V[j + 1], 1.0 / hn);
+                }
+              for (int i = 0; i < j; ++i)
+                {
+                  const double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);
+                  Hm(i + 1, j)   = -sn[i] * Hm(i, j) + cs[i] * Hm(i + 1, j);
+                  Hm(i, j)       = t;
+                }
+              const double den = std::hypot(Hm(j, j), Hm(j + 1, j));
+              cs[j] = Hm(j, j) / den;
+              sn[j] = Hm(j + 1, j) / den;
+              Hm(j, j)     = den;
+              Hm(j + 1, j) = 0.0;
+              g[j + 1]     = -sn[j] * g[j];
+              g[j]         = cs[j] * g[j];
+              res.iterations++;
+              jdone              = j + 1;
+              res.final_residual = std::fabs(g[j + 1]);
+              if (res.final_residual <= tol)
+                {
+                  res.converged = true;
+                  stop          = true;
+                }
+              if (res.iterations >= max_iter) stop = true;
+              if (stop) break;
+            }
+          // back substitution and solution update x += sum_j y_j z_j (one fused multi-axpy)
+          std::vector<double> y(jdone);
+          for (int i = jdone - 1; i >= 0; --i)
+            {
+              double s = g[i];
+              for (int k = i + 1; k < jdone; ++k) s -= Hm(i, k) * y[k];
+              y[i] = s / Hm(i, i);
+            }
+          std::vector<const BlockVec<double> *> zs;
+          for (int i = 0; i < jdone; ++i) zs.push_back(&Z[i]);
+          v_multi_axpy(x, zs, y.data());
+          if (res.converged || res.iterations >= max_iter) break;
+        }
+      for (int k = 0; k < nb; ++k)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(x_blocks[k], x.d + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      if (!res.converged)
+        {
+          set_error("fgmres: no convergence after %d iterations (residual %.3e, tolerance %.3e)", res.iterations, res.final_residual, tol);
+          return STFEM_ERR_NO_CONVERGENCE;
+        }
+      return STFEM_OK;
+    }
+  };
+} // namespace stfem

@@ -14,6 +14,7 @@ struct stfem_op
   void *d_alpha = nullptr, *d_beta = nullptr, *d_alphaT = nullptr, *d_betaT = nullptr;
   void *d_metric = nullptr; // general geometry: per cell, per q-point metric (+JxW)
   void *d_coeff = nullptr;  // per-cell Laplace coefficient
+  std::vector<double> h_coeff_cell, h_coeff_q; // host copies (Vanka set-up works in double)
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points
   bool  timing = false;
   float last_ms = 0.f;

@@ -1,0 +1,245 @@
+// Two-level transfer operators of the space-time multigrid.
+//   SpaceTransfer : deal.II MGTwoLevelTransfer as used by MGTwoLevelBlockTransfer
+//                   (reference include/stmg.h:38-112, built at :594-602): nodal embedding of FE_Q between a
+//                   coarse and a fine level (h: every cell split in 2^dim, p: degree change on the same mesh),
+//                   restriction = exact transpose, constrained DoFs excluded.
+//                   Tensor-product structure: one 1D pass per direction, all time blocks in one launch,
+//                   no index tables, no atomics (every output entry is produced by exactly one thread).
+//   TimeTransfer  : MGTwoLevelTransferTime (stmg.h:114-247): small dense matrix across the time blocks,
+//                   one streaming pass (the reference does nnz(P) vector updates, operators.h:252-265).
+#pragma once
+#include "basis_host.hpp"
+#include "fe_time.hpp"
+#include "vec.cuh"
+
+namespace stfem
+{
+  constexpr int TR_MAX_F = 13; // fine local nodes per coarse cell (2*6+1)
+  constexpr int TR_MAX_C = 7;
+
+  template <typename T>
+  struct Transfer1D
+  {
+    T   P[TR_MAX_F * TR_MAX_C]; // P[lf * nc_loc + a]
+    int sf, sc;                 // fine / coarse DoF strides per coarse cell
+    int n_cells;                // coarse cells in this direction
+  };
+
+  // One tensor direction.  Array layout [blocks][n2][n1][n0] with the transfer acting on axis `axis`;
+  // sizes given for the OUTPUT array (out_n) and the input extent along the axis (in_len).
+  // mode 0: prolongation (out fine), 1: restriction (out coarse).  final: add into out and apply `mask`.
+  template <typename T>
+  __global__ void k_transfer_1d(Transfer1D<T> tr, int mode, int axis, int on0, int on1, int on2, int in_len, long long blocks,
+                                const T *__restrict__ in, T *__restrict__ out, int final_add, unsigned dirichlet, int dim)
+  {
+    const long long out_per_block = (long long)on0 * on1 * on2;
+    const long long total         = out_per_block * blocks;
+    const int       nc_loc        = tr.sc + 1;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const long long b  = gid / out_per_block;
+        long long       r  = gid % out_per_block;
+        const int       i0 = (int)(r % on0);
+        r /= on0;
+        const int i1 = (int)(r % on1);
+        const int i2 = (int)(r / on1);
+        int       idx[3] = {i0, i1, i2};
+        const int o      = idx[axis];
+        // input strides: same as output except along axis
+        const int       in0 = axis == 0 ? in_len : on0, in1 = axis == 1 ? in_len : on1, in2 = axis == 2 ? in_len : on2;
+        const long long in_per_block = (long long)in0 * in1 * in2;
+        const long long stride       = axis == 0 ? 1 : (axis == 1 ? in0 : (long long)in0 * in1);
+        idx[axis]                    = 0;
+        const T *src = in + b * in_per_block + (long long)idx[0] + (long long)in0 * (idx[1] + (long long)in1 * idx[2]);
+        T        s   = 0;
+        if (mode == 0)
+          {
+            int c = o / tr.sf;
+            if (c > tr.n_cells - 1) c = tr.n_cells - 1;
+            const int lf = o - c * tr.sf;
+            for (int a = 0; a < nc_loc; ++a) s += tr.P[lf * nc_loc + a] * src[stride * (c * tr.sc + a)];
+          }
+        else
+          {
+            int c_hi = o / tr.sc;
+            int c_lo = (o % tr.sc == 0) ? c_hi - 1 : c_hi;
+            if (c_lo < 0) c_lo = 0;
+            if (c_hi > tr.n_cells - 1) c_hi = tr.n_cells - 1;
+            for (int c = c_lo; c <= c_hi; ++c)
+              {
+                const int a      = o - c * tr.sc;
+                const int lf_end = (c == tr.n_cells - 1) ? tr.sf : tr.sf - 1; // owned fine nodes of cell c
+                for (int lf = 0; lf <= lf_end; ++lf) s += tr.P[lf * nc_loc + a] * src[stride * (c * tr.sf + lf)];
+              }
+          }
+        if (final_add)
+          {
+            bool con = false;
+            if (((dirichlet >> 0) & 1u) && i0 == 0) con = true;
+            if (((dirichlet >> 1) & 1u) && i0 == on0 - 1) con = true;
+            if (((dirichlet >> 2) & 1u) && i1 == 0) con = true;
+            if (((dirichlet >> 3) & 1u) && i1 == on1 - 1) con = true;
+            if (dim == 3)
+              {
+                if (((dirichlet >> 4) & 1u) && i2 == 0) con = true;
+                if (((dirichlet >> 5) & 1u) && i2 == on2 - 1) con = true;
+              }
+            if (!con) out[gid] += s;
+          }
+        else
+          out[gid] = s;
+      }
+  }
+
+  template <typename T>
+  struct SpaceTransfer
+  {
+    stfem_ctx    *ctx = nullptr;
+    int           dim = 3;
+    int           npf[3] = {1, 1, 1}, npc[3] = {1, 1, 1};
+    unsigned      dirichlet = 0;
+    Transfer1D<T> tr[3];
+    BlockVec<T>   tmp1, tmp2;
+    int           nb_alloc = 0;
+
+    // coarse: n_cells_c, degree kc ; fine: n_cells_f, degree kf
+    int init(stfem_ctx *c, int dim_, const int *ncell_c, int kc, const int *ncell_f, int kf, unsigned dirichlet_)
+    {
+      ctx = c; dim = dim_; dirichlet = dirichlet_;
+      const bool h = ncell_f[0] == 2 * ncell_c[0];
+      STFEM_REQUIRE(h ? (kc == kf) : (ncell_f[0] == ncell_c[0] && kf >= kc), "space transfer: levels are neither h- nor p-related");
+      STFEM_REQUIRE(kf <= 6 && kc <= 6, "space transfer: degree > 6");
+      const auto gc = gauss_lobatto(kc + 1).x, gf = gauss_lobatto(kf + 1).x;
+      for (int d = 0; d < 3; ++d)
+        {
+          npf[d] = d < dim ? kf * ncell_f[d] + 1 : 1;
+          npc[d] = d < dim ? kc * ncell_c[d] + 1 : 1;
+          if (d >= dim) continue;
+          if (h) STFEM_REQUIRE(ncell_f[d] == 2 * ncell_c[d], "space transfer: anisotropic refinement");
+          Transfer1D<T> &t = tr[d];
+          t.n_cells = ncell_c[d];
+          t.sc      = kc;
+          t.sf      = h ? 2 * kf : kf;
+          const int nc_loc = kc + 1;
+          for (int lf = 0; lf <= t.sf; ++lf)
+            {
+              // position of the fine node in the coarse cell
+              double x;
+              if (h)
+                {
+                  const int child = lf < kf ? 0 : 1;
+                  const int i     = lf - child * kf;
+                  x               = 0.5 * (gf[i] + child);
+                  if (lf == 2 * kf) x = 1.0;
+                }
+              else
+                x = gf[lf];
+              for (int a = 0; a < nc_loc; ++a)
+                {
+                  double v = lagrange_value(gc, a, x);
+                  if (std::fabs(v) < 1e-15) v = 0.0;
+                  t.P[lf * nc_loc + a] = (T)v;
+                }
+            }
+        }
+      return STFEM_OK;
+    }
+
+    int ensure_tmp(int nb)
+    {
+      if (nb <= nb_alloc) return STFEM_OK;
+      const long long nf = (long long)npf[0] * npf[1] * npf[2];
+      STFEM_FORWARD(tmp1.alloc(ctx, nb, nf));
+      STFEM_FORWARD(tmp2.alloc(ctx, nb, nf));
+      nb_alloc = nb;
+      return STFEM_OK;
+    }
+
+    void launch(int mode, int axis, const int *on, int in_len, int nb, const T *in, T *out, bool fin)
+    {
+      const long long total = (long long)on[0] * on[1] * on[2] * nb;
+      k_transfer_1d<T><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(tr[axis], mode, axis, on[0], on[1], on[2], in_len, nb, in,
+                                                                            out, fin ? 1 : 0, dirichlet, dim);
+      ctx->launches++;
+    }
+
+    // fine += P coarse
+    int prolongate_and_add(BlockVec<T> &fine, const BlockVec<T> &coarse)
+    {
+      const int nb = coarse.nb;
+      STFEM_FORWARD(ensure_tmp(nb));
+      int       on[3] = {npf[0], npc[1], npc[2]};
+      const T  *in    = coarse.d;
+      T        *bufs[2] = {tmp1.d, tmp2.d};
+      for (int d = 0; d < dim; ++d)
+        {
+          for (int e = 0; e < 3; ++e) on[e] = e <= d ? npf[e] : npc[e];
+          const bool fin = d == dim - 1;
+          T         *out = fin ? fine.d : bufs[d & 1];
+          launch(0, d, on, npc[d], nb, in, out, fin);
+          in = out;
+        }
+      return STFEM_OK;
+    }
+
+    // coarse += P^T fine
+    int restrict_and_add(BlockVec<T> &coarse, const BlockVec<T> &fine)
+    {
+      const int nb = fine.nb;
+      STFEM_FORWARD(ensure_tmp(nb));
+      int      on[3];
+      const T *in = fine.d;
+      T       *bufs[2] = {tmp1.d, tmp2.d};
+      int      step = 0;
+      for (int d = dim - 1; d >= 0; --d, ++step)
+        {
+          for (int e = 0; e < 3; ++e) on[e] = e >= d ? npc[e] : npf[e];
+          const bool fin = d == 0;
+          T         *out = fin ? coarse.d : bufs[step & 1];
+          launch(1, d, on, npf[d], nb, in, out, fin);
+          in = out;
+        }
+      return STFEM_OK;
+    }
+  };
+
+  template <typename T>
+  struct TimeTransfer
+  {
+    std::vector<double> P, R; // P: nb_hi x nb_lo, R: nb_lo x nb_hi
+    int                 nb_hi = 0, nb_lo = 0;
+
+    // type: CGP/DG ; (nts_hi, nd_hi) / (nts_lo, nd_lo) block structure (get_blk_indices, stmg.h:460-501)
+    int init(int type, int nts_hi, int nd_hi, int nts_lo, int nd_lo, bool restrict_is_transpose_prolongate, char mg_type)
+    {
+      const int r = type == DG ? nd_hi - 1 : nd_hi, r_lo = type == DG ? nd_lo - 1 : nd_lo;
+      Mat       Pm, down;
+      try
+        {
+          if (mg_type == 'k')
+            {
+              Pm   = time_projection_matrix(type, r_lo, r, nts_hi);
+              down = time_projection_matrix(type, r, r_lo, nts_hi);
+            }
+          else
+            {
+              Pm   = time_prolongation_matrix(type, r, nts_hi);
+              down = time_restriction_matrix(type, r, nts_hi);
+            }
+        }
+      catch (const std::exception &e)
+        {
+          set_error("time transfer: %s", e.what());
+          return STFEM_ERR_INVALID;
+        }
+      nb_hi = Pm.m; nb_lo = Pm.n;
+      STFEM_REQUIRE(nb_hi == nts_hi * nd_hi && nb_lo == nts_lo * nd_lo, "time transfer: block structure mismatch (%d x %d vs %d, %d)",
+                    nb_hi, nb_lo, nts_hi * nd_hi, nts_lo * nd_lo);
+      P = Pm.a;
+      R = restrict_is_transpose_prolongate ? Pm.transposed().a : down.a;
+      return STFEM_OK;
+    }
+    void prolongate_and_add(BlockVec<T> &hi, const BlockVec<T> &lo) { v_block_matmul(hi, P, nb_hi, nb_lo, lo, true); }
+    void restrict_and_add(BlockVec<T> &lo, const BlockVec<T> &hi) { v_block_matmul(lo, R, nb_lo, nb_hi, hi, true); }
+  };
+} // namespace stfem

@@ -1,0 +1,433 @@
+// Cell-patch additive Schwarz smoother ("Vanka" / block Jacobi).
+// Replaces PreconditionVanka of the reference (include/stmg.h:745-872) and the patch extraction
+// restrict_to_full_matrices_ (include/compute_block_matrix.h:50-139):
+//   per cell  B_c = Beta (x) M_c + Alpha (x) K_c,  where K_c, M_c are the ASSEMBLED matrices restricted to the
+//   cell's DoFs (contributions of the neighbouring cells on shared DoFs included), rows scaled by the valence
+//   of the row DoF; stored inverse; apply = gather -> dense matvec -> scatter-add.
+// Here the patch matrices are built matrix-free on the device (no sparse matrix is ever assembled), the
+// (nb*n_c)^2 inverses come from a batched Gauss-Jordan kernel in double precision, and on Cartesian meshes
+// with constant coefficients only the <= 3^dim distinct patches are stored (the reference stores one per cell).
+#pragma once
+#include "op.hpp"
+#include "vec.cuh"
+
+namespace stfem
+{
+  struct VankaGeom
+  {
+    int       dim, n1;
+    int       n[3], np[3];
+    long long n_cells;
+    unsigned  dirichlet;
+    double    h[3];
+    const double *metric; // general: per cell per q (nsym+1) doubles (coefficient folded in), else null
+    const double *coeff_cell;
+    double        S[49], D[49], w[7]; // 1D shape values / derivatives at Gauss points [q*n1+i], weights
+  };
+
+  __device__ inline bool vk_constrained(const VankaGeom &g, int ix, int iy, int iz)
+  {
+    const unsigned d = g.dirichlet;
+    if ((d & 1u) && ix == 0) return true;
+    if ((d & 2u) && ix == g.np[0] - 1) return true;
+    if ((d & 4u) && iy == 0) return true;
+    if ((d & 8u) && iy == g.np[1] - 1) return true;
+    if (g.dim == 3)
+      {
+        if ((d & 16u) && iz == 0) return true;
+        if ((d & 32u) && iz == g.np[2] - 1) return true;
+      }
+    return false;
+  }
+
+  // K_c'(i,j), M_c'(i,j) of one cell by quadrature
+  __device__ inline void vk_cell_entry(const VankaGeom &g, long long cell, const int *li, const int *lj, double &Kij, double &Mij)
+  {
+    const int n1 = g.n1, dim = g.dim;
+    const int nq = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    const int nsym = dim * (dim + 1) / 2;
+    double    k = 0, m = 0;
+    const double coef = g.coeff_cell ? g.coeff_cell[cell] : 1.0;
+    const double vol  = g.h[0] * g.h[1] * (dim == 3 ? g.h[2] : 1.0);
+    for (int q = 0; q < nq; ++q)
+      {
+        const int qx = q % n1, qy = (q / n1) % n1, qz = dim == 3 ? q / (n1 * n1) : 0;
+        const double six = g.S[qx * n1 + li[0]], siy = g.S[qy * n1 + li[1]], siz = dim == 3 ? g.S[qz * n1 + li[2]] : 1.0;
+        const double sjx = g.S[qx * n1 + lj[0]], sjy = g.S[qy * n1 + lj[1]], sjz = dim == 3 ? g.S[qz * n1 + lj[2]] : 1.0;
+        const double dix = g.D[qx * n1 + li[0]], diy = g.D[qy * n1 + li[1]], diz = dim == 3 ? g.D[qz * n1 + li[2]] : 0.0;
+        const double djx = g.D[qx * n1 + lj[0]], djy = g.D[qy * n1 + lj[1]], djz = dim == 3 ? g.D[qz * n1 + lj[2]] : 0.0;
+        const double gi[3] = {dix * siy * siz, six * diy * siz, six * siy * diz};
+        const double gj[3] = {djx * sjy * sjz, sjx * djy * sjz, sjx * sjy * djz};
+        const double vi = six * siy * siz, vj = sjx * sjy * sjz;
+        if (g.metric)
+          {
+            const double *mt = g.metric + ((size_t)cell * nq + q) * (nsym + 1);
+            m += mt[nsym] * vi * vj;
+            if (dim == 2)
+              k += coef * (gi[0] * (mt[0] * gj[0] + mt[1] * gj[1]) + gi[1] * (mt[1] * gj[0] + mt[2] * gj[1]));
+            else
+              k += coef * (gi[0] * (mt[0] * gj[0] + mt[1] * gj[1] + mt[2] * gj[2]) + gi[1] * (mt[1] * gj[0] + mt[3] * gj[1] + mt[4] * gj[2]) +
+                           gi[2] * (mt[2] * gj[0] + mt[4] * gj[1] + mt[5] * gj[2]));
+          }
+        else
+          {
+            const double wq = vol * g.w[qx] * g.w[qy] * (dim == 3 ? g.w[qz] : 1.0);
+            m += wq * vi * vj;
+            double s = 0;
+            for (int d = 0; d < dim; ++d) s += gi[d] * gj[d] / (g.h[d] * g.h[d]);
+            k += coef * wq * s;
+          }
+      }
+    Kij = k; Mij = m;
+  }
+
+  // one thread per (patch, i, j): assembled patch entry incl. neighbour contributions, valence scaling,
+  // constraint handling, then the nb x nb time blocks of B (row-major double, ld = nb*nc)
+  __global__ void k_vanka_build(VankaGeom g, const long long *__restrict__ cells, int n_patches, int nb, const double *__restrict__ alpha,
+                                const double *__restrict__ beta, double *__restrict__ B)
+  {
+    const int n1 = g.n1, dim = g.dim, k = n1 - 1;
+    const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    const long long total = (long long)n_patches * nc * nc;
+    const int       ld    = nb * nc;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const int       pidx = (int)(gid / ((long long)nc * nc));
+        const int       ij   = (int)(gid % ((long long)nc * nc));
+        const int       i = ij / nc, j = ij % nc;
+        const long long cell = cells[pidx];
+        const int c[3] = {(int)(cell % g.n[0]), (int)((cell / g.n[0]) % g.n[1]), dim == 3 ? (int)(cell / ((long long)g.n[0] * g.n[1])) : 0};
+        const int li[3] = {i % n1, (i / n1) % n1, dim == 3 ? i / (n1 * n1) : 0};
+        const int lj[3] = {j % n1, (j / n1) % n1, dim == 3 ? j / (n1 * n1) : 0};
+        const int gi[3] = {c[0] * k + li[0], c[1] * k + li[1], c[2] * k + li[2]};
+        const int gj[3] = {c[0] * k + lj[0], c[1] * k + lj[1], c[2] * k + lj[2]};
+        const bool ci = vk_constrained(g, gi[0], gi[1], gi[2]), cj = vk_constrained(g, gj[0], gj[1], gj[2]);
+        double Kp = 0, Mp = 0, valence = 1;
+        // allowed neighbour offsets per direction
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int d = 0; d < dim; ++d)
+          {
+            if (li[d] == 0 && lj[d] == 0 && c[d] > 0) lo[d] = -1;
+            if (li[d] == k && lj[d] == k && c[d] < g.n[d] - 1) hi[d] = 1;
+            if ((li[d] == 0 && c[d] > 0) || (li[d] == k && c[d] < g.n[d] - 1)) valence *= 2;
+          }
+        if ((ci || cj) && i != j)
+          {
+            Kp = 0; Mp = 0;
+          }
+        else
+          {
+            for (int oz = lo[2]; oz <= hi[2]; ++oz)
+              for (int oy = lo[1]; oy <= hi[1]; ++oy)
+                for (int ox = lo[0]; ox <= hi[0]; ++ox)
+                  {
+                    const int o[3] = {ox, oy, oz};
+                    int       a[3], b[3];
+                    for (int d = 0; d < 3; ++d)
+                      {
+                        a[d] = o[d] == 0 ? li[d] : (o[d] < 0 ? k : 0);
+                        b[d] = o[d] == 0 ? lj[d] : (o[d] < 0 ? k : 0);
+                      }
+                    const long long nc_cell = (long long)(c[0] + ox) + (long long)g.n[0] * ((c[1] + oy) + (long long)g.n[1] * (c[2] + oz));
+                    double kk, mm;
+                    vk_cell_entry(g, nc_cell, a, b, kk, mm);
+                    if (ci) { kk = fabs(kk); mm = fabs(mm); }
+                    Kp += kk; Mp += mm;
+                  }
+          }
+        double *Bp = B + (size_t)pidx * ld * ld;
+        for (int a = 0; a < nb; ++a)
+          for (int b = 0; b < nb; ++b)
+            Bp[(size_t)(i + a * nc) * ld + (j + b * nc)] = valence * (beta[a * nb + b] * Mp + alpha[a * nb + b] * Kp);
+      }
+  }
+
+  // in-place Gauss-Jordan inverse with partial pivoting, one CTA per matrix (FullMatrix::gauss_jordan)
+  __global__ void k_batched_inverse(double *__restrict__ A, int n, int *__restrict__ perm_ws, int *__restrict__ info)
+  {
+    double *M    = A + (size_t)blockIdx.x * n * n;
+    int    *perm = perm_ws + (size_t)blockIdx.x * n;
+    __shared__ double s_val[256];
+    __shared__ int    s_idx[256];
+    __shared__ double s_piv;
+    extern __shared__ double s_col[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int kcol = 0; kcol < n; ++kcol)
+      {
+        double best = -1;
+        int    bi   = kcol;
+        for (int r = kcol + tid; r < n; r += nt)
+          {
+            const double v = fabs(M[(size_t)r * n + kcol]);
+            if (v > best) { best = v; bi = r; }
+          }
+        s_val[tid] = best; s_idx[tid] = bi;
+        __syncthreads();
+        for (int s = nt / 2; s > 0; s >>= 1)
+          {
+            if (tid < s && s_val[tid + s] > s_val[tid]) { s_val[tid] = s_val[tid + s]; s_idx[tid] = s_idx[tid + s]; }
+            __syncthreads();
+          }
+        const int p = s_idx[0];
+        if (tid == 0)
+          {
+            perm[kcol] = p;
+            if (s_val[0] == 0.0) atomicExch(info, 1 + (int)blockIdx.x);
+          }
+        if (p != kcol)
+          for (int cidx = tid; cidx < n; cidx += nt)
+            {
+              const double t = M[(size_t)kcol * n + cidx];
+              M[(size_t)kcol * n + cidx] = M[(size_t)p * n + cidx];
+              M[(size_t)p * n + cidx]    = t;
+            }
+        __syncthreads();
+        if (tid == 0)
+          {
+            s_piv = M[(size_t)kcol * n + kcol];
+            M[(size_t)kcol * n + kcol] = 1.0;
+          }
+        __syncthreads();
+        const double ip = 1.0 / s_piv;
+        for (int cidx = tid; cidx < n; cidx += nt) M[(size_t)kcol * n + cidx] *= ip;
+        __syncthreads();
+        // eliminate all other rows at once: the pivot column is staged in shared memory first
+        for (int r = tid; r < n; r += nt) s_col[r] = M[(size_t)r * n + kcol];
+        __syncthreads();
+        for (long long e = tid; e < (long long)n * n; e += nt)
+          {
+            const int r = (int)(e / n), cidx = (int)(e % n);
+            if (r == kcol) continue;
+            const double f = s_col[r];
+            if (f != 0.0) M[e] = (cidx == kcol ? 0.0 : M[e]) - f * M[(size_t)kcol * n + cidx];
+          }
+        __syncthreads();
+      }
+    // undo the row interchanges as column interchanges in reverse order
+    for (int kcol = n - 1; kcol >= 0; --kcol)
+      {
+        const int p = perm[kcol];
+        if (p != kcol)
+          for (int r = tid; r < n; r += nt)
+            {
+              const double t = M[(size_t)r * n + kcol];
+              M[(size_t)r * n + kcol] = M[(size_t)r * n + p];
+              M[(size_t)r * n + p]    = t;
+            }
+        __syncthreads();
+      }
+  }
+
+  // store the inverse transposed (column-major) in the level precision: invT[c*n + r] = inv[r][c]
+  template <typename T>
+  __global__ void k_store_inverse_T(const double *__restrict__ A, int n, long long n_mat, T *__restrict__ out)
+  {
+    const long long total = n_mat * n * n;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const long long mtx = gid / ((long long)n * n);
+        const int       rc  = (int)(gid % ((long long)n * n));
+        const int       cidx = rc / n, r = rc % n;
+        out[gid] = (T)A[(size_t)mtx * n * n + (size_t)r * n + cidx];
+      }
+  }
+
+  struct VankaApplyArgs
+  {
+    int       dim, n1, nb;
+    int       n[3], np[3];
+    long long n_cells, N;
+    int       dedup;        // 1: matrix index from the position class of the cell (type_to_mat), 0: one per cell
+    int       type_to_mat[27];
+  };
+
+  // dst += R_c^T B_c^-1 R_c src   for every cell; one CTA per cell, one thread per patch row
+  template <typename T>
+  __global__ void k_vanka_apply(VankaApplyArgs a, const T *__restrict__ invT, const T *__restrict__ src, T *__restrict__ dst)
+  {
+    extern __shared__ __align__(16) unsigned char vk_smem[];
+    T            *x  = reinterpret_cast<T *>(vk_smem);
+    const int     n1 = a.n1, k = n1 - 1, dim = a.dim;
+    const int     nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    const int     nrow = a.nb * nc;
+    for (long long cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x)
+      {
+        const int c[3] = {(int)(cell % a.n[0]), (int)((cell / a.n[0]) % a.n[1]), dim == 3 ? (int)(cell / ((long long)a.n[0] * a.n[1])) : 0};
+        long long mat  = cell;
+        if (a.dedup)
+          {
+            int t = 0, mul = 1;
+            for (int d = 0; d < dim; ++d)
+              {
+                const int cls = a.n[d] == 1 ? 0 : (c[d] == 0 ? 0 : (c[d] == a.n[d] - 1 ? 2 : 1));
+                t += cls * mul;
+                mul *= 3;
+              }
+            mat = a.type_to_mat[t];
+          }
+        const T *Bm = invT + (size_t)mat * nrow * nrow;
+        __syncthreads();
+        for (int r = threadIdx.x; r < nrow; r += blockDim.x)
+          {
+            const int b = r / nc, l = r % nc;
+            const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
+            const long long gi = (long long)(c[0] * k + li[0]) + (long long)a.np[0] * ((c[1] * k + li[1]) + (long long)a.np[1] * (c[2] * k + li[2]));
+            x[r] = src[(size_t)b * a.N + gi];
+          }
+        __syncthreads();
+        for (int r = threadIdx.x; r < nrow; r += blockDim.x)
+          {
+            T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int cc = 0;
+            for (; cc + 3 < nrow; cc += 4)
+              {
+                s0 += Bm[(size_t)cc * nrow + r] * x[cc];
+                s1 += Bm[(size_t)(cc + 1) * nrow + r] * x[cc + 1];
+                s2 += Bm[(size_t)(cc + 2) * nrow + r] * x[cc + 2];
+                s3 += Bm[(size_t)(cc + 3) * nrow + r] * x[cc + 3];
+              }
+            for (; cc < nrow; ++cc) s0 += Bm[(size_t)cc * nrow + r] * x[cc];
+            const T   s = (s0 + s1) + (s2 + s3);
+            const int b = r / nc, l = r % nc;
+            const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
+            const long long gi = (long long)(c[0] * k + li[0]) + (long long)a.np[0] * ((c[1] * k + li[1]) + (long long)a.np[1] * (c[2] * k + li[2]));
+            atomicAdd(dst + (size_t)b * a.N + gi, s);
+          }
+      }
+  }
+
+  template <typename T>
+  struct Vanka
+  {
+    stfem_op      *op = nullptr;
+    T             *d_invT = nullptr;
+    long long      n_mat = 0;
+    int            nrow = 0;
+    VankaApplyArgs args;
+    size_t         bytes = 0;
+
+    ~Vanka() { if (d_invT) cudaFree(d_invT); }
+
+    int setup(stfem_op *op_);
+    // dst = sum_c R_c^T B_c^-1 R_c src   (stmg.h:832-872; dst zeroed first)
+    int vmult(BlockVec<T> &dst, const BlockVec<T> &src)
+    {
+      stfem_ctx *ctx = op->mesh->ctx;
+      STFEM_FORWARD(dst.zero());
+      const int threads = nrow < 64 ? 64 : (nrow > 256 ? 256 : ((nrow + 31) / 32) * 32);
+      const long long cap = (long long)ctx->sm_count * 16;
+      const int grid = (int)(args.n_cells < cap ? args.n_cells : cap);
+      k_vanka_apply<T><<<grid, threads, sizeof(T) * nrow, ctx->stream>>>(args, d_invT, src.d, dst.d);
+      ctx->launches++;
+      STFEM_CUDA_CHECK(cudaGetLastError());
+      return STFEM_OK;
+    }
+  };
+
+  int metric_double(stfem_op *op, double **out); // capi_op.cu: double metric incl. per-q coefficient (caller frees)
+
+  template <typename T>
+  int Vanka<T>::setup(stfem_op *op_)
+  {
+    op = op_;
+    stfem_mesh *m   = op->mesh;
+    stfem_ctx  *ctx = m->ctx;
+    STFEM_REQUIRE(op->nb_rows == op->nb_cols, "Vanka: operator must be square in time");
+    const int dim = m->dim, n1 = op->degree + 1, nb = op->nb_rows;
+    const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    nrow         = nb * nc;
+    VankaGeom g;
+    g.dim = dim; g.n1 = n1; g.n_cells = m->n_cells; g.dirichlet = m->dirichlet;
+    for (int d = 0; d < 3; ++d)
+      {
+        g.n[d]  = m->n[d];
+        g.np[d] = op->np[d];
+        g.h[d]  = d < dim ? (m->upper[d] - m->lower[d]) / m->n[d] : 1.0;
+      }
+    for (int q = 0; q < n1 * n1; ++q) { g.S[q] = op->shape->S[q]; g.D[q] = op->shape->D[q]; }
+    for (int q = 0; q < n1; ++q) g.w[q] = op->shape->wq[q];
+    const bool general = op->d_metric != nullptr;
+    const bool dedup   = !general && op->h_coeff_cell.empty();
+    double    *d_metric = nullptr, *d_coeff = nullptr;
+    if (general) STFEM_FORWARD(metric_double(op, &d_metric));
+    g.metric = d_metric;
+    if (!op->h_coeff_cell.empty())
+      {
+        STFEM_CUDA_CHECK(cudaMalloc(&d_coeff, sizeof(double) * m->n_cells));
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_coeff, op->h_coeff_cell.data(), sizeof(double) * m->n_cells, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    g.coeff_cell = d_coeff;
+    // patch list
+    std::vector<long long> cells;
+    args.dedup = dedup ? 1 : 0;
+    for (int t = 0; t < 27; ++t) args.type_to_mat[t] = -1;
+    if (dedup)
+      {
+        const int ntz = dim == 3 ? 3 : 1;
+        for (int tz = 0; tz < ntz; ++tz)
+          for (int ty = 0; ty < 3; ++ty)
+            for (int tx = 0; tx < 3; ++tx)
+              {
+                const int t[3] = {tx, ty, tz};
+                bool      ok   = true;
+                long long c[3] = {0, 0, 0};
+                for (int d = 0; d < dim; ++d)
+                  {
+                    const int nd = m->n[d];
+                    if (t[d] == 0) c[d] = 0;
+                    else if (t[d] == 2) { if (nd < 2) ok = false; c[d] = nd - 1; }
+                    else { if (nd < 3) ok = false; c[d] = 1; }
+                  }
+                if (!ok) continue;
+                args.type_to_mat[tx + 3 * (ty + 3 * tz)] = (int)cells.size();
+                cells.push_back(c[0] + (long long)m->n[0] * (c[1] + (long long)m->n[1] * c[2]));
+              }
+      }
+    else
+      {
+        cells.resize(m->n_cells);
+        for (long long c = 0; c < m->n_cells; ++c) cells[c] = c;
+      }
+    n_mat = (long long)cells.size();
+    bytes = sizeof(T) * (size_t)n_mat * nrow * nrow;
+    STFEM_CUDA_CHECK(cudaMalloc(&d_invT, bytes));
+    double *d_alpha = nullptr, *d_beta = nullptr;
+    STFEM_CUDA_CHECK(cudaMalloc(&d_alpha, sizeof(double) * nb * nb));
+    STFEM_CUDA_CHECK(cudaMalloc(&d_beta, sizeof(double) * nb * nb));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(d_alpha, op->Alpha.data(), sizeof(double) * nb * nb, cudaMemcpyHostToDevice, ctx->stream));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(d_beta, op->Beta.data(), sizeof(double) * nb * nb, cudaMemcpyHostToDevice, ctx->stream));
+    // chunks of patches so the double work matrices stay below ~1.5 GB
+    const size_t per = sizeof(double) * (size_t)nrow * nrow;
+    long long    chunk = (long long)((1500ull << 20) / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_mat) chunk = n_mat;
+    double    *d_B = nullptr;
+    long long *d_cells = nullptr;
+    int       *d_perm = nullptr, *d_info = nullptr;
+    STFEM_CUDA_CHECK(cudaMalloc(&d_B, per * chunk));
+    STFEM_CUDA_CHECK(cudaMalloc(&d_cells, sizeof(long long) * chunk));
+    STFEM_CUDA_CHECK(cudaMalloc(&d_perm, sizeof(int) * chunk * nrow));
+    STFEM_CUDA_CHECK(cudaMalloc(&d_info, sizeof(int)));
+    STFEM_CUDA_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+    for (long long c0 = 0; c0 < n_mat; c0 += chunk)
+      {
+        const long long cn = std::min(chunk, n_mat - c0);
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_cells, cells.data() + c0, sizeof(long long) * cn, cudaMemcpyHostToDevice, ctx->stream));
+        const long long total = cn * nc * nc;
+        k_vanka_build<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(g, d_cells, (int)cn, nb, d_alpha, d_beta, d_B);
+        k_batched_inverse<<<(unsigned)cn, 256, sizeof(double) * nrow, ctx->stream>>>(d_B, nrow, d_perm, d_info);
+        k_store_inverse_T<T><<<grid_for(ctx, cn * nrow * nrow, 256), 256, 0, ctx->stream>>>(d_B, nrow, cn, d_invT + (size_t)c0 * nrow * nrow);
+        ctx->launches += 3;
+        STFEM_CUDA_CHECK(cudaGetLastError());
+      }
+    int info = 0;
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (void *p : {(void *)d_B, (void *)d_cells, (void *)d_perm, (void *)d_info, (void *)d_alpha, (void *)d_beta, (void *)d_metric, (void *)d_coeff})
+      if (p) cudaFree(p);
+    STFEM_REQUIRE(info == 0, "Vanka: singular patch matrix (patch %d)", info - 1);
+    args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
+    for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }
+    return STFEM_OK;
+  }
+} // namespace stfem

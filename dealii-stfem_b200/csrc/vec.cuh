@@ -1,0 +1,277 @@
+// Device block vectors and the BLAS-1 style kernels of the Krylov / smoother updates.
+// Replaces deal.II LinearAlgebra::distributed::BlockVector operations used by the reference's hot path
+// (add/sadd/equ, dot, l2_norm; tensorproduct_add of include/operators.h:211-283; the double<->float
+// copies of GMG::vmult, include/stmg.h:1340-1342).  A block vector is ONE contiguous device array of
+// nb * N numbers (block b at offset b*N), so vector updates are single launches over nb*N entries and
+// the per-block pointers the operator ABI expects are just offsets.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "common.hpp"
+
+namespace stfem
+{
+  template <typename T>
+  struct BlockVec
+  {
+    stfem_ctx *ctx = nullptr;
+    int        nb  = 0;
+    long long  n   = 0; // entries per block
+    T         *d   = nullptr;
+    bool       owner = false;
+    std::vector<void *> ptrs; // per-block pointers (host array of device pointers)
+
+    BlockVec() = default;
+    BlockVec(const BlockVec &) = delete;
+    BlockVec &operator=(const BlockVec &) = delete;
+    BlockVec(BlockVec &&o) noexcept { *this = std::move(o); }
+    BlockVec &operator=(BlockVec &&o) noexcept
+    {
+      release();
+      ctx = o.ctx; nb = o.nb; n = o.n; d = o.d; owner = o.owner; ptrs = std::move(o.ptrs);
+      o.d = nullptr; o.owner = false;
+      return *this;
+    }
+    ~BlockVec() { release(); }
+    void release()
+    {
+      if (owner && d) cudaFree(d);
+      d = nullptr; owner = false;
+    }
+    int alloc(stfem_ctx *c, int nb_, long long n_)
+    {
+      release();
+      ctx = c; nb = nb_; n = n_;
+      STFEM_CUDA_CHECK(cudaMalloc(&d, sizeof(T) * (size_t)nb * n + 16));
+      owner = true;
+      ptrs.resize(nb);
+      for (int b = 0; b < nb; ++b) ptrs[b] = d + (size_t)b * n;
+      return zero();
+    }
+    int zero() { STFEM_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(T) * (size_t)nb * n, ctx->stream)); return STFEM_OK; }
+    long long size() const { return (long long)nb * n; }
+    void *const *block_ptrs() { return ptrs.data(); }
+    const void *const *cblock_ptrs() const { return (const void *const *)ptrs.data(); }
+  };
+
+  // ------------------------------------------------------------------ elementwise kernels
+  template <typename T>
+  __global__ void k_axpy(long long n, T a, const T *__restrict__ x, T *__restrict__ y)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      y[i] += a * x[i];
+  }
+  // y = s*y + a*x
+  template <typename T>
+  __global__ void k_sadd(long long n, T s, T a, const T *__restrict__ x, T *__restrict__ y)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      y[i] = s * y[i] + a * x[i];
+  }
+  // z = a*x + b*y
+  template <typename T>
+  __global__ void k_lincomb(long long n, T a, const T *__restrict__ x, T b, const T *__restrict__ y, T *__restrict__ z)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      z[i] = a * x[i] + b * y[i];
+  }
+  template <typename T>
+  __global__ void k_scale(long long n, T a, T *__restrict__ y)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      y[i] *= a;
+  }
+  template <typename TO, typename TI>
+  __global__ void k_convert(long long n, const TI *__restrict__ x, TO *__restrict__ y)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      y[i] = (TO)x[i];
+  }
+  // w += sum_k c[k] * V_k   (V_k = base + k*stride), coefficients by value
+  constexpr int MAXK = 16;
+  template <typename T>
+  struct MultiCoef { T c[MAXK]; const T *v[MAXK]; int m; };
+  template <typename T>
+  __global__ void k_multi_axpy(long long n, MultiCoef<T> mc, T *__restrict__ w)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        T s = w[i];
+#pragma unroll 4
+        for (int k = 0; k < mc.m; ++k) s += mc.c[k] * mc.v[k][i];
+        w[i] = s;
+      }
+  }
+  // out[k] += <w, V_k>  accumulated in double; warp shuffle + one atomic per warp
+  template <typename T>
+  __global__ void k_multi_dot(long long n, MultiCoef<T> mc, const T *__restrict__ w, double *__restrict__ out)
+  {
+    double acc[MAXK];
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) acc[k] = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        const double wi = (double)w[i];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+          if (k < mc.m) acc[k] += wi * (double)mc.v[k][i];
+      }
+    __shared__ double sh[MAXK][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k)
+      if (k < mc.m)
+        {
+          double v = acc[k];
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) sh[k][warp] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < mc.m)
+      {
+        double v = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sh[threadIdx.x][wv];
+        atomicAdd(out + threadIdx.x, v);
+      }
+  }
+  // dst_i (+)= sum_j P(i,j) src_j over blocks (tensorproduct / tensorproduct_add, operators.h:252-283)
+  template <typename T>
+  struct SmallMat { T a[STFEM_MAX_BLOCKS * STFEM_MAX_BLOCKS]; int m, n; };
+  template <typename T>
+  __global__ void k_block_matmul(long long n, SmallMat<T> P, const T *__restrict__ src, T *__restrict__ dst, int add)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        T s[STFEM_MAX_BLOCKS];
+        for (int j = 0; j < P.n; ++j) s[j] = src[(size_t)j * n + i];
+        for (int r = 0; r < P.m; ++r)
+          {
+            T acc = add ? dst[(size_t)r * n + i] : T(0);
+            for (int j = 0; j < P.n; ++j) acc += P.a[r * P.n + j] * s[j];
+            dst[(size_t)r * n + i] = acc;
+          }
+      }
+  }
+
+  // ------------------------------------------------------------------ host wrappers
+  inline int grid_for(stfem_ctx *ctx, long long n, int threads)
+  {
+    long long g = (n + threads - 1) / threads;
+    const long long cap = (long long)ctx->sm_count * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+  }
+
+  template <typename T>
+  inline void v_axpy(BlockVec<T> &y, T a, const BlockVec<T> &x)
+  {
+    k_axpy<T><<<grid_for(y.ctx, y.size(), 256), 256, 0, y.ctx->stream>>>(y.size(), a, x.d, y.d);
+    y.ctx->launches++;
+  }
+  template <typename T>
+  inline void v_sadd(BlockVec<T> &y, T s, T a, const BlockVec<T> &x)
+  {
+    k_sadd<T><<<grid_for(y.ctx, y.size(), 256), 256, 0, y.ctx->stream>>>(y.size(), s, a, x.d, y.d);
+    y.ctx->launches++;
+  }
+  template <typename T>
+  inline void v_lincomb(BlockVec<T> &z, T a, const BlockVec<T> &x, T b, const BlockVec<T> &y)
+  {
+    k_lincomb<T><<<grid_for(z.ctx, z.size(), 256), 256, 0, z.ctx->stream>>>(z.size(), a, x.d, b, y.d, z.d);
+    z.ctx->launches++;
+  }
+  template <typename T>
+  inline void v_scale(BlockVec<T> &y, T a)
+  {
+    k_scale<T><<<grid_for(y.ctx, y.size(), 256), 256, 0, y.ctx->stream>>>(y.size(), a, y.d);
+    y.ctx->launches++;
+  }
+  template <typename T>
+  inline int v_copy(BlockVec<T> &y, const BlockVec<T> &x)
+  {
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(y.d, x.d, sizeof(T) * (size_t)x.size(), cudaMemcpyDeviceToDevice, y.ctx->stream));
+    return STFEM_OK;
+  }
+  template <typename TO, typename TI>
+  inline void v_convert(BlockVec<TO> &y, const BlockVec<TI> &x)
+  {
+    k_convert<TO, TI><<<grid_for(y.ctx, y.size(), 256), 256, 0, y.ctx->stream>>>(y.size(), x.d, y.d);
+    y.ctx->launches++;
+  }
+
+  // host-visible scratch for reductions (pinned), one per context user
+  struct DotScratch
+  {
+    double *d = nullptr, *h = nullptr;
+    int init()
+    {
+      if (d) return STFEM_OK;
+      STFEM_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * 256));
+      STFEM_CUDA_CHECK(cudaMallocHost(&h, sizeof(double) * 256));
+      return STFEM_OK;
+    }
+    ~DotScratch()
+    {
+      if (d) cudaFree(d);
+      if (h) cudaFreeHost(h);
+    }
+  };
+
+  // out[k] = <w, V[k]> for k < m (any m: chunks of MAXK).  Synchronises the stream.
+  template <typename T>
+  inline int v_multi_dot(DotScratch &sc, const BlockVec<T> &w, const std::vector<const BlockVec<T> *> &V, double *out)
+  {
+    STFEM_FORWARD(sc.init());
+    stfem_ctx *ctx = w.ctx;
+    const int  m   = (int)V.size();
+    if (m > 256) { set_error("multi_dot: too many vectors"); return STFEM_ERR_INVALID; }
+    STFEM_CUDA_CHECK(cudaMemsetAsync(sc.d, 0, sizeof(double) * m, ctx->stream));
+    for (int k0 = 0; k0 < m; k0 += MAXK)
+      {
+        MultiCoef<T> mc;
+        mc.m = std::min(MAXK, m - k0);
+        for (int k = 0; k < mc.m; ++k) mc.v[k] = V[k0 + k]->d;
+        k_multi_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0);
+        ctx->launches++;
+      }
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(sc.h, sc.d, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < m; ++k) out[k] = sc.h[k];
+    return STFEM_OK;
+  }
+  template <typename T>
+  inline int v_dot(DotScratch &sc, const BlockVec<T> &x, const BlockVec<T> &y, double *out)
+  {
+    std::vector<const BlockVec<T> *> V{&y};
+    return v_multi_dot(sc, x, V, out);
+  }
+  // w += sum_k c[k] V[k]
+  template <typename T>
+  inline void v_multi_axpy(BlockVec<T> &w, const std::vector<const BlockVec<T> *> &V, const double *c)
+  {
+    const int m = (int)V.size();
+    for (int k0 = 0; k0 < m; k0 += MAXK)
+      {
+        MultiCoef<T> mc;
+        mc.m = std::min(MAXK, m - k0);
+        for (int k = 0; k < mc.m; ++k)
+          {
+            mc.v[k] = V[k0 + k]->d;
+            mc.c[k] = (T)c[k0 + k];
+          }
+        k_multi_axpy<T><<<grid_for(w.ctx, w.size(), 256), 256, 0, w.ctx->stream>>>(w.size(), mc, w.d);
+        w.ctx->launches++;
+      }
+  }
+  // dst (+)= P src across blocks; dst has P.m blocks, src P.n blocks, same n
+  template <typename T>
+  inline void v_block_matmul(BlockVec<T> &dst, const std::vector<double> &P, int m, int n, const BlockVec<T> &src, bool add)
+  {
+    SmallMat<T> S;
+    S.m = m; S.n = n;
+    for (int i = 0; i < m * n; ++i) S.a[i] = (T)P[i];
+    k_block_matmul<T><<<grid_for(dst.ctx, dst.n, 256), 256, 0, dst.ctx->stream>>>(dst.n, S, src.d, dst.d, add ? 1 : 0);
+    dst.ctx->launches++;
+  }
+} // namespace stfem

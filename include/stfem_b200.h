@@ -119,6 +119,57 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
 int stfem_op_set_timing(stfem_op_t op, int enable);
 float stfem_op_last_kernel_ms(stfem_op_t op);
 
+/* ---- space-time multigrid preconditioner: GMG<dim, Number, LevelMatrixType> (reference
+ *      include/stmg.h:1047-1344) with PreconditionVanka smoothers (stmg.h:745-872), the transfers of
+ *      build_stmg_transfers (stmg.h:538-617) and deal.II's Multigrid V-cycle / MGSmootherPrecondition /
+ *      PreconditionRelaxation|Chebyshev.  Levels are ordered coarse -> fine like
+ *      MGLevelObject; level operators are stfem_op_t objects of ONE precision (float for
+ *      test<double,float>, tests/tp_01.cc:801-804) built by the caller on the level meshes
+ *      (tests/tp_01.cc:250-321).  Parameter names follow PreconditionerGMGAdditionalData
+ *      (include/parameters.h:12-31). ---- */
+typedef struct stfem_mg *stfem_mg_t;
+typedef struct stfem_solver *stfem_solver_t;
+
+typedef struct stfem_mg_desc {
+  int n_levels;
+  const stfem_op_t *level_ops;   /* n_levels, coarse -> fine */
+  const char *mg_type_level;     /* n_levels-1 chars of 'h','p','k','t' (get_mg_sequence) */
+  const int *smoother_types;     /* n_levels: 0 Identity, 1 Relaxation, 2 Chebyshev (get_precondition_stmg_types) */
+  int time_type;                 /* 1 CGP, 2 DG */
+  int n_timesteps_at_once;       /* on the finest level */
+  const int *poly_time_sequence; /* time degrees coarse -> fine (get_poly_mg_sequence) */
+  int n_poly_time;
+  int smoothing_steps;           /* default 1 */
+  double relaxation;             /* 0 = estimate by power iteration */
+  double smoothing_range;        /* default 1 */
+  int eig_n_iterations;          /* default 20 */
+  int variable;                  /* MGSmootherPrecondition variable smoothing, default 1 */
+  int restrict_is_transpose_prolongate; /* default 1 */
+} stfem_mg_desc;
+
+int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out);
+int stfem_mg_destroy(stfem_mg_t mg);
+int stfem_mg_n_levels(stfem_mg_t mg);
+/* GMG::vmult (stmg.h:1331-1344): one V-cycle; dst, src = nb DOUBLE device arrays of the finest level */
+int stfem_mg_vmult(stfem_mg_t mg, void *const *dst, const void *const *src);
+/* Single pieces of the cycle, for parity tests; vectors in the LEVEL precision.
+ * what: 0 PreconditionVanka::vmult, 1 PreconditionSTMG::vmult (smoother), 2 restrict level -> level-1,
+ *       3 prolongate level-1 -> level, 4 level operator vmult, 5 V-cycle started on this level */
+int stfem_mg_level_apply(stfem_mg_t mg, int level, int what, void *const *dst, const void *const *src);
+/* out10: smoother type, lambda estimate, omega, theta, delta, smoothing steps, N, blocks,
+ *        stored patch matrices, bytes of patch storage */
+int stfem_mg_level_info(stfem_mg_t mg, int level, double *out10);
+
+/* SolverFGMRES(ReductionControl(max_iterations, abs_tol, reduce), AdditionalData(max_basis_size))
+ * (include/time_integrators.h:56-59): right-preconditioned flexible GMRES, x is the initial guess on
+ * entry.  M may be NULL (unpreconditioned).  Returns STFEM_ERR_NO_CONVERGENCE like the reference's
+ * AssertThrow on SolverControl::NoConvergence (time_integrators.h:317-320). */
+int stfem_solver_create(stfem_solver_t *out);
+int stfem_solver_destroy(stfem_solver_t s);
+int stfem_fgmres_solve(stfem_solver_t s, stfem_op_t A, stfem_mg_t M, void *const *x, const void *const *b,
+                       int max_basis_size, int max_iterations, double abs_tol, double reduce, int *iterations,
+                       double *initial_residual, double *final_residual);
+
 /* ---- host-side time algebra (no GPU): reference include/fe_time.h, include/fe_time.cc.
  *      type: 1 = CGP, 2 = DG (enum TimeStepType, fe_time.h:18-23).  All matrices row-major doubles. ---- */
 int stfem_fe_time_n_blocks(int type, int r, int n_timesteps_at_once);
