@@ -121,6 +121,13 @@ int stfem_dev_memset(stfem_ctx_t ctx, void *dst_dev, int value, size_t bytes)
   return STFEM_OK;
 }
 
+int stfem_dev_copy(stfem_ctx_t ctx, void *dst_dev, const void *src_dev, size_t bytes)
+{
+  STFEM_REQUIRE(ctx, "null context");
+  STFEM_CUDA_CHECK(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return STFEM_OK;
+}
+
 int stfem_host_alloc_pinned(size_t bytes, void **out)
 {
   STFEM_REQUIRE(out, "null out");

@@ -4,18 +4,6 @@
 
 using namespace stfem;
 
-struct stfem_mg
-{
-  std::unique_ptr<MGBase> impl;
-  int                     number_type = STFEM_F32;
-};
-
-struct stfem_solver
-{
-  Fgmres       fgmres;
-  FgmresResult last;
-};
-
 extern "C" {
 
 int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out)

@@ -1,0 +1,309 @@
+// C ABI: time stepping around the solve — TimeIntegratorFO / TimeIntegratorWave of the reference
+// (include/time_integrators.h:24-459), source integration / interpolation (tests/tp_01.cc:382-408) and the
+// space-time error functional (include/exact_solution.h:503-649).
+#include "assemble.cuh"
+#include "mg.cuh"
+
+using namespace stfem;
+
+namespace
+{
+  struct Combine { const double *src[2 * STFEM_MAX_BLOCKS + 2]; double c[2 * STFEM_MAX_BLOCKS + 2]; int m; };
+
+  __global__ void k_combine(long long n, Combine cb, double *__restrict__ dst, int add)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        double s = add ? dst[i] : 0.0;
+        for (int k = 0; k < cb.m; ++k) s += cb.c[k] * cb.src[k][i];
+        dst[i] = s;
+      }
+  }
+
+  void combine(stfem_ctx *ctx, long long n, const std::vector<const double *> &src, const std::vector<double> &c, double *dst, bool add)
+  {
+    Combine cb;
+    cb.m = 0;
+    for (size_t k = 0; k < src.size(); ++k)
+      if (c[k] != 0.0)
+        {
+          cb.src[cb.m] = src[k];
+          cb.c[cb.m++] = c[k];
+        }
+    if (cb.m == 0 && add) return;
+    k_combine<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, cb, dst, add ? 1 : 0);
+    ctx->launches++;
+  }
+} // namespace
+
+struct stfem_time_integrator
+{
+  int                 type = DG, r = 0, nts = 1, problem = 1, nd = 1, fid = 0;
+  bool                extrapolate = true;
+  double              freq = 1.0, abstol = 1e-12, reduce = 1e-12;
+  int                 max_iter = 200, max_basis = 100;
+  Mat                 A1, B1, G1, Z1, AixB, AixG, AixZ;
+  stfem_op           *matrix = nullptr, *rhs_matrix = nullptr, *rhs_matrix_v = nullptr;
+  stfem_mg           *mg = nullptr;
+  std::vector<double> quad_time;
+  Fgmres              solver;
+  FgmresResult        last;
+  AsmGeom             geom;
+  BlockVec<double>    tmp; // one spatial vector
+
+  int assemble_force(void *const *rhs, double time, double tau)
+  {
+    // time_integrators.h:73-110
+    stfem_ctx *ctx = matrix->mesh->ctx;
+    if (fid == 0) return STFEM_OK;
+    const long long total = geom.n_cells * (geom.dim == 3 ? geom.n1 * geom.n1 * geom.n1 : geom.n1 * geom.n1);
+    auto add = [&](int block, double scale, double t) {
+      if (scale == 0.0) return;
+      k_integrate_function<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(geom, fid, t, freq, scale, (double *)rhs[block]);
+      ctx->launches++;
+    };
+    for (int it = 0; it < nts; ++it)
+      for (size_t j = 0; j < quad_time.size(); ++j)
+        {
+          const double t = time + tau * it + tau * quad_time[j];
+          if (type == DG)
+            add(it * nd + (int)j, A1((int)j, (int)j), t);
+          else if (j == 0)
+            for (int i = 0; i < nd; ++i) add(it * nd + i, -G1(i, 0), t);
+          else
+            add(it * nd + (int)j - 1, A1((int)j - 1, (int)j - 1), t);
+        }
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
+  int do_extrapolate(void *const *x, const void *prev)
+  {
+    // time_integrators.h:180-190
+    stfem_ctx   *ctx = matrix->mesh->ctx;
+    const size_t bytes = sizeof(double) * (size_t)matrix->N;
+    for (int b = 0; b < nts * nd; ++b)
+      if (extrapolate)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(x[b], prev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      else
+        STFEM_CUDA_CHECK(cudaMemsetAsync(x[b], 0, bytes, ctx->stream));
+    return STFEM_OK;
+  }
+};
+
+extern "C" {
+
+int stfem_ti_create(const stfem_ti_desc *d, stfem_ti_t *out)
+{
+  STFEM_REQUIRE(d && out, "stfem_ti_create: null argument");
+  STFEM_REQUIRE(d->time_type == CGP || d->time_type == DG, "stfem_ti_create: bad time type");
+  STFEM_REQUIRE(d->matrix && d->rhs_matrix, "stfem_ti_create: matrix / rhs_matrix missing");
+  STFEM_REQUIRE(d->problem == 1 || (d->problem == 2 && d->rhs_matrix_v), "stfem_ti_create: wave needs rhs_matrix_v");
+  STFEM_REQUIRE(d->Alpha_1 && d->Gamma_1, "stfem_ti_create: Alpha_1 / Gamma_1 missing");
+  auto ti      = std::make_unique<stfem_time_integrator>();
+  ti->type     = d->time_type;
+  ti->r        = d->time_degree;
+  ti->nts      = d->n_timesteps_at_once;
+  ti->problem  = d->problem;
+  ti->nd       = ti->type == DG ? ti->r + 1 : ti->r;
+  ti->fid      = d->rhs_function_id;
+  ti->freq     = d->frequency;
+  ti->extrapolate = d->extrapolate != 0;
+  ti->abstol   = d->abs_tol > 0 ? d->abs_tol : 1e-12;
+  ti->reduce   = d->gmres_tolerance > 0 ? d->gmres_tolerance : 1e-12;
+  ti->max_iter = d->max_iterations > 0 ? d->max_iterations : 200;
+  ti->max_basis = d->max_basis_size > 0 ? d->max_basis_size : 100;
+  ti->matrix = d->matrix; ti->rhs_matrix = d->rhs_matrix; ti->rhs_matrix_v = d->rhs_matrix_v; ti->mg = d->preconditioner;
+  STFEM_REQUIRE(ti->matrix->nb_rows == ti->nts * ti->nd, "stfem_ti_create: matrix has %d blocks, expected %d", ti->matrix->nb_rows, ti->nts * ti->nd);
+  const int nd = ti->nd;
+  ti->A1 = Mat(nd, nd); ti->B1 = Mat(nd, nd); ti->G1 = Mat(nd, 1); ti->Z1 = Mat(nd, 1);
+  std::copy(d->Alpha_1, d->Alpha_1 + nd * nd, ti->A1.a.begin());
+  std::copy(d->Gamma_1, d->Gamma_1 + nd, ti->G1.a.begin());
+  if (d->Beta_1) std::copy(d->Beta_1, d->Beta_1 + nd * nd, ti->B1.a.begin());
+  if (d->Zeta_1) std::copy(d->Zeta_1, d->Zeta_1 + nd, ti->Z1.a.begin());
+  ti->quad_time = time_nodes(ti->type, ti->r);
+  if (ti->problem == 2)
+    {
+      // time_integrators.h:385-398
+      STFEM_REQUIRE(d->Beta_1, "stfem_ti_create: wave needs Beta_1");
+      try
+        {
+          const Mat Ainv = inverse(ti->A1);
+          ti->AixB = Ainv * ti->B1; ti->AixG = Ainv * ti->G1; ti->AixZ = Ainv * ti->Z1;
+        }
+      catch (const std::exception &e)
+        {
+          set_error("stfem_ti_create: %s", e.what());
+          return STFEM_ERR_INVALID;
+        }
+      if (ti->type == DG) ti->AixG.scale(-1.0); else ti->AixZ.scale(-1.0);
+    }
+  fill_asm_geom(ti->geom, ti->matrix->mesh, ti->matrix->degree, ti->matrix->degree + 1);
+  STFEM_FORWARD(ti->tmp.alloc(ti->matrix->mesh->ctx, 1, ti->matrix->N));
+  *out = ti.release();
+  return STFEM_OK;
+}
+
+int stfem_ti_destroy(stfem_ti_t ti)
+{
+  delete ti;
+  return STFEM_OK;
+}
+
+// TimeIntegratorFO::solve (time_integrators.h:300-321)
+int stfem_ti_solve_heat(stfem_ti_t ti, void *const *x, const void *prev_x, void *const *rhs, double time, double tau, int *iterations)
+{
+  STFEM_REQUIRE(ti && x && prev_x && rhs, "stfem_ti_solve_heat: null argument");
+  stfem_ctx   *ctx = ti->matrix->mesh->ctx;
+  const int    nb  = ti->nts * ti->nd;
+  const size_t bytes = sizeof(double) * (size_t)ti->matrix->N;
+  for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(rhs[b], 0, bytes, ctx->stream));
+  const void *src[1] = {prev_x};
+  STFEM_FORWARD(op_apply(ti->rhs_matrix, rhs, src, 1, nb, ti->rhs_matrix->d_alpha, ti->rhs_matrix->d_beta, false));
+  STFEM_FORWARD(ti->assemble_force(rhs, time, tau));
+  STFEM_FORWARD(ti->do_extrapolate(x, prev_x));
+  const int rc = ti->solver.solve(ti->matrix, ti->mg ? ti->mg->impl.get() : nullptr, x, (const void *const *)rhs, ti->max_basis, ti->max_iter,
+                                  ti->abstol, ti->reduce, ti->last);
+  if (iterations) *iterations = ti->last.iterations;
+  return rc;
+}
+
+// TimeIntegratorWave::solve (time_integrators.h:400-447)
+int stfem_ti_solve_wave(stfem_ti_t ti, void *const *u, void *const *v, void *const *rhs, const void *prev_u, const void *prev_v,
+                        double time, double tau, int *iterations)
+{
+  STFEM_REQUIRE(ti && u && v && rhs && prev_u && prev_v, "stfem_ti_solve_wave: null argument");
+  STFEM_REQUIRE(ti->problem == 2, "stfem_ti_solve_wave: integrator was created for the heat equation");
+  stfem_ctx      *ctx = ti->matrix->mesh->ctx;
+  const int       nb = ti->nts * ti->nd, nd = ti->nd;
+  const long long N  = ti->matrix->N;
+  const size_t    bytes = sizeof(double) * (size_t)N;
+  for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(rhs[b], 0, bytes, ctx->stream));
+  const void *su[1] = {prev_u}, *sv[1] = {prev_v};
+  STFEM_FORWARD(op_apply(ti->rhs_matrix, rhs, su, 1, nb, ti->rhs_matrix->d_alpha, ti->rhs_matrix->d_beta, false));
+  STFEM_FORWARD(ti->do_extrapolate(u, prev_u));
+  STFEM_FORWARD(op_apply(ti->rhs_matrix_v, rhs, sv, 1, nb, ti->rhs_matrix_v->d_alpha, ti->rhs_matrix_v->d_beta, false));
+  STFEM_FORWARD(ti->assemble_force(rhs, time, tau));
+  const int rc = ti->solver.solve(ti->matrix, ti->mg ? ti->mg->impl.get() : nullptr, u, (const void *const *)rhs, ti->max_basis, ti->max_iter,
+                                  ti->abstol, ti->reduce, ti->last);
+  if (iterations) *iterations = ti->last.iterations;
+  if (rc != STFEM_OK) return rc;
+  // velocity recovery: v = A^-1 B u (+ terms of the previous end values)
+  for (int it = 0; it < ti->nts; ++it)
+    {
+      const double *pu = it == 0 ? (const double *)prev_u : (const double *)u[it * nd - 1];
+      for (int i = 0; i < nd; ++i)
+        {
+          std::vector<const double *> src;
+          std::vector<double>         c;
+          for (int j = 0; j < nd; ++j)
+            {
+              src.push_back((const double *)u[it * nd + j]);
+              c.push_back(ti->AixB(i, j));
+            }
+          if (ti->type == DG)
+            {
+              src.push_back(pu);
+              c.push_back(ti->AixG(i, 0));
+            }
+          else
+            {
+              const double *pv = it == 0 ? (const double *)prev_v : (const double *)v[it * nd - 1];
+              src.push_back(pv);
+              c.push_back(ti->AixG(i, 0));
+              src.push_back(pu);
+              c.push_back(ti->AixZ(i, 0));
+            }
+          combine(ctx, N, src, c, (double *)v[it * nd + i], false);
+        }
+    }
+  STFEM_CUDA_CHECK(cudaGetLastError());
+  return STFEM_OK;
+}
+
+int stfem_ti_last_residuals(stfem_ti_t ti, double *initial, double *final_)
+{
+  STFEM_REQUIRE(ti, "null integrator");
+  if (initial) *initial = ti->last.initial_residual;
+  if (final_) *final_ = ti->last.final_residual;
+  return STFEM_OK;
+}
+
+int stfem_interpolate(stfem_mesh_t mesh, int degree, int function_id, double frequency, double time, void *dst)
+{
+  STFEM_REQUIRE(mesh && dst && degree >= 1 && degree <= 6, "stfem_interpolate: bad arguments");
+  AsmGeom g;
+  fill_asm_geom(g, mesh, degree, degree + 1);
+  stfem_ctx      *ctx = mesh->ctx;
+  const long long N   = (long long)g.np[0] * g.np[1] * g.np[2];
+  k_interpolate_function<<<grid_for(ctx, N, 256), 256, 0, ctx->stream>>>(g, function_id, time, frequency, (double *)dst);
+  ctx->launches++;
+  STFEM_CUDA_CHECK(cudaGetLastError());
+  return STFEM_OK;
+}
+
+int stfem_integrate_rhs(stfem_mesh_t mesh, int degree, int function_id, double frequency, double time, double scale, void *dst)
+{
+  STFEM_REQUIRE(mesh && dst && degree >= 1 && degree <= 6, "stfem_integrate_rhs: bad arguments");
+  AsmGeom g;
+  fill_asm_geom(g, mesh, degree, degree + 1);
+  stfem_ctx      *ctx   = mesh->ctx;
+  const long long total = g.n_cells * (g.dim == 3 ? g.n1 * g.n1 * g.n1 : g.n1 * g.n1);
+  k_integrate_function<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(g, function_id, time, frequency, scale, (double *)dst);
+  ctx->launches++;
+  STFEM_CUDA_CHECK(cudaGetLastError());
+  return STFEM_OK;
+}
+
+// ErrorCalculator::evaluate_error (exact_solution.h:533-633) for one solve interval; adds tau*w_q*||.||^2 into
+// out3[0] (L2^2) and out3[2] (H1-seminorm^2), max into out3[1] (Linf).  n_space_quad = points per direction of the
+// spatial Gauss rule (the reference passes fe_degree+1 with fe_degree the TIME degree, tp_01.cc:492-498).
+int stfem_evaluate_error(stfem_mesh_t mesh, int degree, int time_type, int time_degree, int n_timesteps_at_once, const void *const *x,
+                         const void *prev_x, double time, double tau, double frequency, int n_space_quad, double *out3)
+{
+  STFEM_REQUIRE(mesh && x && prev_x && out3, "stfem_evaluate_error: null argument");
+  STFEM_REQUIRE(n_space_quad >= 1 && n_space_quad <= 8, "stfem_evaluate_error: n_space_quad out of range");
+  stfem_ctx *ctx = mesh->ctx;
+  AsmGeom    g;
+  fill_asm_geom(g, mesh, degree, n_space_quad);
+  const long long N  = (long long)g.np[0] * g.np[1] * g.np[2];
+  const int       nd = time_type == DG ? time_degree + 1 : time_degree;
+  const Rule      tq = gauss(time_degree + 1);
+  const auto      nodes = time_nodes(time_type, time_degree);
+  double *d_u = nullptr, *d_out = nullptr;
+  STFEM_CUDA_CHECK(cudaMalloc(&d_u, sizeof(double) * N));
+  STFEM_CUDA_CHECK(cudaMalloc(&d_out, sizeof(double) * 3));
+  const long long total = g.n_cells * (g.dim == 3 ? n_space_quad * n_space_quad * n_space_quad : n_space_quad * n_space_quad);
+  for (int it = 0; it < n_timesteps_at_once; ++it)
+    for (size_t q = 0; q < tq.x.size(); ++q)
+      {
+        const double  t  = time + tau * it + tq.x[q] * tau;
+        const double *pv = it == 0 ? (const double *)prev_x : (const double *)x[nd * it - 1];
+        std::vector<const double *> src;
+        std::vector<double>         c;
+        for (size_t i = 0; i < nodes.size(); ++i)
+          {
+            const double v = lagrange_value(nodes, (int)i, tq.x[q]);
+            if (time_type == DG)
+              src.push_back((const double *)x[nd * it + i]);
+            else
+              src.push_back(i == 0 ? pv : (const double *)x[nd * it + i - 1]);
+            c.push_back(v);
+          }
+        combine(ctx, N, src, c, d_u, false);
+        STFEM_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * 3, ctx->stream));
+        k_error<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(g, d_u, t, frequency, d_out);
+        ctx->launches++;
+        double h[3];
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(h, d_out, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        out3[0] += tau * tq.w[q] * h[0];
+        out3[2] += tau * tq.w[q] * h[2];
+        if (h[1] > out3[1]) out3[1] = h[1];
+      }
+  cudaFree(d_u);
+  cudaFree(d_out);
+  return STFEM_OK;
+}
+
+} // extern "C"

@@ -568,3 +568,16 @@ namespace stfem
     }
   };
 } // namespace stfem
+
+// handles of the C ABI
+struct stfem_mg
+{
+  std::unique_ptr<stfem::MGBase> impl;
+  int                            number_type = STFEM_F32;
+};
+
+struct stfem_solver
+{
+  stfem::Fgmres       fgmres;
+  stfem::FgmresResult last;
+};

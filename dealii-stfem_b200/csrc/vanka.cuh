@@ -83,7 +83,7 @@ namespace stfem
 
   // one thread per (patch, i, j): assembled patch entry incl. neighbour contributions, valence scaling,
   // constraint handling, then the nb x nb time blocks of B (row-major double, ld = nb*nc)
-  __global__ void k_vanka_build(VankaGeom g, const long long *__restrict__ cells, int n_patches, int nb, const double *__restrict__ alpha,
+  static __global__ void k_vanka_build(VankaGeom g, const long long *__restrict__ cells, int n_patches, int nb, const double *__restrict__ alpha,
                                 const double *__restrict__ beta, double *__restrict__ B)
   {
     const int n1 = g.n1, dim = g.dim, k = n1 - 1;
@@ -143,7 +143,7 @@ namespace stfem
   }
 
   // in-place Gauss-Jordan inverse with partial pivoting, one CTA per matrix (FullMatrix::gauss_jordan)
-  __global__ void k_batched_inverse(double *__restrict__ A, int n, int *__restrict__ perm_ws, int *__restrict__ info)
+  static __global__ void k_batched_inverse(double *__restrict__ A, int n, int *__restrict__ perm_ws, int *__restrict__ info)
   {
     double *M    = A + (size_t)blockIdx.x * n * n;
     int    *perm = perm_ws + (size_t)blockIdx.x * n;

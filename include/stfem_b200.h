@@ -59,6 +59,7 @@ int stfem_dev_free(stfem_ctx_t ctx, void *p);
 int stfem_dev_upload(stfem_ctx_t ctx, void *dst_dev, const void *src_host, size_t bytes);
 int stfem_dev_download(stfem_ctx_t ctx, void *dst_host, const void *src_dev, size_t bytes);
 int stfem_dev_memset(stfem_ctx_t ctx, void *dst_dev, int value, size_t bytes);
+int stfem_dev_copy(stfem_ctx_t ctx, void *dst_dev, const void *src_dev, size_t bytes);
 int stfem_host_alloc_pinned(size_t bytes, void **out);
 int stfem_host_free_pinned(void *p);
 
@@ -169,6 +170,55 @@ int stfem_solver_destroy(stfem_solver_t s);
 int stfem_fgmres_solve(stfem_solver_t s, stfem_op_t A, stfem_mg_t M, void *const *x, const void *const *b,
                        int max_basis_size, int max_iterations, double abs_tol, double reduce, int *iterations,
                        double *initial_residual, double *final_residual);
+
+/* ---- time stepping: TimeIntegratorFO / TimeIntegratorWave (reference include/time_integrators.h:24-459).
+ *      The right-hand-side function is one of the reference's analytic functions
+ *      (include/exact_solution.h:27-197): 0 zero, 1 ExactSolution, 2 RHSFunction (heat),
+ *      3 wave::ExactSolutionV, 4 wave::RHSFunction; `frequency` is their parameter f. ---- */
+typedef struct stfem_time_integrator *stfem_ti_t;
+
+typedef struct stfem_ti_desc {
+  int time_type;            /* 1 CGP, 2 DG */
+  int time_degree;          /* r */
+  int n_timesteps_at_once;
+  int problem;              /* 1 heat (TimeIntegratorFO), 2 wave (TimeIntegratorWave) */
+  const double *Alpha_1;    /* single-step weights of get_fe_time_weights(type, r, tau, 1): nd x nd */
+  const double *Beta_1;     /* nd x nd (wave only) */
+  const double *Gamma_1;    /* nd x 1 */
+  const double *Zeta_1;     /* nd x 1 (wave only) */
+  stfem_op_t matrix;        /* system matrix, double precision */
+  stfem_mg_t preconditioner; /* may be NULL */
+  stfem_op_t rhs_matrix;    /* nb x 1 slice operator (tests/tp_01.cc:162-168) */
+  stfem_op_t rhs_matrix_v;  /* wave only (tests/tp_01.cc:157-158) */
+  int rhs_function_id;
+  double frequency;
+  int extrapolate;          /* initial guess = previous end value (time_integrators.h:180-190) */
+  double gmres_tolerance;   /* ReductionControl reduce, default 1e-12 */
+  double abs_tol;           /* default 1e-12 */
+  int max_iterations;       /* default 200 */
+  int max_basis_size;       /* default 100 */
+} stfem_ti_desc;
+
+int stfem_ti_create(const stfem_ti_desc *desc, stfem_ti_t *out);
+int stfem_ti_destroy(stfem_ti_t ti);
+/* TimeIntegratorFO::solve (time_integrators.h:300-321): rhs = rhs_matrix.vmult_slice(prev_x) + force,
+ * x = extrapolated initial guess, FGMRES.  x, rhs: nb device arrays; prev_x: one spatial vector. */
+int stfem_ti_solve_heat(stfem_ti_t ti, void *const *x, const void *prev_x, void *const *rhs, double time,
+                        double time_step, int *iterations);
+/* TimeIntegratorWave::solve (time_integrators.h:400-447) including the velocity recovery */
+int stfem_ti_solve_wave(stfem_ti_t ti, void *const *u, void *const *v, void *const *rhs, const void *prev_u,
+                        const void *prev_v, double time, double time_step, int *iterations);
+int stfem_ti_last_residuals(stfem_ti_t ti, double *initial, double *final_);
+/* VectorTools::interpolate / create_right_hand_side of an analytic function (tests/tp_01.cc:382-408);
+ * integrate ADDS scale * (f, phi_i) into dst, constrained rows untouched */
+int stfem_interpolate(stfem_mesh_t mesh, int degree, int function_id, double frequency, double time, void *dst);
+int stfem_integrate_rhs(stfem_mesh_t mesh, int degree, int function_id, double frequency, double time, double scale,
+                        void *dst);
+/* ErrorCalculator::evaluate_error (include/exact_solution.h:533-633) over one solve interval against
+ * ExactSolution: out3[0] += L2^2 part, out3[1] = max(out3[1], Linf), out3[2] += H1-seminorm^2 part */
+int stfem_evaluate_error(stfem_mesh_t mesh, int degree, int time_type, int time_degree, int n_timesteps_at_once,
+                         const void *const *x, const void *prev_x, double time, double time_step, double frequency,
+                         int n_space_quad, double *out3);
 
 /* ---- host-side time algebra (no GPU): reference include/fe_time.h, include/fe_time.cc.
  *      type: 1 = CGP, 2 = DG (enum TimeStepType, fe_time.h:18-23).  All matrices row-major doubles. ---- */

@@ -1,0 +1,68 @@
+"""End-to-end parity of the GPU time loop (HeatWaveProblem over the C ABI = tests/tp_01.cc flow) with
+  (1) the reference's own integration-test output tests/tp_01.output (hard pins: error norms, 6 digits),
+  (2) the CPU oracle run with the same parameters: space-time L2 errors to 1e-10 relative, FGMRES iteration
+      totals within +-1 per solve (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from golden_util import load
+from oracle import tp_01
+
+pytestmark = pytest.mark.gpu
+G = load("tp_01")
+
+
+def _close6(a, b):
+    return abs(a - b) <= 6e-6 * abs(b)
+
+
+CASES = [("tf03", 0, 2), ("tf03", 0, 3), ("tf03", 0, 4), ("tf03", 1, 3), ("tf04", 0, 3), ("tf01", 0, 3), ("tf02", 0, 2),
+         ("tf05", 0, 3), ("tf06", 0, 2), ("tf07", 0, 3), ("tf08", 0, 3)]
+
+
+@pytest.mark.parametrize("name,deg_idx,ref", CASES)
+def test_tp01_rows_match_reference_output_and_oracle(ctx, name, deg_idx, ref):
+    import dealii_stfem_b200 as st
+    p = st.parse_parameters(G["params"][name], 2)
+    k = p["feDegree"] + deg_idx
+    gold = G["tables"][name][deg_idx]["runs"][ref - p["refinement"]]
+    prob = st.HeatWaveProblem(ctx, p, 2, ref, k)
+    row = prob.run()
+    prob.close()
+    assert row["cells"] == gold["cells"] and row["s_dofs"] == gold["s_dofs"] and row["t_dofs"] == gold["t_dofs"]
+    assert row["timesteps"] == gold["timesteps"]
+    assert _close6(row["l2"], gold["l2"]), (row["l2"], gold["l2"])
+    assert _close6(row["linf"], gold["linf"]), (row["linf"], gold["linf"])
+    assert _close6(row["h1"], gold["h1"]), (row["h1"], gold["h1"])
+    o = tp_01.convergence_test(tp_01.parse_parameters(G["params"][name], 2), 2, ref, k, mg_dtype=np.float32)
+    assert row["levels"] == o["levels"]
+    assert abs(row["l2"] - o["l2"]) <= 1e-10 * o["l2"], (row["l2"], o["l2"])
+    assert abs(row["h1"] - o["h1"]) <= 1e-9 * o["h1"]
+    assert abs(row["iterations"] - o["iterations"]) <= row["timesteps"], (row["iterations"], o["iterations"])
+
+
+def test_tp01_soft_pin_iteration_counts(ctx):
+    """Stored iteration totals of tp_01.output (older level ordering = time level at the coarse end)."""
+    import dealii_stfem_b200 as st
+    for name, ref in (("tf03", 4), ("tf07", 3)):
+        p = st.parse_parameters(G["params"][name], 2)
+        p["mgTimeBeforeSpace"] = True
+        gold = G["tables"][name][0]["runs"][ref - p["refinement"]]
+        prob = st.HeatWaveProblem(ctx, p, 2, ref, p["feDegree"])
+        row = prob.run()
+        prob.close()
+        assert abs(row["iterations"] - gold["iterations"]) <= row["timesteps"], (row["iterations"], gold["iterations"])
+        assert _close6(row["l2"], gold["l2"])
+
+
+def test_3d_heat_short_run_matches_oracle(ctx):
+    """3D, Q2 x DG(1), refinement 2, first two time steps."""
+    import dealii_stfem_b200 as st
+    pj = dict(G["params"]["tf03"])
+    p = st.parse_parameters(pj, 3)
+    prob = st.HeatWaveProblem(ctx, p, 3, 2, 1)
+    row = prob.run(max_steps=2)
+    prob.close()
+    o = tp_01.convergence_test(tp_01.parse_parameters(pj, 3), 3, 2, 1, mg_dtype=np.float32, max_steps=2)
+    assert abs(row["l2"] - o["l2"]) <= 1e-10 * o["l2"]
+    assert abs(row["iterations"] - o["iterations"]) <= 2
