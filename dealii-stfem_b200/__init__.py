@@ -7,5 +7,5 @@ driver.py    tp_01-style driver (parameters, level hierarchy, time loop) over th
 Import as `dealii_stfem_b200` (the hyphenated directory is re-exported by that shim).
 """
 from .capi import *  # noqa: F401,F403
-from . import capi, driver, fe_time_host  # noqa: F401
+from . import capi, dist, driver, fe_time_host  # noqa: F401
 from .driver import HeatWaveProblem, parse_parameters  # noqa: F401

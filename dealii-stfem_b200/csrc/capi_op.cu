@@ -240,6 +240,14 @@ namespace stfem
       rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, dst, src, nb_src, nb_dst, alpha, beta) :
                                           dispatch_degree<3, float>(op, dst, src, nb_src, nb_dst, alpha, beta);
     if (rc != STFEM_OK) return rc;
+    // multi-GPU: interface DoFs hold partial sums -> add over the ranks sharing them (cell_loop's compress(add))
+    if (op->mesh->part.active)
+      {
+        if (op->number_type == STFEM_F64)
+          STFEM_FORWARD(halo_compress_add<double>(ctx, op->mesh->part, op->halo, dst, nb_dst, op->np, op->mesh->dim));
+        else
+          STFEM_FORWARD(halo_compress_add<float>(ctx, op->mesh->part, op->halo, dst, nb_dst, op->np, op->mesh->dim));
+      }
     if (op->timing)
       {
         STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));

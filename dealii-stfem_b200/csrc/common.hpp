@@ -57,7 +57,20 @@ struct stfem_ctx
   int          sm_count = 0;
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr; // per-operator kernel timing
   cudaEvent_t  tm0 = nullptr, tm1 = nullptr; // stfem_ctx_timer_*
+  void        *nccl_comm = nullptr;          // ncclComm_t when the context is part of a multi-GPU run
+  int          rank = 0, n_ranks = 1;
 };
+
+namespace stfem
+{
+  struct PartitionInfo
+  {
+    bool active = false;
+    int  grid[3] = {1, 1, 1}, coords[3] = {0, 0, 0};
+    int  neighbor[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}}; // rank of the low/high neighbour per direction, -1 = none
+    int  rank_of(const int c[3]) const { return c[0] + grid[0] * (c[1] + grid[1] * c[2]); }
+  };
+} // namespace stfem
 
 struct stfem_mesh
 {
@@ -70,4 +83,5 @@ struct stfem_mesh
   double    *d_vertices = nullptr; // device, (n+1)^dim * dim doubles, or null
   std::vector<double> h_vertices;
   unsigned   dirichlet = 0;
+  stfem::PartitionInfo part; // box partition of a multi-GPU run (this mesh = the local brick)
 };

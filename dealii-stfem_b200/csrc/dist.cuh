@@ -1,0 +1,109 @@
+// Multi-GPU layer: one process per GPU, box partition of the structured hex mesh, shared interface DoFs
+// duplicated on both sides.  Replaces what deal.II does for the reference inside MatrixFree::cell_loop
+// (ghost update + compress(add), called at include/operators.h:1016), in PreconditionVanka::vmult
+// (include/stmg.h:843, 870-871) and in the MPI_Allreduce of every dot product.
+//
+//   compress_add : after a local cell loop every interface DoF holds a partial sum; the partial sums of the
+//                  ranks sharing it are added so that all copies hold the full value.  Done direction by
+//                  direction (x, then y, then z faces, each including the already summed edges), i.e. 6
+//                  messages per rank instead of 26; ncclSend/ncclRecv grouped per direction over NVLink.
+//   dot products : interface DoFs are counted on the lower rank only, then ncclAllReduce(sum, double).
+// NCCL is loaded with dlopen("libnccl.so.2") so the single-GPU library has no link dependency on it.
+#pragma once
+#include <dlfcn.h>
+
+#include "common.hpp"
+
+namespace stfem
+{
+  // minimal NCCL surface (ABI-stable C functions)
+  typedef struct ncclComm *nccl_comm_t;
+  struct NcclUniqueId { char internal[128]; };
+  struct NcclApi
+  {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    static constexpr int kDouble = 8, kFloat = 7, kChar = 0, kSum = 0; // ncclDataType_t / ncclRedOp_t values
+  };
+  NcclApi *nccl_api(); // loads on first use; nullptr + error message if libnccl is unavailable
+
+#define STFEM_NCCL_CHECK(expr)                                                                     \
+  do                                                                                               \
+    {                                                                                              \
+      int r__ = (expr);                                                                            \
+      if (r__ != 0)                                                                                \
+        {                                                                                          \
+          stfem::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                      \
+                           stfem::nccl_api()->GetErrorString(r__));                                \
+          return STFEM_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    }                                                                                              \
+  while (0)
+
+  using Partition = PartitionInfo;
+
+  // pack / unpack-add one index plane of a [np2][np1][np0] array (all blocks), plane normal to `axis`
+  template <typename T>
+  __global__ void k_pack_plane(const T *const *blocks, int nb, int np0, int np1, int np2, int axis, int index, T *__restrict__ out)
+  {
+    const int       a = axis == 0 ? np1 : np0, b = axis == 2 ? np1 : np2; // plane extents (fast, slow)
+    const long long per = (long long)a * b, total = per * nb;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const int blk = (int)(gid / per);
+        const long long r = gid % per;
+        const int u = (int)(r % a), v = (int)(r / a);
+        long long off;
+        if (axis == 0) off = (long long)index + (long long)np0 * (u + (long long)np1 * v);
+        else if (axis == 1) off = (long long)u + (long long)np0 * (index + (long long)np1 * v);
+        else off = (long long)u + (long long)np0 * (v + (long long)np1 * index);
+        out[gid] = blocks[blk][off];
+      }
+  }
+  template <typename T>
+  __global__ void k_unpack_add_plane(T *const *blocks, int nb, int np0, int np1, int np2, int axis, int index, const T *__restrict__ in)
+  {
+    const int       a = axis == 0 ? np1 : np0, b = axis == 2 ? np1 : np2;
+    const long long per = (long long)a * b, total = per * nb;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const int blk = (int)(gid / per);
+        const long long r = gid % per;
+        const int u = (int)(r % a), v = (int)(r / a);
+        long long off;
+        if (axis == 0) off = (long long)index + (long long)np0 * (u + (long long)np1 * v);
+        else if (axis == 1) off = (long long)u + (long long)np0 * (index + (long long)np1 * v);
+        else off = (long long)u + (long long)np0 * (v + (long long)np1 * index);
+        blocks[blk][off] += in[gid];
+      }
+  }
+
+  struct HaloBuffers
+  {
+    void  *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+    void **d_ptrs = nullptr; // device copy of the block pointer array
+    int    nb_cap = 0;
+    ~HaloBuffers()
+    {
+      for (int s = 0; s < 2; ++s)
+        {
+          if (send[s]) cudaFree(send[s]);
+          if (recv[s]) cudaFree(recv[s]);
+        }
+      if (d_ptrs) cudaFree(d_ptrs);
+    }
+  };
+
+  // sum the partial values of the interface DoFs over the ranks sharing them (compress(add) + ghost update)
+  template <typename T>
+  int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim);
+} // namespace stfem

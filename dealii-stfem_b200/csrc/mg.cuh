@@ -429,6 +429,7 @@ namespace stfem
       const int       nb = A->nb_rows;
       const long long n  = A->N;
       STFEM_REQUIRE(A->number_type == STFEM_F64, "fgmres: the outer operator must be double precision");
+      sc.set_partition(A->mesh->part, A->np, A->mesh->dim);
       if (!x.d || x.nb != nb || x.n != n)
         {
           STFEM_FORWARD(x.alloc(ctx, nb, n));

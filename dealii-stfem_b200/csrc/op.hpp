@@ -2,6 +2,7 @@
 #pragma once
 #include "basis_host.hpp"
 #include "common.hpp"
+#include "dist.cuh"
 
 struct stfem_op
 {
@@ -16,6 +17,7 @@ struct stfem_op
   void *d_coeff = nullptr;  // per-cell Laplace coefficient
   std::vector<double> h_coeff_cell, h_coeff_q; // host copies (Vanka set-up works in double)
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points
+  stfem::HaloBuffers halo;
   bool  timing = false;
   float last_ms = 0.f;
 };

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.hpp"
+#include "dist.cuh"
 
 namespace stfem
 {
@@ -104,15 +105,34 @@ namespace stfem
         w[i] = s;
       }
   }
+  // multi-GPU: interface DoFs are duplicated on both ranks; a dot product counts them on the lower rank only
+  struct DotMask
+  {
+    int       active = 0;
+    int       np[3] = {1, 1, 1};
+    unsigned  skip_high = 0; // bit d: the plane index np[d]-1 belongs to the neighbour rank
+    long long n_block = 0;
+  };
+  __device__ __forceinline__ bool dot_masked(const DotMask &m, long long i)
+  {
+    long long r  = i % m.n_block;
+    const int ix = (int)(r % m.np[0]);
+    r /= m.np[0];
+    const int iy = (int)(r % m.np[1]);
+    const int iz = (int)(r / m.np[1]);
+    return ((m.skip_high & 1u) && ix == m.np[0] - 1) || ((m.skip_high & 2u) && iy == m.np[1] - 1) || ((m.skip_high & 4u) && iz == m.np[2] - 1);
+  }
+
   // out[k] += <w, V_k>  accumulated in double; warp shuffle + one atomic per warp
   template <typename T>
-  __global__ void k_multi_dot(long long n, MultiCoef<T> mc, const T *__restrict__ w, double *__restrict__ out)
+  __global__ void k_multi_dot(long long n, MultiCoef<T> mc, const T *__restrict__ w, double *__restrict__ out, DotMask mask)
   {
     double acc[MAXK];
 #pragma unroll
     for (int k = 0; k < MAXK; ++k) acc[k] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
       {
+        if (mask.active && dot_masked(mask, i)) continue;
         const double wi = (double)w[i];
 #pragma unroll
         for (int k = 0; k < MAXK; ++k)
@@ -204,6 +224,19 @@ namespace stfem
   struct DotScratch
   {
     double *d = nullptr, *h = nullptr;
+    DotMask mask; // set by the owner for partitioned meshes
+    void    set_partition(const PartitionInfo &part, const int np[3], int dim)
+    {
+      mask         = DotMask();
+      mask.active  = part.active ? 1 : 0;
+      mask.n_block = 1;
+      for (int d = 0; d < 3; ++d)
+        {
+          mask.np[d] = d < dim ? np[d] : 1;
+          mask.n_block *= mask.np[d];
+          if (d < dim && part.neighbor[d][1] >= 0) mask.skip_high |= 1u << d;
+        }
+    }
     int init()
     {
       if (d) return STFEM_OK;
@@ -232,8 +265,14 @@ namespace stfem
         MultiCoef<T> mc;
         mc.m = std::min(MAXK, m - k0);
         for (int k = 0; k < mc.m; ++k) mc.v[k] = V[k0 + k]->d;
-        k_multi_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0);
+        k_multi_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0, sc.mask);
         ctx->launches++;
+      }
+    if (ctx->n_ranks > 1 && ctx->nccl_comm)
+      {
+        NcclApi *api = nccl_api();
+        STFEM_REQUIRE(api, "multi_dot: NCCL unavailable");
+        STFEM_NCCL_CHECK(api->AllReduce(sc.d, sc.d, (size_t)m, NcclApi::kDouble, NcclApi::kSum, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
       }
     STFEM_CUDA_CHECK(cudaMemcpyAsync(sc.h, sc.d, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
     STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -120,6 +120,28 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
 int stfem_op_set_timing(stfem_op_t op, int enable);
 float stfem_op_last_kernel_ms(stfem_op_t op);
 
+/* ---- multi-GPU: one process per GPU, box partition of the structured mesh; replaces the MPI domain
+ *      decomposition deal.II provides to the reference (ghost update + compress(add) inside
+ *      MatrixFree::cell_loop called at include/operators.h:1016, MPI_Allreduce of dot products).
+ *      NCCL is opened at run time (dlopen): rank 0 calls stfem_comm_unique_id, the 128 bytes are
+ *      distributed by the launcher (torch.distributed / MPI / files), every rank calls
+ *      stfem_ctx_comm_init.  A mesh created from stfem_partition_brick's local extents and marked with
+ *      stfem_mesh_set_partition makes every operator built on it exchange its interface DoFs. ---- */
+int stfem_comm_unique_id(char *id128);
+int stfem_ctx_comm_init(stfem_ctx_t ctx, int rank, int n_ranks, const char *id128);
+int stfem_ctx_comm_destroy(stfem_ctx_t ctx);
+int stfem_ctx_rank(stfem_ctx_t ctx);
+int stfem_ctx_n_ranks(stfem_ctx_t ctx);
+/* brick of process `coords` (x fastest rank order) in `proc_grid`: local cells, global cell offset,
+ * local bounding box, Dirichlet mask restricted to physical boundary faces.  Pure host logic. */
+int stfem_partition_brick(int dim, const int *n_global, const double *lower, const double *upper, const int *proc_grid,
+                          const int *coords, int *n_local, int *cell_offset, double *local_lower, double *local_upper,
+                          unsigned *dirichlet_faces);
+int stfem_mesh_set_partition(stfem_mesh_t mesh, const int *proc_grid, const int *coords);
+/* add the partial values of interface DoFs over the ranks sharing them (compress(add) + ghost update);
+ * stfem_op_vmult & co. call this internally on partitioned meshes */
+int stfem_op_halo_add(stfem_op_t op, void *const *blocks, int nb);
+
 /* ---- space-time multigrid preconditioner: GMG<dim, Number, LevelMatrixType> (reference
  *      include/stmg.h:1047-1344) with PreconditionVanka smoothers (stmg.h:745-872), the transfers of
  *      build_stmg_transfers (stmg.h:538-617) and deal.II's Multigrid V-cycle / MGSmootherPrecondition /

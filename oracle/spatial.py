@@ -81,8 +81,11 @@ class Mesh:
 class Space:
     """FE_Q(k) DoFs on a Mesh with zero Dirichlet boundary (tests/tp_01.cc:77,92-100)."""
 
-    def __init__(self, mesh, degree):
+    def __init__(self, mesh, degree, dirichlet_faces=None):
+        """dirichlet_faces: bit 2*d+side set = zero Dirichlet on that face (default: all faces)."""
         self.mesh, self.k, self.dim = mesh, degree, mesh.dim
+        if dirichlet_faces is None:
+            dirichlet_faces = (1 << (2 * mesh.dim)) - 1
         self.n1 = degree + 1
         self.np = [degree * v + 1 for v in mesh.n]
         self.n_dofs = int(np.prod(self.np))
@@ -94,11 +97,14 @@ class Space:
         idx = np.arange(self.n_dofs).reshape(self.np[::-1])
         mask = np.zeros(self.np[::-1], bool)
         for ax in range(d):
+            coord = d - 1 - ax                                  # array axis ax <-> coordinate direction
             sl = [slice(None)] * d
-            sl[ax] = 0
-            mask[tuple(sl)] = True
-            sl[ax] = -1
-            mask[tuple(sl)] = True
+            if (dirichlet_faces >> (2 * coord)) & 1:
+                sl[ax] = 0
+                mask[tuple(sl)] = True
+            if (dirichlet_faces >> (2 * coord + 1)) & 1:
+                sl[ax] = -1
+                mask[tuple(sl)] = True
         self.constrained = mask.reshape(-1)
         # cell_dofs[c, local] lexicographic in both
         k = degree

@@ -1,0 +1,102 @@
+"""Multi-process logic of the box partition on CPU (gloo, world_size 2 and 4): brick extents from the
+product's stfem_partition_brick, direction-by-direction compress-add of interface DoFs and the masked
+dot product + all-reduce, emulated with numpy/gloo around the oracle's local operator, must reproduce the
+global operator and the global inner product.  This is the algorithm csrc/dist.cuh runs over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _plane(arr, axis, index):
+    # arr [nb, (nz,) ny, nx]; coordinate axis -> array axis
+    ax = arr.ndim - 1 - axis
+    sl = [slice(None)] * arr.ndim
+    sl[ax] = index
+    return tuple(sl)
+
+
+def _worker(rank, world, port, dim, n_global, k, results):
+    import dealii_stfem_b200 as st
+    from oracle import fe_time as ft, spatial as S
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grid = st.dist.proc_grid_for(world, dim)
+    coords = st.dist.coords_of(rank, grid)
+    lower, upper = [0.0] * dim, [1.0] * dim
+    n_local, off, llo, lup, mask = st.dist.partition_brick(n_global, lower, upper, grid, coords)
+    A, B, _, _ = ft.get_fe_time_weights("DG", 1, 0.05, 1)
+    nb = A.shape[0]
+    # global problem (every rank builds it; small) and global reference result
+    gmesh = S.Mesh(dim, n_global, 0)
+    gspace = S.Space(gmesh, k)
+    gsys = S.SystemMatrix(S.MatrixFreeOperator(gspace, 0, 1), S.MatrixFreeOperator(gspace, 1, 0), A, B)
+    gsrc = np.stack([np.random.RandomState(3 + b).uniform(-1, 1, gspace.n_dofs) for b in range(nb)])
+    gref = gsys.vmult(gsrc)
+    gshape = [nb] + gspace.np[::-1]
+    # local brick
+    lmesh = S.Mesh(dim, n_local, 0, lower=llo, upper=lup)
+    lspace = S.Space(lmesh, k, dirichlet_faces=mask)
+    lsys = S.SystemMatrix(S.MatrixFreeOperator(lspace, 0, 1), S.MatrixFreeOperator(lspace, 1, 0), A, B)
+    sl = tuple([slice(None)] + [slice(k * off[dim - 1 - ax], k * off[dim - 1 - ax] + lspace.np[dim - 1 - ax]) for ax in range(dim)])
+    lsrc = gsrc.reshape(gshape)[sl].reshape(nb, -1)
+    lshape = [nb] + lspace.np[::-1]
+    ldst = lsys.vmult(lsrc).reshape(lshape)
+    # compress-add, direction by direction (csrc/dist.cuh halo_compress_add)
+    for d in range(dim):
+        recv = {}
+        reqs = []
+        for s in (0, 1):
+            c = list(coords)
+            c[d] += -1 if s == 0 else 1
+            if c[d] < 0 or c[d] >= grid[d]:
+                continue
+            nbr = sum(c[a] * int(np.prod(grid[:a])) for a in range(dim))
+            send = torch.from_numpy(np.ascontiguousarray(ldst[_plane(ldst, d, 0 if s == 0 else -1)]))
+            buf = torch.empty_like(send)
+            recv[s] = buf
+            reqs.append(dist.isend(send, nbr))
+            reqs.append(dist.irecv(buf, nbr))
+        for r in reqs:
+            r.wait()
+        for s, buf in recv.items():
+            ldst[_plane(ldst, d, 0 if s == 0 else -1)] += buf.numpy()
+    err = np.abs(ldst - gref.reshape(gshape)[sl]).max() / np.abs(gref).max()
+    # masked dot + allreduce
+    w = np.ones(lshape[1:], bool)
+    for d in range(dim):
+        if coords[d] < grid[d] - 1:
+            w[_plane(w[None], d, -1)[1:]] = False
+    x, y = lsrc.reshape(lshape), ldst
+    local = torch.tensor([float((x * y * w[None]).sum())], dtype=torch.float64)
+    dist.all_reduce(local)
+    gdot = float((gsrc * gref).sum())
+    derr = abs(local.item() - gdot) / abs(gdot)
+    results[rank] = (err, derr)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dim,n_global,k", [(2, 2, [4, 4], 2), (2, 3, [4, 2, 2], 2), (4, 2, [4, 4], 3), (4, 3, [4, 4, 2], 1)])
+def test_box_partition_reproduces_global_operator(world, dim, n_global, k):
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, dim, n_global, k, results), nprocs=world, join=True)
+    assert len(results) == world
+    for r in range(world):
+        err, derr = results[r]
+        assert err < 1e-13, (r, err)
+        assert derr < 1e-13, (r, derr)
