@@ -3,6 +3,7 @@
 #include "basis_host.hpp"
 #include "common.hpp"
 #include "op.hpp"
+#include "st_vmult_cart.cuh"
 #include "st_vmult_generic.cuh"
 
 namespace stfem
@@ -207,10 +208,109 @@ namespace stfem
     return STFEM_OK;
   }
 
+
+  // Cartesian 3D fast path (st_vmult_cart.cuh)
+  template <int N1, typename T, int MAXT, int MINB>
+  static int launch_cart(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
+                         const void *beta)
+  {
+    stfem_mesh      *m = op->mesh;
+    CartArgs<T, N1>  a;
+    const ShapeHost &sh = *op->shape;
+    double           h[3], vol = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        h[d] = (m->upper[d] - m->lower[d]) / m->n[d];
+        vol *= h[d];
+        a.n[d]  = m->n[d];
+        a.np[d] = op->np[d];
+      }
+    for (int i = 0; i < N1; ++i)
+      for (int j = 0; j < N1; ++j)
+        {
+          long double mm = 0, kk = 0;
+          for (int q = 0; q < N1; ++q)
+            {
+              mm += (long double)sh.wq[q] * sh.S[q * N1 + i] * sh.S[q * N1 + j];
+              kk += (long double)sh.wq[q] * sh.D[q * N1 + i] * sh.D[q * N1 + j];
+            }
+          a.M[i * N1 + j]  = (T)mm;
+          a.Ky[i * N1 + j] = (T)(kk / (h[1] * h[1]));
+          a.Kz[i * N1 + j] = (T)(kk / (h[2] * h[2]));
+          a.Mx[i * N1 + j] = (T)(mm * vol);
+          a.Kx[i * N1 + j] = (T)(kk * vol / (h[0] * h[0]));
+        }
+    a.n_cells = m->n_cells;
+    a.nb_src  = nb_src;
+    a.nb_dst  = nb_dst;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
+      {
+        a.src[b] = b < nb_src ? (const T *)src[b] : nullptr;
+        a.dst[b] = b < nb_dst ? (T *)dst[b] : nullptr;
+      }
+    a.alpha      = (const T *)alpha;
+    a.beta       = (const T *)beta;
+    a.coeff_cell = (const T *)op->d_coeff;
+    a.dirichlet  = m->dirichlet;
+    // cells per CTA: fill warps (threads a multiple of 32 if possible), <= 256 threads, <= 72 KB of shared memory
+    const int    tpc     = nb_dst * N1;
+    const size_t per_cell = (size_t)2 * nb_dst * ExchLayout<N1>::CBS * sizeof(T);
+    int          best = 1;
+    double       best_score = -1;
+    const size_t smem_cap = (size_t)(220 * 1024) / MINB;
+    for (int c = 1; c * tpc <= MAXT; ++c)
+      {
+        if (c * per_cell > smem_cap) break;
+        const int    thr = c * tpc;
+        const double eff = (double)thr / (((thr + 31) / 32) * 32);
+        const double score = eff + 1e-4 * thr; // fill warps first, then prefer the larger CTA
+        if (score > best_score + 1e-9)
+          {
+            best_score = score;
+            best       = c;
+          }
+      }
+    STFEM_REQUIRE(tpc <= MAXT && per_cell <= smem_cap, "st_vmult: %d threads per cell / %zu bytes do not fit the CTA (degree %d, %d blocks)",
+                  tpc, per_cell, N1 - 1, nb_dst);
+    a.cells_per_cta      = best;
+    const size_t smem    = best * per_cell;
+    const int    threads = best * tpc;
+    auto         kern    = st_vmult_cart_kernel<N1, T, MAXT, MINB>;
+    if (smem > 48 * 1024)
+      STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (m->n_cells + best - 1) / best;
+    kern<<<(unsigned)grid, threads, smem, m->ctx->stream>>>(a);
+    m->ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
   template <int DIM, typename T>
   static int dispatch_degree(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst,
                              const void *alpha, const void *beta)
   {
+    if (DIM == 3 && op->variant != 1 && op->mesh->cartesian && !op->d_metric)
+      {
+        const int nbd = nb_dst;
+        switch (op->degree)
+          {
+            case 1: return launch_cart<2, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            case 2: return launch_cart<3, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            case 3:
+              // variants 10.. = tuning configurations (launch bounds) of the same kernel
+              if (op->variant == 11 || nbd * 4 > 128) return launch_cart<4, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 12) return launch_cart<4, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              return launch_cart<4, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            case 4:
+              if (op->variant == 11 || nbd * 5 > 128) return launch_cart<5, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 12) return launch_cart<5, T, 160, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 13) return launch_cart<5, T, 192, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 14) return launch_cart<5, T, 96, 4>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              return launch_cart<5, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            case 5: return launch_cart<6, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            default: break;
+          }
+      }
     switch (op->degree)
       {
         case 1: return launch_generic<DIM, 2, T>(op, dst, src, nb_src, nb_dst, alpha, beta);

@@ -1,0 +1,248 @@
+// st_vmult, Cartesian variant (3D): fused application of
+//     dst_j (+)= sum_s  Alpha(j,s) c_cell K src_s + Beta(j,s) M src_s
+// on axis-aligned hexahedra.  Same arithmetic contract as the reference's cell kernel
+// (include/operators.h:1112-1173, quadrature QGauss(k+1), FE_Q(k)) and block loop
+// (SystemMatrix::vmult, include/operators.h:536-559), restructured for the B200 FP64 pipe:
+//
+//  * On a Cartesian cell  M_c = vol  Mh (x) Mh (x) Mh  and
+//    K_c = vol (Kh/hx^2 (x) Mh (x) Mh + Mh (x) Kh/hy^2 (x) Mh + Mh (x) Mh (x) Kh/hz^2)
+//    with the 1D reference matrices Mh = S^T W S, Kh = D^T W D of the Gauss rule, so the
+//    interpolate -> q-point -> integrate chain collapses to 1D matrix applications on NODAL
+//    values: 8 line sweeps per block instead of 12 + quadrature-point work.
+//  * The temporal contraction is done on the nodal values while they are gathered
+//    (v = sum_s Beta(j,s) u_s, w = sum_s Alpha(j,s) c u_s): everything after it is
+//    per destination block, no exchange between time blocks is needed.
+//  * One thread owns one y-z PLANE of a (cell, dst block): N1 x N1 values of v and w in registers,
+//    lanes run along x, so global loads / reductions are coalesced (x is the fastest index).
+//    The y and z sweeps run entirely in registers with the 1D matrices as compile-time indexed
+//    constant-bank operands; ONE exchange through shared memory (fields P, Q) feeds the x sweep.
+//        y:  s = Mh v + Ky w,  t = Mh w          z:  P = Mh s + Kz t,  Q = Mh t
+//        x:  out = (vol Mh) P + (vol Kh/hx^2) Q
+//    Per thread (Q4, nb = 2): ~1100 FMA against ~150 shared-memory accesses, so the kernel is
+//    FP64-pipe bound instead of shared-memory bound (the generic kernel needs an LDS per FMA).
+//  * The cell's space-time block is gathered once and scattered once (RED.ADD per node; nodes on
+//    cell faces get one reduction per adjacent cell, resolved in L2).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/stfem_b200.h"
+
+namespace stfem
+{
+  // shared-memory layout of the exchange buffer: [cell-block][line][x], line stride LS, cell-block
+  // stride CBS; `blocked`: x-sweep thread r takes lines N1*r..N1*r+N1-1, else r, r+N1, ...
+  // (chosen by a bank-conflict search)
+  template <int N1> struct ExchLayout;
+  template <> struct ExchLayout<2> { static constexpr int LS = 3, CBS = 14; static constexpr bool blocked = false; };
+  template <> struct ExchLayout<3> { static constexpr int LS = 3, CBS = 27; static constexpr bool blocked = true; };
+  template <> struct ExchLayout<4> { static constexpr int LS = 5, CBS = 84; static constexpr bool blocked = false; };
+  template <> struct ExchLayout<5> { static constexpr int LS = 5, CBS = 125; static constexpr bool blocked = true; };
+  template <> struct ExchLayout<6> { static constexpr int LS = 7, CBS = 266; static constexpr bool blocked = false; };
+  template <> struct ExchLayout<7> { static constexpr int LS = 7, CBS = 343; static constexpr bool blocked = true; };
+
+  template <typename T, int N1>
+  struct CartArgs
+  {
+    T         M[N1 * N1];                  // Mh (y and z sweeps)
+    T         Ky[N1 * N1], Kz[N1 * N1];    // Kh / hy^2, Kh / hz^2
+    T         Mx[N1 * N1], Kx[N1 * N1];    // vol * Mh, vol * Kh / hx^2
+    int       n[3], np[3];
+    long long n_cells;
+    int       nb_src, nb_dst, cells_per_cta;
+    unsigned  dirichlet;
+    const T  *src[STFEM_MAX_BLOCKS];
+    T        *dst[STFEM_MAX_BLOCKS];
+    const T  *alpha, *beta; // device, nb_dst x nb_src row-major
+    const T  *coeff_cell;   // optional per-cell Laplace coefficient
+  };
+
+  // MAXT / MINB: launch bounds (threads per CTA, resident CTAs per SM) = the register budget ptxas gets
+  template <int N1, typename T, int MAXT, int MINB>
+  __global__ void __launch_bounds__(MAXT, MINB) st_vmult_cart_kernel(const __grid_constant__ CartArgs<T, N1> a)
+  {
+    using L           = ExchLayout<N1>;
+    constexpr int K   = N1 - 1;
+    constexpr int LS  = L::LS;
+    constexpr int CBS = L::CBS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *bufP = reinterpret_cast<T *>(smem_raw);
+    T *bufQ = bufP + (size_t)a.cells_per_cta * a.nb_dst * CBS;
+
+    const int tid  = threadIdx.x;
+    const int tpc  = a.nb_dst * N1; // threads per cell
+    const int slot = tid / tpc;
+    const int rem  = tid - slot * tpc;
+    const int j    = rem / N1;     // destination block
+    const int i    = rem - j * N1; // x index of this thread's plane (phases A, C); line group (phase B)
+    const int cb   = tid / N1;     // cell-block slot in shared memory
+
+    const long long cell   = (long long)blockIdx.x * a.cells_per_cta + slot;
+    const bool      active = cell < a.n_cells;
+    int             cx = 0, cy = 0, cz = 0;
+    if (active)
+      {
+        long long c = cell;
+        cx          = (int)(c % a.n[0]);
+        c /= a.n[0];
+        cy = (int)(c % a.n[1]);
+        cz = (int)(c / a.n[1]);
+      }
+    const unsigned dm  = a.dirichlet;
+    const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;
+    const bool     ylo = (dm & 4u) && cy == 0, yhi = (dm & 8u) && cy == a.n[1] - 1;
+    const bool     zlo = (dm & 16u) && cz == 0, zhi = (dm & 32u) && cz == a.n[2] - 1;
+    const bool     plane_constrained = (xlo && i == 0) || (xhi && i == K);
+    const bool     any_yz            = ylo || yhi || zlo || zhi;
+    const int      sy                = a.np[0];
+    const int      sz                = a.np[0] * a.np[1];
+    const long long base = (long long)(cx * K + i) + (long long)a.np[0] * ((long long)(cy * K) + (long long)a.np[1] * (cz * K));
+
+    // ---------------- phase A: gather + temporal contraction (read_dof_values: constrained -> 0)
+    T v[N1][N1], w[N1][N1]; // [z][y]
+#pragma unroll
+    for (int k = 0; k < N1; ++k)
+#pragma unroll
+      for (int jy = 0; jy < N1; ++jy) v[k][jy] = w[k][jy] = T(0);
+    if (active && !plane_constrained)
+      {
+        const T coef = a.coeff_cell ? a.coeff_cell[cell] : T(1);
+        for (int s = 0; s < a.nb_src; ++s)
+          {
+            const T  be = a.beta[j * a.nb_src + s];
+            const T  al = a.alpha[j * a.nb_src + s] * coef;
+            const T *p  = a.src[s] + base;
+            if (!any_yz)
+              {
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy)
+                    {
+                      const T u = p[jy * sy + k * sz];
+                      v[k][jy] += be * u;
+                      w[k][jy] += al * u;
+                    }
+              }
+            else
+              {
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy)
+                    {
+                      const bool c = (ylo && jy == 0) || (yhi && jy == K) || (zlo && k == 0) || (zhi && k == K);
+                      const T    u = c ? T(0) : p[jy * sy + k * sz];
+                      v[k][jy] += be * u;
+                      w[k][jy] += al * u;
+                    }
+              }
+          }
+      }
+
+    // ---------------- y sweep (registers):  s = Mh v + Ky w,  t = Mh w
+#pragma unroll
+    for (int k = 0; k < N1; ++k)
+      {
+        T s[N1], t[N1];
+#pragma unroll
+        for (int q = 0; q < N1; ++q)
+          {
+            T ss = T(0), tt = T(0);
+#pragma unroll
+            for (int jy = 0; jy < N1; ++jy)
+              {
+                ss += a.M[q * N1 + jy] * v[k][jy];
+                ss += a.Ky[q * N1 + jy] * w[k][jy];
+                tt += a.M[q * N1 + jy] * w[k][jy];
+              }
+            s[q] = ss;
+            t[q] = tt;
+          }
+#pragma unroll
+        for (int q = 0; q < N1; ++q)
+          {
+            v[k][q] = s[q];
+            w[k][q] = t[q];
+          }
+      }
+
+    // ---------------- z sweep (registers) + publish:  P = Mh s + Kz t,  Q = Mh t
+    {
+      T *pP = bufP + cb * CBS + i;
+      T *pQ = bufQ + cb * CBS + i;
+#pragma unroll
+      for (int jy = 0; jy < N1; ++jy)
+#pragma unroll
+        for (int q = 0; q < N1; ++q)
+          {
+            T pp = T(0), qq = T(0);
+#pragma unroll
+            for (int k = 0; k < N1; ++k)
+              {
+                pp += a.M[q * N1 + k] * v[k][jy];
+                pp += a.Kz[q * N1 + k] * w[k][jy];
+                qq += a.M[q * N1 + k] * w[k][jy];
+              }
+            pP[(q * N1 + jy) * LS] = pp;
+            pQ[(q * N1 + jy) * LS] = qq;
+          }
+    }
+    __syncthreads();
+
+    // ---------------- phase B: x sweep on N1 lines of this cell-block, result overwrites P
+    {
+#pragma unroll
+      for (int m = 0; m < N1; ++m)
+        {
+          const int line = L::blocked ? N1 * i + m : i + N1 * m;
+          T        *pP   = bufP + cb * CBS + line * LS;
+          const T  *pQ   = bufQ + cb * CBS + line * LS;
+          T         P[N1], Q[N1];
+#pragma unroll
+          for (int x = 0; x < N1; ++x)
+            {
+              P[x] = pP[x];
+              Q[x] = pQ[x];
+            }
+#pragma unroll
+          for (int q = 0; q < N1; ++q)
+            {
+              T o = T(0);
+#pragma unroll
+              for (int x = 0; x < N1; ++x)
+                {
+                  o += a.Mx[q * N1 + x] * P[x];
+                  o += a.Kx[q * N1 + x] * Q[x];
+                }
+              pP[q] = o;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase C: scatter-add (distribute_local_to_global: constrained rows skipped)
+    if (active && !plane_constrained)
+      {
+        T       *d  = a.dst[j] + base;
+        const T *pP = bufP + cb * CBS + i;
+        if (!any_yz)
+          {
+#pragma unroll
+            for (int k = 0; k < N1; ++k)
+#pragma unroll
+              for (int jy = 0; jy < N1; ++jy) atomicAdd(d + jy * sy + k * sz, pP[(k * N1 + jy) * LS]);
+          }
+        else
+          {
+#pragma unroll
+            for (int k = 0; k < N1; ++k)
+#pragma unroll
+              for (int jy = 0; jy < N1; ++jy)
+                {
+                  const bool c = (ylo && jy == 0) || (yhi && jy == K) || (zlo && k == 0) || (zhi && k == K);
+                  if (!c) atomicAdd(d + jy * sy + k * sz, pP[(k * N1 + jy) * LS]);
+                }
+          }
+      }
+  }
+} // namespace stfem

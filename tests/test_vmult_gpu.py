@@ -174,3 +174,85 @@ def test_per_cell_coefficient_cartesian(ctx):
         op.vmult(d_dst, d_src)
         assert _rel(d_dst.download(), ref_dst) < 1e-12
         d_src.free(); d_dst.free(); op.close(); gm.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Cartesian 3D fast path (csrc/st_vmult_cart.cuh): nodal 1D-matrix form of the same operator.  Checked against the
+# oracle AND against the generic q-point kernel (variant 1) on anisotropic boxes, partial Dirichlet masks, all
+# supported degrees, rectangular time matrices and per-cell coefficients.
+CART_CASES = [
+    # k, subdivisions, upper, ttype, r, nts, dirichlet mask
+    (1, [3, 2, 2], [1.5, 1.0, 0.5], "DG", 1, 1, 0x3f),
+    (2, [2, 3, 1], [1.0, 2.0, 0.7], "CGP", 2, 1, 0x3f),
+    (3, [2, 2, 3], [1.0, 1.0, 1.0], "DG", 2, 1, 0x15),       # Dirichlet on the three lower faces only
+    (4, [3, 2, 2], [1.2, 0.8, 1.0], "CGP", 2, 1, 0x3f),      # config 2 family
+    (4, [2, 2, 2], [1.0, 1.0, 1.0], "DG", 1, 2, 0x2a),       # 4 blocks, upper faces
+    (4, [5, 1, 1], [1.0, 1.0, 1.0], "DG", 2, 1, 0x00),       # no constraints, nb = 3
+    (5, [2, 1, 2], [1.0, 0.5, 1.0], "DG", 0, 1, 0x3f),
+]
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("case", CART_CASES, ids=lambda c: "k%d_%s_%s%d_x%d_m%x" % (c[0], "x".join(map(str, c[1])), c[3], c[4], c[5], c[6]))
+def test_cartesian_kernel(ctx, case, number_type):
+    import dealii_stfem_b200 as st
+    k, sub, upper, ttype, r, nts, mask = case
+    mesh = S.Mesh(3, sub, 0, lower=[0, 0, 0], upper=upper)
+    space = S.Space(mesh, k, dirichlet_faces=mask)
+    A, B, _, _ = _time_matrices(ttype, r, nts)
+    nb = A.shape[0]
+    dt = np.float64 if number_type == 0 else np.float32
+    sysm = S.SystemMatrix(S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0), A, B)
+    src = _rand_block(nb, space.n_dofs).astype(dt)
+    ref_dst = sysm.vmult(src.astype(np.float64))
+    ref_t = sysm.Tvmult(src.astype(np.float64))
+    gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper, dirichlet_faces=mask)
+    outs = {}
+    for variant in (0, 1):
+        op = st.Operator(gm, k, A, B, number_type=number_type, variant=variant)
+        d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+        op.vmult(d_dst, d_src)
+        out = d_dst.download()
+        assert _rel(out.astype(np.float64), ref_dst) < TOL[number_type], "variant %d" % variant
+        assert np.all(out[:, space.constrained] == 0)
+        op.Tvmult(d_dst, d_src)
+        assert _rel(d_dst.download().astype(np.float64), ref_t) < TOL[number_type], "variant %d (T)" % variant
+        outs[variant] = out
+        d_src.free(); d_dst.free(); op.close()
+    assert _rel(outs[0].astype(np.float64), outs[1].astype(np.float64)) < TOL[number_type]
+    gm.close()
+
+
+def test_cartesian_kernel_slice_and_cell_coefficient(ctx):
+    import dealii_stfem_b200 as st
+    k = 4
+    mesh = S.Mesh(3, [5, 5, 5], 0, lower=[-1, -1, -1], upper=[1, 1, 1])
+    space = S.Space(mesh, k)
+    coef = S.Coefficient(3, [5, 5, 5], [-1, -1, -1], [1, 1, 1], distort_coeff=0.5)
+    K = S.MatrixFreeOperator(space, 0.0, 1.0)
+    K.evaluate_coefficient(coef)
+    M = S.MatrixFreeOperator(space, 1.0, 0.0)
+    cc = K.laplace_coeff[:, 0].copy()
+    gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper)
+    # square system with a per-cell coefficient
+    A, B, G, Z = _time_matrices("CGP", 3, 1)
+    sysm = S.SystemMatrix(K, M, A, B)
+    src = _rand_block(A.shape[0], space.n_dofs)
+    op = st.Operator(gm, k, A, B, laplace_coeff_cell=cc)
+    d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+    op.vmult(d_dst, d_src)
+    assert _rel(d_dst.download(), sysm.vmult(src)) < 1e-12
+    d_src.free(); d_dst.free(); op.close()
+    # nb x 1 slice operator accumulating into dst (operators.h:586-611)
+    sl = S.SystemMatrix(K, M, G, Z)
+    nb = G.shape[0]
+    src0 = _rand_block(1, space.n_dofs, seed=7)
+    dst0 = _rand_block(nb, space.n_dofs, seed=9)
+    dst0[:, space.constrained] = 0
+    ref_dst = sl.vmult_slice_add(dst0.copy(), src0[0])
+    op = st.Operator(gm, k, G, Z, laplace_coeff_cell=cc)
+    d_src = op.new_vector(1).upload(src0)
+    d_dst = op.new_vector(nb).upload(dst0)
+    op.vmult_slice_add(d_dst, d_src)
+    assert _rel(d_dst.download(), ref_dst) < 1e-12
+    d_src.free(); d_dst.free(); op.close(); gm.close()
