@@ -124,40 +124,66 @@ namespace stfem
     return false;
   }
 
-  // rhs_i += scale * sum_q f(x_q, t) phi_i(x_q) JxW ; one thread per (cell, local dof); constrained rows skipped
+  // rhs_i += scale * sum_q f(x_q, t) phi_i(x_q) JxW ; one CTA per cell: f JxW is evaluated ONCE per quadrature
+  // point into shared memory, then integrated by sum factorisation (one tensor direction per pass);
+  // constrained rows skipped
   static __global__ void k_integrate_function(AsmGeom g, int fid, double t, double freq, double scale, double *__restrict__ rhs)
   {
     const int dim = g.dim, n1 = g.n1, nq1 = g.nq1, k = n1 - 1;
-    const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
     const int nq = dim == 3 ? nq1 * nq1 * nq1 : nq1 * nq1;
-    const long long total = g.n_cells * nc;
-    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+    const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    __shared__ double bufA[512], bufB[512]; // nq1, n1 <= 8
+    for (long long cell = blockIdx.x; cell < g.n_cells; cell += gridDim.x)
       {
-        const long long cell = gid / nc;
-        const int       l    = (int)(gid % nc);
-        const int c[3]  = {(int)(cell % g.n[0]), (int)((cell / g.n[0]) % g.n[1]), dim == 3 ? (int)(cell / ((long long)g.n[0] * g.n[1])) : 0};
-        const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
-        const int gi[3] = {c[0] * k + li[0], c[1] * k + li[1], c[2] * k + li[2]};
-        if (asm_constrained(g, gi[0], gi[1], gi[2])) continue;
-        double s = 0;
-        for (int q = 0; q < nq; ++q)
+        const int c[3] = {(int)(cell % g.n[0]), (int)((cell / g.n[0]) % g.n[1]), dim == 3 ? (int)(cell / ((long long)g.n[0] * g.n[1])) : 0};
+        __syncthreads();
+        for (int q = threadIdx.x; q < nq; q += blockDim.x)
           {
             const int    qi[3] = {q % nq1, (q / nq1) % nq1, dim == 3 ? q / (nq1 * nq1) : 0};
             const double xi[3] = {g.xq[qi[0]], g.xq[qi[1]], dim == 3 ? g.xq[qi[2]] : 0.0};
             double       x[3], J[3][3], inv[3][3];
             map_q1(g, c, xi, x, J);
             const double det = det_inv(dim, J, inv);
-            double       phi = g.S[qi[0] * n1 + li[0]] * g.S[qi[1] * n1 + li[1]];
-            double       w   = g.wq[qi[0]] * g.wq[qi[1]];
+            const double w   = g.wq[qi[0]] * g.wq[qi[1]] * (dim == 3 ? g.wq[qi[2]] : 1.0);
+            bufA[q]          = analytic_value(fid, dim, x, t, freq) * det * w;
+          }
+        __syncthreads();
+        // x: A[qz][qy][qx] -> B[qz][qy][lx]
+        const int rows_x = dim == 3 ? nq1 * nq1 : nq1;
+        for (int o = threadIdx.x; o < rows_x * n1; o += blockDim.x)
+          {
+            const int row = o / n1, lx = o % n1;
+            double    s   = 0;
+            for (int qx = 0; qx < nq1; ++qx) s += g.S[qx * n1 + lx] * bufA[row * nq1 + qx];
+            bufB[o] = s;
+          }
+        __syncthreads();
+        // y: B[qz][qy][lx] -> A[qz][ly][lx]
+        const int nz_q = dim == 3 ? nq1 : 1;
+        for (int o = threadIdx.x; o < nz_q * n1 * n1; o += blockDim.x)
+          {
+            const int lx = o % n1, ly = (o / n1) % n1, qz = o / (n1 * n1);
+            double    s  = 0;
+            for (int qy = 0; qy < nq1; ++qy) s += g.S[qy * n1 + ly] * bufB[(qz * nq1 + qy) * n1 + lx];
+            bufA[o] = s;
+          }
+        __syncthreads();
+        for (int l = threadIdx.x; l < nc; l += blockDim.x)
+          {
+            const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
+            double    s;
             if (dim == 3)
               {
-                phi *= g.S[qi[2] * n1 + li[2]];
-                w *= g.wq[qi[2]];
+                s = 0;
+                for (int qz = 0; qz < nq1; ++qz) s += g.S[qz * n1 + li[2]] * bufA[(qz * n1 + li[1]) * n1 + li[0]];
               }
-            s += analytic_value(fid, dim, x, t, freq) * phi * det * w;
+            else
+              s = bufA[l];
+            const int gi[3] = {c[0] * k + li[0], c[1] * k + li[1], c[2] * k + li[2]};
+            if (asm_constrained(g, gi[0], gi[1], gi[2])) continue;
+            const long long dof = (long long)gi[0] + (long long)g.np[0] * (gi[1] + (long long)g.np[1] * gi[2]);
+            atomicAdd(rhs + dof, scale * s);
           }
-        const long long dof = (long long)gi[0] + (long long)g.np[0] * (gi[1] + (long long)g.np[1] * gi[2]);
-        atomicAdd(rhs + dof, scale * s);
       }
   }
 

@@ -407,9 +407,14 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
         AT[j * nr + i] = op->Alpha[i * nc + j];
         BT[j * nr + i] = op->Beta[i * nc + j];
       }
+  std::vector<double> AN(op->Alpha), BN(op->Beta);
+  for (auto &v : AN) v = -v;
+  for (auto &v : BN) v = -v;
   const bool f64 = desc->number_type == STFEM_F64;
   if (f64)
     {
+      STFEM_FORWARD(upload_matrix<double>(ctx, AN, &op->d_alpha_neg));
+      STFEM_FORWARD(upload_matrix<double>(ctx, BN, &op->d_beta_neg));
       STFEM_FORWARD(upload_matrix<double>(ctx, op->Alpha, &op->d_alpha));
       STFEM_FORWARD(upload_matrix<double>(ctx, op->Beta, &op->d_beta));
       STFEM_FORWARD(upload_matrix<double>(ctx, AT, &op->d_alphaT));
@@ -417,6 +422,8 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
     }
   else
     {
+      STFEM_FORWARD(upload_matrix<float>(ctx, AN, &op->d_alpha_neg));
+      STFEM_FORWARD(upload_matrix<float>(ctx, BN, &op->d_beta_neg));
       STFEM_FORWARD(upload_matrix<float>(ctx, op->Alpha, &op->d_alpha));
       STFEM_FORWARD(upload_matrix<float>(ctx, op->Beta, &op->d_beta));
       STFEM_FORWARD(upload_matrix<float>(ctx, AT, &op->d_alphaT));
@@ -449,7 +456,7 @@ int stfem_op_destroy(stfem_op_t op)
   if (!op) return STFEM_OK;
   cudaSetDevice(op->mesh->ctx->device);
   cudaStreamSynchronize(op->mesh->ctx->stream);
-  for (void *p : {op->d_alpha, op->d_beta, op->d_alphaT, op->d_betaT, op->d_metric, op->d_coeff})
+  for (void *p : {op->d_alpha, op->d_beta, op->d_alphaT, op->d_betaT, op->d_alpha_neg, op->d_beta_neg, op->d_metric, op->d_coeff})
     if (p) cudaFree(p);
   for (void *p : op->d_scratch)
     if (p) cudaFree(p);

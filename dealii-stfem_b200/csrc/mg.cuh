@@ -8,6 +8,7 @@
 //   deal.II SolverFGMRES + ReductionControl  (include/time_integrators.h:56-59, 315)
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "fe_time.hpp"
@@ -76,6 +77,37 @@ namespace stfem
       return op_apply(op, dst.block_ptrs(), src.cblock_ptrs(), op->nb_cols, op->nb_rows, op->d_alpha, op->d_beta, true);
     }
 
+    // r = b - A x.  Single GPU: r is initialised with b and the operator kernel reduces -A x into it (no
+    // separate vector update); partitioned meshes go through a temporary so that only A x is summed over ranks.
+    int residual(int l, BlockVec<T> &r, const BlockVec<T> &x, const BlockVec<T> &b)
+    {
+      stfem_op *op = L[l].op;
+      if (op->mesh->part.active)
+        {
+          STFEM_FORWARD(A(l, r, x));
+          v_sadd(r, (T)-1, (T)1, b);
+          return STFEM_OK;
+        }
+      STFEM_FORWARD(v_copy(r, b));
+      return op_apply(op, r.block_ptrs(), x.cblock_ptrs(), op->nb_cols, op->nb_rows, op->d_alpha_neg, op->d_beta_neg, false);
+    }
+    // dst += scale * P^-1 src  (Vanka); partitioned meshes: the increment is summed over ranks before it is added
+    int vanka_add(int l, BlockVec<T> &dst, const BlockVec<T> &src, T scale)
+    {
+      MGLevel<T> &lv = L[l];
+      if (lv.op->mesh->part.active)
+        {
+          if (tmp_part.size() <= (size_t)l) tmp_part.resize(L.size());
+          if (!tmp_part[l].d) STFEM_FORWARD(tmp_part[l].alloc(ctx, src.nb, src.n));
+          STFEM_FORWARD(lv.vanka->vmult(tmp_part[l], src));
+          STFEM_FORWARD(halo_compress_add<T>(ctx, lv.op->mesh->part, lv.op->halo, tmp_part[l].block_ptrs(), src.nb, lv.op->np, lv.op->mesh->dim));
+          v_axpy(dst, scale, tmp_part[l]);
+          return STFEM_OK;
+        }
+      return lv.vanka->vmult_add(dst, src, scale);
+    }
+    std::vector<BlockVec<T>> tmp_part;
+
     // PreconditionSTMG::vmult(dst, src)   (stmg.h:1018-1023)
     int smoother_vmult(int l, BlockVec<T> &dst, const BlockVec<T> &src)
     {
@@ -84,21 +116,19 @@ namespace stfem
       if (lv.smoother == 1)
         {
           // PreconditionRelaxation: x = w P^-1 b ; n_it-1 times x += w P^-1 (b - A x)
-          STFEM_FORWARD(lv.vanka->vmult(dst, src));
-          v_scale(dst, (T)lv.omega);
+          STFEM_FORWARD(dst.zero());
+          STFEM_FORWARD(vanka_add(l, dst, src, (T)lv.omega));
           for (int it = 1; it < opt.smoothing_steps; ++it)
             {
-              STFEM_FORWARD(A(l, lv.d2, dst));
-              v_sadd(lv.d2, (T)-1, (T)1, src); // d2 = b - A x
-              STFEM_FORWARD(lv.vanka->vmult(lv.t, lv.d2));
-              v_axpy(dst, (T)lv.omega, lv.t);
+              STFEM_FORWARD(residual(l, lv.d2, dst, src));
+              STFEM_FORWARD(vanka_add(l, dst, lv.d2, (T)lv.omega));
             }
           return STFEM_OK;
         }
       // Chebyshev of degree smoothing_steps, zero start vector
       const double th = lv.theta, de = lv.delta;
-      STFEM_FORWARD(lv.vanka->vmult(lv.d2, src));
-      v_scale(lv.d2, (T)(1.0 / th)); // d
+      STFEM_FORWARD(lv.d2.zero());
+      STFEM_FORWARD(vanka_add(l, lv.d2, src, (T)(1.0 / th))); // d
       STFEM_FORWARD(v_copy(dst, lv.d2));
       if (opt.smoothing_steps < 2) return STFEM_OK;
       const bool   fin = de != 0.0;
@@ -107,13 +137,10 @@ namespace stfem
       for (int it = 1; it < opt.smoothing_steps; ++it)
         {
           const double rho = fin ? 1.0 / (2.0 * sigma - rho_old) : 0.0;
-          STFEM_FORWARD(A(l, lv.t, dst));
-          v_sadd(lv.t, (T)-1, (T)1, src); // r = b - A x
+          STFEM_FORWARD(residual(l, lv.t, dst, src)); // r = b - A x
           // d = rho*rho_old*d + (2 rho/delta) P^-1 r   (delta = 0: plain Richardson with 1/theta)
-          BlockVec<T> &pr = lv.sol; // scratch: only used outside the V-cycle recursion of this level's smoother
-          (void)pr;
-          STFEM_FORWARD(lv.vanka->vmult(lv.r, lv.t));
-          v_sadd(lv.d2, (T)(rho * rho_old), (T)(fin ? 2.0 * rho / de : 1.0 / th), lv.r);
+          v_scale(lv.d2, (T)(rho * rho_old));
+          STFEM_FORWARD(vanka_add(l, lv.d2, lv.t, (T)(fin ? 2.0 * rho / de : 1.0 / th)));
           v_axpy(dst, (T)1, lv.d2);
           rho_old = rho;
         }
@@ -131,36 +158,20 @@ namespace stfem
     int smooth_step(int l, BlockVec<T> &u, const BlockVec<T> &rhs)
     {
       MGLevel<T> &lv = L[l];
-      STFEM_FORWARD(A(l, lv.r, u));
-      v_sadd(lv.r, (T)-1, (T)1, rhs);
-      // the smoother uses lv.t/lv.d2/lv.r as scratch: keep the residual in lv.d
-      STFEM_FORWARD(v_copy(lv.d, lv.r));
-      BlockVec<T> &corr = lv.t;
+      // the smoother uses lv.t/lv.d2/lv.r as scratch: the residual lives in lv.d
+      STFEM_FORWARD(residual(l, lv.d, u, rhs));
       if (lv.smoother == 0)
         {
           v_axpy(u, (T)1, lv.d);
           return STFEM_OK;
         }
-      // result of the smoother must not alias its scratch: smoother_vmult writes dst first into `corr2`
-      STFEM_FORWARD(smoother_vmult_into(l, corr, lv.d));
+      if (lv.smoother == 1 && opt.smoothing_steps == 1) // u += w P^-1 r in one fused scatter
+        return vanka_add(l, u, lv.d, (T)lv.omega);
+      BlockVec<T> &corr = lv.r;
+      STFEM_FORWARD(smoother_vmult(l, corr, lv.d));
       v_axpy(u, (T)1, corr);
       return STFEM_OK;
     }
-    // smoother_vmult with dst = lv.t: for relaxation steps>1 and Chebyshev the scratch lv.t is needed, use lv.sol2
-    int smoother_vmult_into(int l, BlockVec<T> &dst, const BlockVec<T> &src)
-    {
-      MGLevel<T> &lv = L[l];
-      if (lv.smoother != 0 && opt.smoothing_steps > 1)
-        {
-          // dst aliases lv.t which the multi-step smoothers use: go through a private buffer
-          if (tmp_multi.size() <= (size_t)l) tmp_multi.resize(L.size());
-          if (!tmp_multi[l].d) STFEM_FORWARD(tmp_multi[l].alloc(ctx, src.nb, src.n));
-          STFEM_FORWARD(smoother_vmult(l, tmp_multi[l], src));
-          return v_copy(dst, tmp_multi[l]);
-        }
-      return smoother_vmult(l, dst, src);
-    }
-    std::vector<BlockVec<T>> tmp_multi;
 
     // Multigrid::level_v_step; defect in L[l].defect, result in L[l].sol
     int v_step(int l)
@@ -171,8 +182,7 @@ namespace stfem
       // t = defect - A sol
       {
         BlockVec<T> &res = lv.d;
-        STFEM_FORWARD(A(l, res, lv.sol));
-        v_sadd(res, (T)-1, (T)1, lv.defect);
+        STFEM_FORWARD(residual(l, res, lv.sol, lv.defect));
         MGLevel<T> &lc = L[l - 1];
         STFEM_FORWARD(lc.defect.zero());
         if (lv.ttype == 'h' || lv.ttype == 'p')
@@ -213,7 +223,8 @@ namespace stfem
           for (int it = 0; it < opt.eig_n_iterations; ++it)
             {
               STFEM_FORWARD(A(l, tmp, v));
-              STFEM_FORWARD(lv.vanka->vmult(w, tmp));
+              STFEM_FORWARD(w.zero());
+              STFEM_FORWARD(vanka_add(l, w, tmp, (T)1));
               double                           out[2];
               std::vector<const BlockVec<T> *> V{&v, &w};
               STFEM_FORWARD(v_multi_dot(sc, w, V, out));
@@ -301,6 +312,12 @@ namespace stfem
       return STFEM_OK;
     }
 
+    static bool contiguous(const void *const *p, int nb, long long n, size_t elem)
+    {
+      for (int b = 1; b < nb; ++b)
+        if ((const char *)p[b] != (const char *)p[0] + (size_t)b * n * elem) return false;
+      return true;
+    }
     int stage_in(BlockVec<T> &dst, const void *const *src, int nb, long long n)
     {
       if (std::is_same<T, double>::value)
@@ -309,10 +326,15 @@ namespace stfem
             STFEM_CUDA_CHECK(cudaMemcpyAsync((char *)dst.d + sizeof(T) * (size_t)b * n, src[b], sizeof(T) * n, cudaMemcpyDeviceToDevice, ctx->stream));
           return STFEM_OK;
         }
-      if (!src64.d) STFEM_FORWARD(src64.alloc(ctx, nb, n));
-      for (int b = 0; b < nb; ++b)
-        STFEM_CUDA_CHECK(cudaMemcpyAsync(src64.d + (size_t)b * n, src[b], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-      k_convert<T, double><<<grid_for(ctx, dst.size(), 256), 256, 0, ctx->stream>>>(dst.size(), src64.d, dst.d);
+      const double *from = (const double *)src[0];
+      if (!contiguous(src, nb, n, sizeof(double)))
+        {
+          if (!src64.d) STFEM_FORWARD(src64.alloc(ctx, nb, n));
+          for (int b = 0; b < nb; ++b)
+            STFEM_CUDA_CHECK(cudaMemcpyAsync(src64.d + (size_t)b * n, src[b], sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+          from = src64.d;
+        }
+      k_convert<T, double><<<grid_for(ctx, dst.size(), 256), 256, 0, ctx->stream>>>(dst.size(), from, dst.d);
       ctx->launches++;
       return STFEM_OK;
     }
@@ -324,6 +346,12 @@ namespace stfem
             STFEM_CUDA_CHECK(cudaMemcpyAsync(dst[b], (const char *)src.d + sizeof(T) * (size_t)b * n, sizeof(T) * n, cudaMemcpyDeviceToDevice, ctx->stream));
           return STFEM_OK;
         }
+      if (contiguous(dst, nb, n, sizeof(double)))
+        {
+          k_convert<double, T><<<grid_for(ctx, src.size(), 256), 256, 0, ctx->stream>>>(src.size(), src.d, (double *)dst[0]);
+          ctx->launches++;
+          return STFEM_OK;
+        }
       if (!dst64.d) STFEM_FORWARD(dst64.alloc(ctx, nb, n));
       k_convert<double, T><<<grid_for(ctx, src.size(), 256), 256, 0, ctx->stream>>>(src.size(), src.d, dst64.d);
       ctx->launches++;
@@ -332,12 +360,48 @@ namespace stfem
       return STFEM_OK;
     }
 
+    // The V-cycle between the two precision copies is a fixed launch sequence without host decisions: it is
+    // captured once into a CUDA graph (after one eager pass has made every lazy allocation) and replayed.
+    cudaGraphExec_t graph_exec = nullptr;
+    long long       graph_launches = 0;
+    int             n_vcycles = 0;
+    ~Multigrid()
+    {
+      if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    }
+    int cycle()
+    {
+      const int  top      = (int)L.size() - 1;
+      static const bool no_graph = std::getenv("STFEM_NO_GRAPH") != nullptr;
+      const bool part     = L[top].op->mesh->part.active;
+      bool       timing   = false;
+      for (auto &lv : L) timing = timing || lv.op->timing;
+      if (no_graph || part || timing || n_vcycles++ == 0) return v_step(top);
+      if (!graph_exec)
+        {
+          cudaGraph_t     graph = nullptr;
+          const long long l0    = ctx->launches;
+          STFEM_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+          const int rc = v_step(top);
+          const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+          if (rc != STFEM_OK) return rc;
+          STFEM_CUDA_CHECK(ce);
+          graph_launches = ctx->launches - l0;
+          ctx->launches  = l0;
+          STFEM_CUDA_CHECK(cudaGraphInstantiate(&graph_exec, graph, 0));
+          cudaGraphDestroy(graph);
+        }
+      STFEM_CUDA_CHECK(cudaGraphLaunch(graph_exec, ctx->stream));
+      ctx->launches += graph_launches;
+      return STFEM_OK;
+    }
+
     // GMG::vmult (stmg.h:1331-1344): double in, one V-cycle in level precision, double out
     int vmult(void *const *dst, const void *const *src) override
     {
       MGLevel<T> &top = L.back();
       STFEM_FORWARD(stage_in(top.defect, src, top.op->nb_rows, top.op->N));
-      STFEM_FORWARD(v_step((int)L.size() - 1));
+      STFEM_FORWARD(cycle());
       return stage_out(dst, top.sol, top.op->nb_rows, top.op->N);
     }
 
@@ -361,7 +425,8 @@ namespace stfem
           case 0: // Vanka
             STFEM_REQUIRE(lv.vanka, "level %d has no Vanka smoother", l);
             STFEM_FORWARD(load(lv.defect, src));
-            STFEM_FORWARD(lv.vanka->vmult(lv.sol, lv.defect));
+            STFEM_FORWARD(lv.sol.zero());
+            STFEM_FORWARD(vanka_add(l, lv.sol, lv.defect, (T)1));
             return store(dst, lv.sol);
           case 1: // PreconditionSTMG::vmult
             STFEM_FORWARD(load(lv.defect, src));

@@ -13,6 +13,7 @@ struct stfem_op
   std::unique_ptr<stfem::ShapeHost> shape;
   std::vector<double> Alpha, Beta; // host copies, row-major nb_rows x nb_cols
   void *d_alpha = nullptr, *d_beta = nullptr, *d_alphaT = nullptr, *d_betaT = nullptr;
+  void *d_alpha_neg = nullptr, *d_beta_neg = nullptr; // -Alpha, -Beta: residual r = b - A x in one cell loop
   void *d_metric = nullptr; // general geometry: per cell, per q-point metric (+JxW)
   void *d_coeff = nullptr;  // per-cell Laplace coefficient
   std::vector<double> h_coeff_cell, h_coeff_q; // host copies (Vanka set-up works in double)

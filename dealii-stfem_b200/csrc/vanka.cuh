@@ -9,6 +9,7 @@
 // with constant coefficients only the <= 3^dim distinct patches are stored (the reference stores one per cell).
 #pragma once
 #include "op.hpp"
+#include "vanka_fd.cuh"
 #include "vec.cuh"
 
 namespace stfem
@@ -243,7 +244,7 @@ namespace stfem
 
   // dst += R_c^T B_c^-1 R_c src   for every cell; one CTA per cell, one thread per patch row
   template <typename T>
-  __global__ void k_vanka_apply(VankaApplyArgs a, const T *__restrict__ invT, const T *__restrict__ src, T *__restrict__ dst)
+  __global__ void k_vanka_apply(VankaApplyArgs a, const T *__restrict__ invT, const T *__restrict__ src, T *__restrict__ dst, T scale)
   {
     extern __shared__ __align__(16) unsigned char vk_smem[];
     T            *x  = reinterpret_cast<T *>(vk_smem);
@@ -291,7 +292,7 @@ namespace stfem
             const int b = r / nc, l = r % nc;
             const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
             const long long gi = (long long)(c[0] * k + li[0]) + (long long)a.np[0] * ((c[1] * k + li[1]) + (long long)a.np[1] * (c[2] * k + li[2]));
-            atomicAdd(dst + (size_t)b * a.N + gi, s);
+            atomicAdd(dst + (size_t)b * a.N + gi, scale * s);
           }
       }
   }
@@ -305,22 +306,40 @@ namespace stfem
     int            nrow = 0;
     VankaApplyArgs args;
     size_t         bytes = 0;
+    // fast-diagonalisation form (vanka_fd.cuh): 3D Cartesian constant-coefficient levels
+    bool                fd = false;
+    T                  *d_modes = nullptr;
+    std::vector<double> fdS, fdST; // [3][4][n1*n1]
 
-    ~Vanka() { if (d_invT) cudaFree(d_invT); }
+    ~Vanka()
+    {
+      if (d_invT) cudaFree(d_invT);
+      if (d_modes) cudaFree(d_modes);
+    }
 
     int setup(stfem_op *op_);
-    // dst = sum_c R_c^T B_c^-1 R_c src   (stmg.h:832-872; dst zeroed first)
-    int vmult(BlockVec<T> &dst, const BlockVec<T> &src)
+    int setup_fd();
+    template <int N1, int NB>
+    int launch_fd(const T *src, T *dst, T scale);
+    int apply_fd(const T *src, T *dst, T scale);
+    // dst += scale * sum_c R_c^T B_c^-1 R_c src
+    int vmult_add(BlockVec<T> &dst, const BlockVec<T> &src, T scale)
     {
       stfem_ctx *ctx = op->mesh->ctx;
-      STFEM_FORWARD(dst.zero());
+      if (fd) return apply_fd(src.d, dst.d, scale);
       const int threads = nrow < 64 ? 64 : (nrow > 256 ? 256 : ((nrow + 31) / 32) * 32);
       const long long cap = (long long)ctx->sm_count * 16;
       const int grid = (int)(args.n_cells < cap ? args.n_cells : cap);
-      k_vanka_apply<T><<<grid, threads, sizeof(T) * nrow, ctx->stream>>>(args, d_invT, src.d, dst.d);
+      k_vanka_apply<T><<<grid, threads, sizeof(T) * nrow, ctx->stream>>>(args, d_invT, src.d, dst.d, scale);
       ctx->launches++;
       STFEM_CUDA_CHECK(cudaGetLastError());
       return STFEM_OK;
+    }
+    // dst = sum_c R_c^T B_c^-1 R_c src   (stmg.h:832-872; dst zeroed first)
+    int vmult(BlockVec<T> &dst, const BlockVec<T> &src)
+    {
+      STFEM_FORWARD(dst.zero());
+      return vmult_add(dst, src, T(1));
     }
   };
 
@@ -348,6 +367,11 @@ namespace stfem
     for (int q = 0; q < n1; ++q) g.w[q] = op->shape->wq[q];
     const bool general = op->d_metric != nullptr;
     const bool dedup   = !general && op->h_coeff_cell.empty();
+    args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
+    for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }
+    // variant 2 on the level operator keeps the dense patch inverses (cross-check of the Kronecker form)
+    if (dedup && dim == 3 && n1 >= 2 && n1 <= 6 && op->variant != 2 && (nb <= 4 || nb == 6 || nb == 8))
+      return setup_fd();
     double    *d_metric = nullptr, *d_coeff = nullptr;
     if (general) STFEM_FORWARD(metric_double(op, &d_metric));
     g.metric = d_metric;
@@ -429,5 +453,265 @@ namespace stfem
     args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
     for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }
     return STFEM_OK;
+  }
+
+  // ------------------------------------------------------------------ fast-diagonalisation set-up (host, double)
+  namespace fdhost
+  {
+    // symmetric Jacobi eigenvalue iteration: A (n x n, row-major, destroyed) -> eigenvalues on the diagonal, Q columns
+    inline void jacobi_eig(std::vector<double> &A, std::vector<double> &Q, int n)
+    {
+      Q.assign((size_t)n * n, 0.0);
+      for (int i = 0; i < n; ++i) Q[i * n + i] = 1.0;
+      for (int sweep = 0; sweep < 100; ++sweep)
+        {
+          double off = 0, diag = 0;
+          for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) (i == j ? diag : off) += A[i * n + j] * A[i * n + j];
+          if (off <= 1e-32 * (diag + 1e-300)) break;
+          for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q)
+              {
+                const double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double t     = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s_ = t * c;
+                for (int k = 0; k < n; ++k)
+                  {
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s_ * akq;
+                    A[k * n + q] = s_ * akp + c * akq;
+                  }
+                for (int k = 0; k < n; ++k)
+                  {
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s_ * aqk;
+                    A[q * n + k] = s_ * apk + c * aqk;
+                  }
+                for (int k = 0; k < n; ++k)
+                  {
+                    const double qkp = Q[k * n + p], qkq = Q[k * n + q];
+                    Q[k * n + p] = c * qkp - s_ * qkq;
+                    Q[k * n + q] = s_ * qkp + c * qkq;
+                  }
+              }
+        }
+    }
+
+    // generalised symmetric problem K s = lambda M s, M SPD: S (columns) with S^T M S = I, S^T K S = diag(lambda)
+    inline void gen_eig(const std::vector<double> &M, const std::vector<double> &K, int n, std::vector<double> &S, std::vector<double> &lam)
+    {
+      std::vector<double> Lc((size_t)n * n, 0.0);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j)
+          {
+            double s_ = M[i * n + j];
+            for (int k = 0; k < j; ++k) s_ -= Lc[i * n + k] * Lc[j * n + k];
+            Lc[i * n + j] = i == j ? std::sqrt(s_) : s_ / Lc[j * n + j];
+          }
+      // Li = L^-1
+      std::vector<double> Li((size_t)n * n, 0.0);
+      for (int c = 0; c < n; ++c)
+        for (int i = 0; i < n; ++i)
+          {
+            double s_ = i == c ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) s_ -= Lc[i * n + k] * Li[k * n + c];
+            Li[i * n + c] = s_ / Lc[i * n + i];
+          }
+      // A = Li K Li^T
+      std::vector<double> T1((size_t)n * n, 0.0), A((size_t)n * n, 0.0), Q;
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          for (int k = 0; k < n; ++k) T1[i * n + j] += Li[i * n + k] * K[k * n + j];
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          for (int k = 0; k < n; ++k) A[i * n + j] += T1[i * n + k] * Li[j * n + k];
+      for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) A[i * n + j] = A[j * n + i] = 0.5 * (A[i * n + j] + A[j * n + i]);
+      jacobi_eig(A, Q, n);
+      lam.resize(n);
+      for (int i = 0; i < n; ++i) lam[i] = A[i * n + i];
+      // S = Li^T Q
+      S.assign((size_t)n * n, 0.0);
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          for (int k = 0; k < n; ++k) S[i * n + j] += Li[k * n + i] * Q[k * n + j];
+    }
+
+    // in-place inverse of a small dense matrix (Gauss-Jordan, partial pivoting); false if singular
+    inline bool small_inverse(std::vector<double> &A, int n)
+    {
+      std::vector<double> I((size_t)n * n, 0.0);
+      for (int i = 0; i < n; ++i) I[i * n + i] = 1.0;
+      for (int c = 0; c < n; ++c)
+        {
+          int p = c;
+          for (int r = c + 1; r < n; ++r)
+            if (std::fabs(A[r * n + c]) > std::fabs(A[p * n + c])) p = r;
+          if (A[p * n + c] == 0.0) return false;
+          if (p != c)
+            for (int k = 0; k < n; ++k)
+              {
+                std::swap(A[p * n + k], A[c * n + k]);
+                std::swap(I[p * n + k], I[c * n + k]);
+              }
+          const double ip = 1.0 / A[c * n + c];
+          for (int k = 0; k < n; ++k) { A[c * n + k] *= ip; I[c * n + k] *= ip; }
+          for (int r = 0; r < n; ++r)
+            if (r != c)
+              {
+                const double f = A[r * n + c];
+                if (f != 0.0)
+                  for (int k = 0; k < n; ++k) { A[r * n + k] -= f * A[c * n + k]; I[r * n + k] -= f * I[c * n + k]; }
+              }
+        }
+      A = I;
+      return true;
+    }
+  } // namespace fdhost
+
+  template <typename T>
+  int Vanka<T>::setup_fd()
+  {
+    stfem_mesh *m   = op->mesh;
+    stfem_ctx  *ctx = m->ctx;
+    const int   n1 = op->degree + 1, k = n1 - 1, nb = op->nb_rows;
+    nrow           = nb * n1 * n1 * n1;
+    fd             = true;
+    fdS.assign((size_t)3 * 4 * n1 * n1, 0.0);
+    fdST.assign((size_t)3 * 4 * n1 * n1, 0.0);
+    std::vector<double> lam((size_t)3 * 4 * n1, 0.0);
+    // reference-cell 1D matrices of the Gauss rule
+    std::vector<double> Mh((size_t)n1 * n1, 0.0), Kh((size_t)n1 * n1, 0.0);
+    for (int i = 0; i < n1; ++i)
+      for (int j = 0; j < n1; ++j)
+        {
+          long double mm = 0, kk = 0;
+          for (int q = 0; q < n1; ++q)
+            {
+              mm += (long double)op->shape->wq[q] * op->shape->S[q * n1 + i] * op->shape->S[q * n1 + j];
+              kk += (long double)op->shape->wq[q] * op->shape->D[q * n1 + i] * op->shape->D[q * n1 + j];
+            }
+          Mh[i * n1 + j] = (double)mm;
+          Kh[i * n1 + j] = (double)kk;
+        }
+    for (int d = 0; d < 3; ++d)
+      {
+        const double h = (m->upper[d] - m->lower[d]) / m->n[d];
+        for (int cls = 0; cls < 4; ++cls)
+          {
+            const bool has_lo = cls == 1 || cls == 2, has_hi = cls == 0 || cls == 1;
+            std::vector<double> M1((size_t)n1 * n1), K1((size_t)n1 * n1);
+            for (int i = 0; i < n1 * n1; ++i) { M1[i] = h * Mh[i]; K1[i] = Kh[i] / h; }
+            // neighbouring cell on the shared end node (assembled matrix restricted to the cell)
+            if (has_lo) { M1[0] += h * Mh[k * n1 + k]; K1[0] += Kh[k * n1 + k] / h; }
+            if (has_hi) { M1[k * n1 + k] += h * Mh[0]; K1[k * n1 + k] += Kh[0] / h; }
+            // constrained end nodes: row/column decoupled, positive diagonal kept
+            const bool con[2] = {!has_lo && ((m->dirichlet >> (2 * d)) & 1u), !has_hi && ((m->dirichlet >> (2 * d + 1)) & 1u)};
+            for (int e = 0; e < 2; ++e)
+              if (con[e])
+                {
+                  const int a_ = e == 0 ? 0 : k;
+                  for (int j = 0; j < n1; ++j)
+                    if (j != a_) M1[a_ * n1 + j] = M1[j * n1 + a_] = K1[a_ * n1 + j] = K1[j * n1 + a_] = 0.0;
+                }
+            std::vector<double> S1, l1;
+            fdhost::gen_eig(M1, K1, n1, S1, l1);
+            double *pS  = fdS.data() + ((size_t)d * 4 + cls) * n1 * n1;
+            double *pST = fdST.data() + ((size_t)d * 4 + cls) * n1 * n1;
+            for (int a_ = 0; a_ < n1; ++a_)
+              for (int q = 0; q < n1; ++q)
+                {
+                  pS[a_ * n1 + q]  = S1[a_ * n1 + q];
+                  pST[q * n1 + a_] = S1[a_ * n1 + q];
+                }
+            for (int q = 0; q < n1; ++q) lam[((size_t)d * 4 + cls) * n1 + q] = l1[q];
+          }
+      }
+    // per (type, mode): (Beta + lambda Alpha)^-1
+    const size_t   n_modes = (size_t)n1 * n1 * n1;
+    std::vector<T> modes((size_t)64 * n_modes * nb * nb);
+    std::vector<double> Bm((size_t)nb * nb);
+    for (int cz = 0; cz < 4; ++cz)
+      for (int cy = 0; cy < 4; ++cy)
+        for (int cx = 0; cx < 4; ++cx)
+          {
+            const int type = cx + 4 * (cy + 4 * cz);
+            for (int mz = 0; mz < n1; ++mz)
+              for (int my = 0; my < n1; ++my)
+                for (int mx = 0; mx < n1; ++mx)
+                  {
+                    const double l = lam[((size_t)0 * 4 + cx) * n1 + mx] + lam[((size_t)1 * 4 + cy) * n1 + my] + lam[((size_t)2 * 4 + cz) * n1 + mz];
+                    for (int i = 0; i < nb * nb; ++i) Bm[i] = op->Beta[i] + l * op->Alpha[i];
+                    STFEM_REQUIRE(fdhost::small_inverse(Bm, nb), "Vanka (Kronecker form): singular mode matrix");
+                    T *out = modes.data() + (((size_t)type * n1 * n1 + (mz * n1 + my)) * n1 + mx) * nb * nb;
+                    for (int i = 0; i < nb * nb; ++i) out[i] = (T)Bm[i];
+                  }
+          }
+    bytes = modes.size() * sizeof(T);
+    n_mat = 0;
+    STFEM_CUDA_CHECK(cudaMalloc(&d_modes, bytes));
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(d_modes, modes.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return STFEM_OK;
+  }
+
+  template <typename T>
+  template <int N1, int NB>
+  int Vanka<T>::launch_fd(const T *src, T *dst, T scale)
+  {
+    stfem_mesh *m   = op->mesh;
+    stfem_ctx  *ctx = m->ctx;
+    VankaFdArgs<T, N1> a;
+    for (int d = 0; d < 3; ++d)
+      for (int cls = 0; cls < 4; ++cls)
+        for (int i = 0; i < N1 * N1; ++i)
+          {
+            a.S[d][cls][i]  = (T)fdS[((size_t)d * 4 + cls) * N1 * N1 + i];
+            a.ST[d][cls][i] = (T)fdST[((size_t)d * 4 + cls) * N1 * N1 + i];
+          }
+    for (int d = 0; d < 3; ++d) { a.n[d] = m->n[d]; a.np[d] = op->np[d]; }
+    a.n_cells   = m->n_cells;
+    a.nb        = NB;
+    a.dirichlet = m->dirichlet;
+    a.neighbor_mask = 0;
+    for (int d = 0; d < 3; ++d)
+      for (int sd = 0; sd < 2; ++sd)
+        if (m->part.active && m->part.neighbor[d][sd] >= 0) a.neighbor_mask |= 1u << (2 * d + sd);
+    a.src = src; a.dst = dst; a.N = op->N; a.modes = d_modes; a.scale = scale;
+    const int tpc = NB * N1;
+    int       best = 1;
+    double    best_score = -1;
+    for (int c = 1; c * tpc <= 256; ++c)
+      {
+        const int    thr = c * tpc;
+        const double score = (double)thr / (((thr + 31) / 32) * 32) + (thr >= 96 && thr <= 160 ? 0.01 : 0.0);
+        if (score > best_score + 1e-9) { best_score = score; best = c; }
+      }
+    a.cells_per_cta = best;
+    const size_t smem = (size_t)best * NB * ExchLayout<N1>::CBS * sizeof(T);
+    auto kern = k_vanka_fd<N1, NB, T>;
+    if (smem > 48 * 1024) STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (m->n_cells + best - 1) / best;
+    kern<<<(unsigned)grid, best * tpc, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
+  template <typename T>
+  int Vanka<T>::apply_fd(const T *src, T *dst, T scale)
+  {
+    const int n1 = op->degree + 1, nb = op->nb_rows;
+#define STFEM_FD_CASE(N1_, NB_) \
+  if (n1 == N1_ && nb == NB_) return launch_fd<N1_, NB_>(src, dst, scale);
+#define STFEM_FD_DEG(N1_) \
+  STFEM_FD_CASE(N1_, 1) STFEM_FD_CASE(N1_, 2) STFEM_FD_CASE(N1_, 3) STFEM_FD_CASE(N1_, 4) STFEM_FD_CASE(N1_, 6) STFEM_FD_CASE(N1_, 8)
+    STFEM_FD_DEG(2) STFEM_FD_DEG(3) STFEM_FD_DEG(4) STFEM_FD_DEG(5) STFEM_FD_DEG(6)
+#undef STFEM_FD_DEG
+#undef STFEM_FD_CASE
+    set_error("Vanka (Kronecker form): degree %d with %d blocks not instantiated", n1 - 1, nb);
+    return STFEM_ERR_UNSUPPORTED;
   }
 } // namespace stfem
