@@ -114,6 +114,31 @@ namespace stfem
     return STFEM_OK;
   }
 
+  template <typename T>
+  int halo_scale_interfaces(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim)
+  {
+    if (!part.active) return STFEM_OK;
+    if (hb.nb_cap < nb)
+      {
+        if (hb.d_ptrs) cudaFree(hb.d_ptrs);
+        STFEM_CUDA_CHECK(cudaMalloc(&hb.d_ptrs, sizeof(void *) * STFEM_MAX_BLOCKS));
+        hb.nb_cap = STFEM_MAX_BLOCKS;
+      }
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(hb.d_ptrs, blocks, sizeof(void *) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned faces = 0;
+    for (int d = 0; d < dim; ++d)
+      for (int s = 0; s < 2; ++s)
+        if (part.neighbor[d][s] >= 0) faces |= 1u << (2 * d + s);
+    const long long total = (long long)np[0] * np[1] * (dim == 3 ? np[2] : 1) * nb;
+    const int       grid  = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
+    k_scale_interfaces<T><<<grid, 256, 0, ctx->stream>>>((T *const *)hb.d_ptrs, nb, np[0], np[1], dim == 3 ? np[2] : 1, faces);
+    ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+  template int halo_scale_interfaces<double>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
+  template int halo_scale_interfaces<float>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
+
   template int halo_compress_add<double>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
   template int halo_compress_add<float>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
 } // namespace stfem

@@ -4,6 +4,7 @@
 #include "common.hpp"
 #include "op.hpp"
 #include "st_vmult_cart.cuh"
+#include "vec.cuh"
 #include "st_vmult_generic.cuh"
 
 namespace stfem
@@ -330,23 +331,46 @@ namespace stfem
     STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (op->timing) STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     const size_t bytes = (size_t)op->N * (op->number_type == STFEM_F64 ? 8 : 4);
-    if (zero_dst)
-      for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(dst[b], 0, bytes, ctx->stream));
+    // partitioned mesh + accumulate: the increment goes to a scratch vector first, so that only the increment is
+    // summed over the ranks sharing an interface DoF
+    void *const *target = dst;
+    const bool   via_scratch = op->mesh->part.active && !zero_dst;
+    if (via_scratch)
+      {
+        while ((int)op->d_part_scratch.size() < nb_dst)
+          {
+            void *p = nullptr;
+            STFEM_CUDA_CHECK(cudaMalloc(&p, bytes + 16));
+            op->d_part_scratch.push_back(p);
+          }
+        target = op->d_part_scratch.data();
+      }
+    if (zero_dst || via_scratch)
+      for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(target[b], 0, bytes, ctx->stream));
     int rc;
     if (op->mesh->dim == 2)
-      rc = op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, dst, src, nb_src, nb_dst, alpha, beta) :
-                                          dispatch_degree<2, float>(op, dst, src, nb_src, nb_dst, alpha, beta);
+      rc = op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
+                                          dispatch_degree<2, float>(op, target, src, nb_src, nb_dst, alpha, beta);
     else
-      rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, dst, src, nb_src, nb_dst, alpha, beta) :
-                                          dispatch_degree<3, float>(op, dst, src, nb_src, nb_dst, alpha, beta);
+      rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
+                                          dispatch_degree<3, float>(op, target, src, nb_src, nb_dst, alpha, beta);
     if (rc != STFEM_OK) return rc;
     // multi-GPU: interface DoFs hold partial sums -> add over the ranks sharing them (cell_loop's compress(add))
     if (op->mesh->part.active)
       {
         if (op->number_type == STFEM_F64)
-          STFEM_FORWARD(halo_compress_add<double>(ctx, op->mesh->part, op->halo, dst, nb_dst, op->np, op->mesh->dim));
+          STFEM_FORWARD(halo_compress_add<double>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim));
         else
-          STFEM_FORWARD(halo_compress_add<float>(ctx, op->mesh->part, op->halo, dst, nb_dst, op->np, op->mesh->dim));
+          STFEM_FORWARD(halo_compress_add<float>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim));
+        if (via_scratch)
+          for (int b = 0; b < nb_dst; ++b)
+            {
+              if (op->number_type == STFEM_F64)
+                k_axpy<double><<<grid_for(ctx, op->N, 256), 256, 0, ctx->stream>>>(op->N, 1.0, (const double *)target[b], (double *)dst[b]);
+              else
+                k_axpy<float><<<grid_for(ctx, op->N, 256), 256, 0, ctx->stream>>>(op->N, 1.0f, (const float *)target[b], (float *)dst[b]);
+              ctx->launches++;
+            }
       }
     if (op->timing)
       {
@@ -459,6 +483,8 @@ int stfem_op_destroy(stfem_op_t op)
   for (void *p : {op->d_alpha, op->d_beta, op->d_alphaT, op->d_betaT, op->d_alpha_neg, op->d_beta_neg, op->d_metric, op->d_coeff})
     if (p) cudaFree(p);
   for (void *p : op->d_scratch)
+    if (p) cudaFree(p);
+  for (void *p : op->d_part_scratch)
     if (p) cudaFree(p);
   delete op;
   return STFEM_OK;

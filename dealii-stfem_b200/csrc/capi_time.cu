@@ -77,6 +77,13 @@ struct stfem_time_integrator
     return STFEM_OK;
   }
 
+  int halo_add(void *const *blocks, int nb)
+  {
+    stfem_mesh *m = matrix->mesh;
+    if (!m->part.active || fid == 0) return STFEM_OK;
+    return halo_compress_add<double>(m->ctx, m->part, matrix->halo, blocks, nb, matrix->np, m->dim);
+  }
+
   int do_extrapolate(void *const *x, const void *prev)
   {
     // time_integrators.h:180-190
@@ -159,8 +166,11 @@ int stfem_ti_solve_heat(stfem_ti_t ti, void *const *x, const void *prev_x, void 
   const size_t bytes = sizeof(double) * (size_t)ti->matrix->N;
   for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(rhs[b], 0, bytes, ctx->stream));
   const void *src[1] = {prev_x};
-  STFEM_FORWARD(op_apply(ti->rhs_matrix, rhs, src, 1, nb, ti->rhs_matrix->d_alpha, ti->rhs_matrix->d_beta, false));
+  // the source term is assembled cell-wise (partial sums on rank interfaces): sum it over the ranks before the
+  // operator part, which does its own interface sum, is added
   STFEM_FORWARD(ti->assemble_force(rhs, time, tau));
+  STFEM_FORWARD(ti->halo_add(rhs, nb));
+  STFEM_FORWARD(op_apply(ti->rhs_matrix, rhs, src, 1, nb, ti->rhs_matrix->d_alpha, ti->rhs_matrix->d_beta, false));
   STFEM_FORWARD(ti->do_extrapolate(x, prev_x));
   const int rc = ti->solver.solve(ti->matrix, ti->mg ? ti->mg->impl.get() : nullptr, x, (const void *const *)rhs, ti->max_basis, ti->max_iter,
                                   ti->abstol, ti->reduce, ti->last);
@@ -180,10 +190,11 @@ int stfem_ti_solve_wave(stfem_ti_t ti, void *const *u, void *const *v, void *con
   const size_t    bytes = sizeof(double) * (size_t)N;
   for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(rhs[b], 0, bytes, ctx->stream));
   const void *su[1] = {prev_u}, *sv[1] = {prev_v};
+  STFEM_FORWARD(ti->assemble_force(rhs, time, tau));
+  STFEM_FORWARD(ti->halo_add(rhs, nb));
   STFEM_FORWARD(op_apply(ti->rhs_matrix, rhs, su, 1, nb, ti->rhs_matrix->d_alpha, ti->rhs_matrix->d_beta, false));
   STFEM_FORWARD(ti->do_extrapolate(u, prev_u));
   STFEM_FORWARD(op_apply(ti->rhs_matrix_v, rhs, sv, 1, nb, ti->rhs_matrix_v->d_alpha, ti->rhs_matrix_v->d_beta, false));
-  STFEM_FORWARD(ti->assemble_force(rhs, time, tau));
   const int rc = ti->solver.solve(ti->matrix, ti->mg ? ti->mg->impl.get() : nullptr, u, (const void *const *)rhs, ti->max_basis, ti->max_iter,
                                   ti->abstol, ti->reduce, ti->last);
   if (iterations) *iterations = ti->last.iterations;

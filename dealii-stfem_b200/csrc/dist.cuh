@@ -86,6 +86,27 @@ namespace stfem
       }
   }
 
+  // multiply the entries on rank-interface planes by 1/2 per shared direction (so that a sum over ranks of a
+  // quantity that is complete on every rank counts it once): used before the restriction of a residual
+  template <typename T>
+  __global__ void k_scale_interfaces(T *const *blocks, int nb, int np0, int np1, int np2, unsigned shared_faces)
+  {
+    const long long per = (long long)np0 * np1 * np2, total = per * nb;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const int       blk = (int)(gid / per);
+        long long       r   = gid % per;
+        const int       ix = (int)(r % np0);
+        r /= np0;
+        const int iy = (int)(r % np1), iz = (int)(r / np1);
+        T         w  = T(1);
+        if (((shared_faces & 1u) && ix == 0) || ((shared_faces & 2u) && ix == np0 - 1)) w *= T(0.5);
+        if (((shared_faces & 4u) && iy == 0) || ((shared_faces & 8u) && iy == np1 - 1)) w *= T(0.5);
+        if (((shared_faces & 16u) && iz == 0) || ((shared_faces & 32u) && iz == np2 - 1)) w *= T(0.5);
+        if (w != T(1)) blocks[blk][gid % per] *= w;
+      }
+  }
+
   struct HaloBuffers
   {
     void  *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
@@ -106,4 +127,6 @@ namespace stfem
   // sum the partial values of the interface DoFs over the ranks sharing them (compress(add) + ghost update)
   template <typename T>
   int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim);
+  template <typename T>
+  int halo_scale_interfaces(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim);
 } // namespace stfem

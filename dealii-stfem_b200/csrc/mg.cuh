@@ -29,6 +29,26 @@ namespace stfem
       v[i] = (T)((double)((i % n) % 11) - mean);
   }
 
+  // the same start vector on a partitioned mesh: value from the GLOBAL lexicographic index, so that the copies
+  // of an interface DoF agree on all ranks
+  template <typename T>
+  __global__ void k_initial_guess_part(int np0, int np1, int np2, int off0, int off1, int off2, long long gnp0, long long gnp1, long long gnp2,
+                                       int nb, T *__restrict__ v)
+  {
+    const long long n = (long long)np0 * np1 * np2, ng = gnp0 * gnp1 * gnp2;
+    const long long full = ng / 11, rem = ng % 11;
+    const double    mean = (double)(full * 55 + rem * (rem - 1) / 2) / (double)ng;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * nb; i += (long long)gridDim.x * blockDim.x)
+      {
+        long long r  = i % n;
+        const int ix = (int)(r % np0);
+        r /= np0;
+        const int       iy = (int)(r % np1), iz = (int)(r / np1);
+        const long long g  = (long long)(ix + off0) + gnp0 * ((long long)(iy + off1) + gnp1 * (long long)(iz + off2));
+        v[i] = (T)((double)(g % 11) - mean);
+      }
+  }
+
   template <typename T>
   struct MGLevel
   {
@@ -173,6 +193,29 @@ namespace stfem
       return STFEM_OK;
     }
 
+    // coarse (+)= R fine.  Partitioned meshes: interface entries of the (complete) fine vector are weighted by
+    // 1/multiplicity first, the local restrictions are then summed over the ranks (space transfers only; the time
+    // transfers act DoF-wise).  `fine` is scaled in place.
+    int restrict_level(int l, BlockVec<T> &coarse, BlockVec<T> &fine)
+    {
+      MGLevel<T> &lv = L[l];
+      if (lv.ttype != 'h' && lv.ttype != 'p')
+        {
+          lv.tt.restrict_and_add(coarse, fine);
+          return STFEM_OK;
+        }
+      const PartitionInfo &part = lv.op->mesh->part;
+      if (part.active)
+        STFEM_FORWARD(halo_scale_interfaces<T>(ctx, part, lv.op->halo, fine.block_ptrs(), fine.nb, lv.op->np, lv.op->mesh->dim));
+      STFEM_FORWARD(lv.st.restrict_and_add(coarse, fine));
+      if (part.active)
+        {
+          stfem_op *oc = L[l - 1].op;
+          STFEM_FORWARD(halo_compress_add<T>(ctx, oc->mesh->part, oc->halo, coarse.block_ptrs(), coarse.nb, oc->np, oc->mesh->dim));
+        }
+      return STFEM_OK;
+    }
+
     // Multigrid::level_v_step; defect in L[l].defect, result in L[l].sol
     int v_step(int l)
     {
@@ -185,10 +228,7 @@ namespace stfem
         STFEM_FORWARD(residual(l, res, lv.sol, lv.defect));
         MGLevel<T> &lc = L[l - 1];
         STFEM_FORWARD(lc.defect.zero());
-        if (lv.ttype == 'h' || lv.ttype == 'p')
-          STFEM_FORWARD(lv.st.restrict_and_add(lc.defect, res));
-        else
-          lv.tt.restrict_and_add(lc.defect, res);
+        STFEM_FORWARD(restrict_level(l, lc.defect, res));
       }
       STFEM_FORWARD(v_step(l - 1));
       {
@@ -213,7 +253,23 @@ namespace stfem
         }
       // power iteration on P^-1 A (A.7)
       BlockVec<T> &v = lv.sol, &w = lv.defect, &tmp = lv.t;
-      k_initial_guess<T><<<grid_for(ctx, v.size(), 256), 256, 0, ctx->stream>>>(v.n, v.nb, v.d);
+      const PartitionInfo &part = lv.op->mesh->part;
+      sc.set_partition(part, lv.op->np, lv.op->mesh->dim);
+      if (part.active)
+        {
+          const int k = lv.op->degree, *np = lv.op->np, *nl = lv.op->mesh->n;
+          long long gnp[3];
+          int       off[3];
+          for (int d = 0; d < 3; ++d)
+            {
+              gnp[d] = d < lv.op->mesh->dim ? (long long)k * nl[d] * part.grid[d] + 1 : 1;
+              off[d] = d < lv.op->mesh->dim ? k * nl[d] * part.coords[d] : 0;
+            }
+          k_initial_guess_part<T><<<grid_for(ctx, v.size(), 256), 256, 0, ctx->stream>>>(np[0], np[1], np[2], off[0], off[1], off[2], gnp[0], gnp[1],
+                                                                                        gnp[2], v.nb, v.d);
+        }
+      else
+        k_initial_guess<T><<<grid_for(ctx, v.size(), 256), 256, 0, ctx->stream>>>(v.n, v.nb, v.d);
       ctx->launches++;
       double nrm2 = 0, lam = 1.0;
       STFEM_FORWARD(v_dot(sc, v, v, &nrm2));
@@ -436,8 +492,7 @@ namespace stfem
             STFEM_REQUIRE(l > 0, "no coarser level");
             STFEM_FORWARD(load(lv.d, src));
             STFEM_FORWARD(L[l - 1].defect.zero());
-            if (lv.ttype == 'h' || lv.ttype == 'p') STFEM_FORWARD(lv.st.restrict_and_add(L[l - 1].defect, lv.d));
-            else lv.tt.restrict_and_add(L[l - 1].defect, lv.d);
+            STFEM_FORWARD(restrict_level(l, L[l - 1].defect, lv.d));
             return store(dst, L[l - 1].defect);
           case 3: // prolongate level l-1 -> l (dst zeroed)
             STFEM_REQUIRE(l > 0, "no coarser level");

@@ -18,6 +18,7 @@ struct stfem_op
   void *d_coeff = nullptr;  // per-cell Laplace coefficient
   std::vector<double> h_coeff_cell, h_coeff_q; // host copies (Vanka set-up works in double)
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points
+  std::vector<void *> d_part_scratch; // partitioned meshes: increment of an accumulating apply before the halo sum
   stfem::HaloBuffers halo;
   bool  timing = false;
   float last_ms = 0.f;

@@ -372,6 +372,7 @@ namespace stfem
     // variant 2 on the level operator keeps the dense patch inverses (cross-check of the Kronecker form)
     if (dedup && dim == 3 && n1 >= 2 && n1 <= 6 && op->variant != 2 && (nb <= 4 || nb == 6 || nb == 8))
       return setup_fd();
+    STFEM_REQUIRE(!m->part.active, "Vanka: on partitioned meshes only the Kronecker form (3D Cartesian, constant coefficient) is implemented");
     double    *d_metric = nullptr, *d_coeff = nullptr;
     if (general) STFEM_FORWARD(metric_double(op, &d_metric));
     g.metric = d_metric;

@@ -103,8 +103,12 @@ def level_time_weights(ttype, tau, nts, mg_type_level, poly_time, wave):
 class HeatWaveProblem:
     """One (refinement, degree) run of the reference's convergence_test lambda."""
 
-    def __init__(self, ctx, params, dim, refinement, fe_degree, vertices_fn=None, mg_number_type=capi.F32, space_degree=None):
+    def __init__(self, ctx, params, dim, refinement, fe_degree, vertices_fn=None, mg_number_type=capi.F32, space_degree=None,
+                 partition=None):
+        """partition = (proc_grid, coords): this rank owns one brick of the box partition (multi-GPU runs; the context
+        must hold a communicator, dist.init_comm).  params describe the GLOBAL mesh."""
         self.ctx, self.p, self.dim = ctx, params, dim
+        self.partition = partition
         p = params
         self.ttype = p["timeType"]
         self.is_cgp = self.ttype == "CGP"
@@ -160,7 +164,14 @@ class HeatWaveProblem:
             if fine_vertices is not None:
                 step = 1 << (refinement - rf)
                 v = np.ascontiguousarray(fine_vertices[tuple([slice(None, None, step)] * dim)]).reshape(-1, dim)
-            self.meshes[rf] = capi.Mesh(ctx, n, lower=lo, upper=up, vertices=v)
+            if partition is None:
+                self.meshes[rf] = capi.Mesh(ctx, n, lower=lo, upper=up, vertices=v)
+            else:
+                from . import dist
+                assert v is None, "partitioned runs support Cartesian meshes only"
+                n_loc, _, llo, lup, mask = dist.partition_brick(n, lo, up, partition[0], partition[1])
+                self.meshes[rf] = capi.Mesh(ctx, n_loc, lower=llo, upper=lup, dirichlet_faces=mask)
+                dist.set_partition(self.meshes[rf], partition[0], partition[1])
         self.level_ops = [capi.Operator(self.meshes[level_ref[l]], level_degree[l], fetw[l][0], fetw[l][1], number_type=mg_number_type)
                           for l in range(nl)]
         self.mg = capi.Multigrid(ctx, self.level_ops, self.mg_type_level, self.ptypes, self.ttype, self.nts, self.poly_time,
