@@ -128,14 +128,18 @@ def ncu_traffic(n_cells):
     return json.load(open(p)).get("dram_bytes_per_launch")
 
 
-def solve_leg(st, ctx, refinement, n_steps=3):
+def solve_leg(st, ctx, refinement, n_steps=3, grid=None, coords=None, reduce_max=None):
     """Full STMG-preconditioned FGMRES time steps of configs[1] (3D heat, Q4 x cG(2), float multigrid) through the
     product driver: rhs assembly + solve per step, all on the device (tests/tp_01.cc:646-669)."""
-    pj = {"timeType": TTYPE, "problemType": "heat", "feDegree": TDEG, "refinement": refinement, "subdivisions": "3,3,3",
+    grid = grid or [1, 1, 1]
+    world = int(np.prod(grid))
+    pj = {"timeType": TTYPE, "problemType": "heat", "feDegree": TDEG, "refinement": refinement,
+          "subdivisions": ",".join(str(3 * g) for g in grid), "hyperRectUpperRight": ",".join(str(float(g)) for g in grid),
           "mgTimeBeforeSpace": "true", "smoother": "relaxation", "spaceTimeConvergenceTest": "true"}
     p = st.parse_parameters(pj, 3)
     t0 = time.perf_counter()
-    prob = st.HeatWaveProblem(ctx, p, 3, refinement, TDEG, space_degree=DEGREE)
+    prob = st.HeatWaveProblem(ctx, p, 3, refinement, TDEG, space_degree=DEGREE,
+                              partition=(grid, coords) if world > 1 else None)
     ctx.synchronize()
     setup_s = time.perf_counter() - t0
     its = [prob.step(evaluate_error=False)]         # warm-up step (graph capture, lazy allocations)
@@ -145,14 +149,17 @@ def solve_leg(st, ctx, refinement, n_steps=3):
     for _ in range(n_steps):
         its.append(prob.step(evaluate_error=False))
     ms = ctx.timer_stop()
+    if reduce_max is not None:
+        ms = reduce_max(ms)
     launches = ctx.launches - l0
-    dofs = prob.n * prob.nb
+    dofs = prob.n * prob.nb * world          # interface DoFs counted on every rank owning a copy (< 1 %)
     out = {"metric": "space-time DoFs/s, STMG-FGMRES solve (3D heat, Q4 x cG(2), FP64 outer / FP32 multigrid)",
            "value": dofs * n_steps / (ms * 1e-3), "unit": UNIT, "ms_per_solve": ms / n_steps, "timesteps": n_steps,
            "fgmres_iterations_per_solve": its[1:], "st_dofs": dofs, "levels": "".join(prob.mg_type_level),
            "work_per_s": dofs * sum(its[1:]) / (ms * 1e-3), "setup_s": setup_s, "gpu_launches": int(launches),
-           "config": "subdivisions 3,3,3 refinement %d, tau %.4g, relaxation smoother around cell-patch Vanka, "
-                     "variable V-cycle, reduce 1e-12" % (refinement, prob.tau)}
+           "config": "subdivisions 3,3,3 per GPU brick, refinement %d, tau %.4g, relaxation smoother around cell-patch Vanka "
+                     "(Kronecker form), variable V-cycle captured as a CUDA graph, reduce 1e-12, partition %s" %
+                     (refinement, prob.tau, "x".join(map(str, grid)))}
     prob.close()
     return out
 
@@ -211,7 +218,26 @@ def main():
     ctx = st.Context(dev)
     A, B = time_weights()
     n = args.cells
-    mesh = st.Mesh(ctx, [n, n, n])
+    grid, coords = [1, 1, 1], [0, 0, 0]
+    if world > 1:
+        # box partition 2x1x1, 2x2x1, 2x2x2: every rank owns one n^3 brick (unit cube) of the global mesh; the operator
+        # sums interface DoFs over NVLink (ncclSend/ncclRecv) inside every vmult
+        grid = st.dist.proc_grid_for(world, 3)
+        coords = st.dist.coords_of(rank, grid)
+
+        def bcast(b):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().numpy().tobytes())
+
+        st.dist.init_comm(ctx, rank, world, bcast)
+        n_loc, _, llo, lup, mask = st.dist.partition_brick([n * g for g in grid], [0.0] * 3, [float(g) for g in grid], grid, coords)
+        mesh = st.Mesh(ctx, n_loc, lower=llo, upper=lup, dirichlet_faces=mask)
+        st.dist.set_partition(mesh, grid, coords)
+    else:
+        mesh = st.Mesh(ctx, [n, n, n])
     op = st.Operator(mesh, DEGREE, A, B, number_type=st.F64, variant=args.variant)
     nb = op.nb_rows
     dofs_rank = op.n * nb
@@ -276,7 +302,8 @@ def main():
             "config": {"workload": "configs[1]: 3D heat, Q4 x cG(2), %d^3 cells per GPU, %d spatial DoFs x %d time blocks "
                                    "= %.4g space-time DoFs per GPU; one step = one fused operator vmult" % (n, op.n, nb, dofs_rank),
                        "l2": "inputs+outputs %.0f MB per step, larger than the 126 MB L2" % (2 * dofs_rank * 8 / 1e6),
-                       "parallelism": "box partition, %d independent brick(s); halo exchange not in this timing" % world,
+                       "parallelism": "box partition %s, one brick per GPU%s" % ("x".join(map(str, grid)), ", interface DoFs summed "
+                                       "over NVLink (ncclSend/ncclRecv) inside every step" if world > 1 else ""),
                        "kernel_variant": args.variant, "checksum": checksum},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n), "peak_source": peak_src, "kernel_ms": kernel_ms,
@@ -286,11 +313,19 @@ def main():
             "e2e": {"value": total_dofs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(dofs_rank * 8), "d2h_bytes_per_step": int(dofs_rank * 8)},
             "gpu_launches": int(launches), "clocks": clocks}
-    if world == 1 and not args.no_solve:
+    if not args.no_solve:
         for v in (x, y):
             v.free()
         x = y = None
-        line["solve"] = solve_leg(st, ctx, args.solve_refinement)
+
+        def reduce_max(v):
+            if world == 1:
+                return v
+            tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        line["solve"] = solve_leg(st, ctx, args.solve_refinement, grid=grid, coords=coords, reduce_max=reduce_max)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, ms, threads, ndofs = cpu_reference_run(CPU_SAMPLE_CELLS, 3, 1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

@@ -48,6 +48,11 @@ int stfem_ctx_destroy(stfem_ctx_t ctx)
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->tm0);
   cudaEventDestroy(ctx->tm1);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return STFEM_OK;

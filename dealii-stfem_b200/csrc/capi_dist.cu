@@ -44,9 +44,11 @@ namespace stfem
   }
 
   template <typename T>
-  int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim)
+  int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim,
+                        cudaStream_t stream)
   {
     if (!part.active) return STFEM_OK;
+    if (!stream) stream = ctx->stream;
     NcclApi *api = nccl_api();
     STFEM_REQUIRE(api && ctx->nccl_comm, "halo exchange: context has no NCCL communicator (stfem_ctx_comm_init)");
     // buffers sized for the largest face
@@ -70,13 +72,9 @@ namespace stfem
           }
         hb.bytes = need;
       }
-    if (hb.nb_cap < nb)
-      {
-        if (hb.d_ptrs) cudaFree(hb.d_ptrs);
-        STFEM_CUDA_CHECK(cudaMalloc(&hb.d_ptrs, sizeof(void *) * STFEM_MAX_BLOCKS));
-        hb.nb_cap = STFEM_MAX_BLOCKS;
-      }
-    STFEM_CUDA_CHECK(cudaMemcpyAsync(hb.d_ptrs, blocks, sizeof(void *) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    STFEM_REQUIRE(nb <= STFEM_MAX_BLOCKS, "halo: too many blocks");
+    BlockPtrs bp;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b) bp.p[b] = b < nb ? blocks[b] : nullptr;
     const int np2 = dim == 3 ? np[2] : 1;
     for (int d = 0; d < dim; ++d)
       {
@@ -90,7 +88,7 @@ namespace stfem
         for (int s = 0; s < 2; ++s)
           if (part.neighbor[d][s] >= 0)
             {
-              k_pack_plane<T><<<grid, threads, 0, ctx->stream>>>((const T *const *)hb.d_ptrs, nb, np[0], np[1], np2, d, s == 0 ? 0 : np[d] - 1, (T *)hb.send[s]);
+              k_pack_plane<T><<<grid, threads, 0, stream>>>(bp, nb, np[0], np[1], np2, d, s == 0 ? 0 : np[d] - 1, (T *)hb.send[s]);
               ctx->launches++;
               any = true;
             }
@@ -99,14 +97,14 @@ namespace stfem
         for (int s = 0; s < 2; ++s)
           if (part.neighbor[d][s] >= 0)
             {
-              STFEM_NCCL_CHECK(api->Send(hb.send[s], count * sizeof(T), NcclApi::kChar, part.neighbor[d][s], (nccl_comm_t)ctx->nccl_comm, ctx->stream));
-              STFEM_NCCL_CHECK(api->Recv(hb.recv[s], count * sizeof(T), NcclApi::kChar, part.neighbor[d][s], (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+              STFEM_NCCL_CHECK(api->Send(hb.send[s], count * sizeof(T), NcclApi::kChar, part.neighbor[d][s], (nccl_comm_t)ctx->nccl_comm, stream));
+              STFEM_NCCL_CHECK(api->Recv(hb.recv[s], count * sizeof(T), NcclApi::kChar, part.neighbor[d][s], (nccl_comm_t)ctx->nccl_comm, stream));
             }
         STFEM_NCCL_CHECK(api->GroupEnd());
         for (int s = 0; s < 2; ++s)
           if (part.neighbor[d][s] >= 0)
             {
-              k_unpack_add_plane<T><<<grid, threads, 0, ctx->stream>>>((T *const *)hb.d_ptrs, nb, np[0], np[1], np2, d, s == 0 ? 0 : np[d] - 1, (const T *)hb.recv[s]);
+              k_unpack_add_plane<T><<<grid, threads, 0, stream>>>(bp, nb, np[0], np[1], np2, d, s == 0 ? 0 : np[d] - 1, (const T *)hb.recv[s]);
               ctx->launches++;
             }
       }
@@ -118,20 +116,16 @@ namespace stfem
   int halo_scale_interfaces(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim)
   {
     if (!part.active) return STFEM_OK;
-    if (hb.nb_cap < nb)
-      {
-        if (hb.d_ptrs) cudaFree(hb.d_ptrs);
-        STFEM_CUDA_CHECK(cudaMalloc(&hb.d_ptrs, sizeof(void *) * STFEM_MAX_BLOCKS));
-        hb.nb_cap = STFEM_MAX_BLOCKS;
-      }
-    STFEM_CUDA_CHECK(cudaMemcpyAsync(hb.d_ptrs, blocks, sizeof(void *) * nb, cudaMemcpyHostToDevice, ctx->stream));
+    STFEM_REQUIRE(nb <= STFEM_MAX_BLOCKS, "halo: too many blocks");
+    BlockPtrs bp;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b) bp.p[b] = b < nb ? blocks[b] : nullptr;
     unsigned faces = 0;
     for (int d = 0; d < dim; ++d)
       for (int s = 0; s < 2; ++s)
         if (part.neighbor[d][s] >= 0) faces |= 1u << (2 * d + s);
     const long long total = (long long)np[0] * np[1] * (dim == 3 ? np[2] : 1) * nb;
     const int       grid  = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
-    k_scale_interfaces<T><<<grid, 256, 0, ctx->stream>>>((T *const *)hb.d_ptrs, nb, np[0], np[1], dim == 3 ? np[2] : 1, faces);
+    k_scale_interfaces<T><<<grid, 256, 0, ctx->stream>>>(bp, nb, np[0], np[1], dim == 3 ? np[2] : 1, faces);
     ctx->launches++;
     STFEM_CUDA_CHECK(cudaGetLastError());
     return STFEM_OK;
@@ -139,8 +133,8 @@ namespace stfem
   template int halo_scale_interfaces<double>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
   template int halo_scale_interfaces<float>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
 
-  template int halo_compress_add<double>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
-  template int halo_compress_add<float>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int);
+  template int halo_compress_add<double>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int, cudaStream_t);
+  template int halo_compress_add<float>(stfem_ctx *, const Partition &, HaloBuffers &, void *const *, int, const int[3], int, cudaStream_t);
 } // namespace stfem
 
 using namespace stfem;

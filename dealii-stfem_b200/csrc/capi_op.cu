@@ -1,5 +1,7 @@
 // C ABI: space-time operator (SystemMatrix + MatrixFreeOperator of the reference,
 // include/operators.h:516-663 and :967-1191).
+#include <cstdlib>
+
 #include "basis_host.hpp"
 #include "common.hpp"
 #include "op.hpp"
@@ -241,7 +243,15 @@ namespace stfem
           a.Mx[i * N1 + j] = (T)(mm * vol);
           a.Kx[i * N1 + j] = (T)(kk * vol / (h[0] * h[0]));
         }
-    a.n_cells = m->n_cells;
+    a.n_cells = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        a.box_lo[d] = op->box_lo ? op->box_lo[d] : 0;
+        a.box_n[d]  = op->box_n ? op->box_n[d] : m->n[d];
+        a.n_cells *= a.box_n[d];
+      }
+    if (a.n_cells <= 0) return STFEM_OK;
+    cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
     a.nb_src  = nb_src;
     a.nb_dst  = nb_dst;
     for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
@@ -279,10 +289,25 @@ namespace stfem
     auto         kern    = st_vmult_cart_kernel<N1, T, MAXT, MINB>;
     if (smem > 48 * 1024)
       STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = (m->n_cells + best - 1) / best;
-    kern<<<(unsigned)grid, threads, smem, m->ctx->stream>>>(a);
+    const long long grid = (a.n_cells + best - 1) / best;
+    kern<<<(unsigned)grid, threads, smem, stream>>>(a);
     m->ctx->launches++;
     STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
+  // true if op_apply runs the Cartesian kernel (which supports cell sub-boxes / streams)
+  static bool uses_cart(const stfem_op *op)
+  {
+    return op->mesh->dim == 3 && op->variant != 1 && op->mesh->cartesian && !op->d_metric && op->degree <= 5;
+  }
+
+  int ctx_ensure_aux(stfem_ctx *ctx)
+  {
+    if (ctx->aux[0]) return STFEM_OK;
+    for (int i = 0; i < 2; ++i) STFEM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+    STFEM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    STFEM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     return STFEM_OK;
   }
 
@@ -347,21 +372,73 @@ namespace stfem
       }
     if (zero_dst || via_scratch)
       for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(target[b], 0, bytes, ctx->stream));
-    int rc;
-    if (op->mesh->dim == 2)
-      rc = op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
-                                          dispatch_degree<2, float>(op, target, src, nb_src, nb_dst, alpha, beta);
-    else
-      rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
-                                          dispatch_degree<3, float>(op, target, src, nb_src, nb_dst, alpha, beta);
-    if (rc != STFEM_OK) return rc;
-    // multi-GPU: interface DoFs hold partial sums -> add over the ranks sharing them (cell_loop's compress(add))
-    if (op->mesh->part.active)
+    auto dispatch = [&]() -> int {
+      if (op->mesh->dim == 2)
+        return op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
+                                              dispatch_degree<2, float>(op, target, src, nb_src, nb_dst, alpha, beta);
+      return op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
+                                            dispatch_degree<3, float>(op, target, src, nb_src, nb_dst, alpha, beta);
+    };
+    auto halo = [&](cudaStream_t stream) -> int {
+      if (op->number_type == STFEM_F64)
+        return halo_compress_add<double>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim, stream);
+      return halo_compress_add<float>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim, stream);
+    };
+    const PartitionInfo &part = op->mesh->part;
+    // multi-GPU: interface DoFs hold partial sums -> add over the ranks sharing them (cell_loop's compress(add)).
+    // Large Cartesian bricks: the shell of cells touching a rank interface runs first, the exchange then overlaps
+    // the interior cells on a second stream.
+    static const bool no_overlap = std::getenv("STFEM_NO_OVERLAP") != nullptr;
+    const int *mn = op->mesh->n;
+    if (part.active && uses_cart(op) && !no_overlap && mn[0] >= 8 && mn[1] >= 8 && mn[2] >= 8)
       {
-        if (op->number_type == STFEM_F64)
-          STFEM_FORWARD(halo_compress_add<double>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim));
-        else
-          STFEM_FORWARD(halo_compress_add<float>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim));
+        STFEM_FORWARD(ctx_ensure_aux(ctx));
+        int ilo[3], ihi[3];
+        for (int d = 0; d < 3; ++d)
+          {
+            ilo[d] = part.neighbor[d][0] >= 0 ? 1 : 0;
+            ihi[d] = part.neighbor[d][1] >= 0 ? mn[d] - 1 : mn[d];
+          }
+        // shell: z slabs (full x, y), y slabs (z interior), x slabs (y, z interior)
+        int rlo[3] = {0, 0, 0}, rhi[3] = {mn[0], mn[1], mn[2]};
+        for (int d = 2; d >= 0; --d)
+          {
+            for (int sd = 0; sd < 2; ++sd)
+              {
+                if (part.neighbor[d][sd] < 0) continue;
+                int lo[3] = {rlo[0], rlo[1], rlo[2]}, nn[3] = {rhi[0] - rlo[0], rhi[1] - rlo[1], rhi[2] - rlo[2]};
+                lo[d]      = sd == 0 ? 0 : mn[d] - 1;
+                nn[d]      = 1;
+                op->box_lo = lo;
+                op->box_n  = nn;
+                const int rc = dispatch();
+                op->box_lo = op->box_n = nullptr;
+                if (rc != STFEM_OK) return rc;
+              }
+            rlo[d] = ilo[d];
+            rhi[d] = ihi[d];
+          }
+        STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+        STFEM_FORWARD(halo(ctx->aux[0]));
+        STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ctx->aux[0]));
+        {
+          int nn[3] = {ihi[0] - ilo[0], ihi[1] - ilo[1], ihi[2] - ilo[2]};
+          op->box_lo = ilo;
+          op->box_n  = nn;
+          const int rc = dispatch();
+          op->box_lo = op->box_n = nullptr;
+          if (rc != STFEM_OK) return rc;
+        }
+        STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      }
+    else
+      {
+        STFEM_FORWARD(dispatch());
+        if (part.active) STFEM_FORWARD(halo(ctx->stream));
+      }
+    if (part.active)
+      {
         if (via_scratch)
           for (int b = 0; b < nb_dst; ++b)
             {
@@ -524,13 +601,14 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
   STFEM_REQUIRE(op->nb_rows == op->nb_cols, "stfem_op_vmult_host: operator not square");
   stfem_ctx   *ctx   = op->mesh->ctx;
   const int    nb    = op->nb_rows;
-  const size_t bytes = (size_t)op->N * (op->number_type == STFEM_F64 ? 8 : 4);
+  const size_t esz   = op->number_type == STFEM_F64 ? 8 : 4;
+  const size_t bytes = (size_t)op->N * esz;
   STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
   if (op->d_scratch.size() < (size_t)2 * nb)
     {
       for (void *p : op->d_scratch) cudaFree(p);
       op->d_scratch.assign(2 * nb, nullptr);
-      for (auto &p : op->d_scratch) STFEM_CUDA_CHECK(cudaMalloc(&p, bytes));
+      for (auto &p : op->d_scratch) STFEM_CUDA_CHECK(cudaMalloc(&p, bytes + 16));
     }
   std::vector<void *>       d(nb);
   std::vector<const void *> s(nb);
@@ -538,11 +616,64 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
     {
       d[b] = op->d_scratch[b];
       s[b] = op->d_scratch[nb + b];
-      STFEM_CUDA_CHECK(cudaMemcpyAsync(op->d_scratch[nb + b], src_host[b], bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-  STFEM_FORWARD(stfem_op_vmult(op, d.data(), s.data(), transpose));
-  for (int b = 0; b < nb; ++b)
-    STFEM_CUDA_CHECK(cudaMemcpyAsync(dst_host[b], d[b], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  const void *alpha = transpose ? op->d_alphaT : op->d_alpha, *beta = transpose ? op->d_betaT : op->d_beta;
+  const int  *mn = op->mesh->n;
+  static const bool no_pipeline = std::getenv("STFEM_NO_PIPELINE") != nullptr;
+  if (!uses_cart(op) || op->mesh->part.active || mn[2] < 4 || no_pipeline)
+    {
+      for (int b = 0; b < nb; ++b)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(op->d_scratch[nb + b], src_host[b], bytes, cudaMemcpyHostToDevice, ctx->stream));
+      STFEM_FORWARD(stfem_op_vmult(op, d.data(), s.data(), transpose));
+      for (int b = 0; b < nb; ++b)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(dst_host[b], d[b], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      return STFEM_OK;
+    }
+  // Pipelined over z slabs of cells: upload of slab s+1 (copy engine 1), cell kernel of slab s, download of the
+  // node planes slab s has completed (copy engine 2) run concurrently; PCIe is used in both directions at once.
+  STFEM_FORWARD(ctx_ensure_aux(ctx));
+  const int    k       = op->degree;
+  const int    n_slabs = mn[2] < 16 ? mn[2] : 16;
+  const size_t plane   = (size_t)op->np[0] * op->np[1] * esz; // bytes of one z plane of nodes
+  while (ctx->ev_pool.size() < (size_t)2 * n_slabs + 1)
+    {
+      cudaEvent_t e;
+      STFEM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->ev_pool.push_back(e);
+    }
+  cudaStream_t up = ctx->aux[0], down = ctx->aux[1];
+  // all three streams start after whatever is queued on the context stream
+  STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  STFEM_CUDA_CHECK(cudaStreamWaitEvent(up, ctx->ev_fork, 0));
+  STFEM_CUDA_CHECK(cudaStreamWaitEvent(down, ctx->ev_fork, 0));
+  for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(d[b], 0, bytes, ctx->stream));
+  for (int sl = 0; sl < n_slabs; ++sl)
+    {
+      const int z0 = (int)((long long)mn[2] * sl / n_slabs), z1 = (int)((long long)mn[2] * (sl + 1) / n_slabs);
+      // upload node planes (k z0, k z1] (+ plane 0 for the first slab)
+      const size_t p0 = sl == 0 ? 0 : (size_t)k * z0 + 1, p1 = (size_t)k * z1 + 1;
+      for (int b = 0; b < nb; ++b)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync((char *)op->d_scratch[nb + b] + p0 * plane, (const char *)src_host[b] + p0 * plane, (p1 - p0) * plane,
+                                         cudaMemcpyHostToDevice, up));
+      STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_pool[2 * sl], up));
+      STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_pool[2 * sl], 0));
+      int lo[3] = {0, 0, z0}, nn[3] = {mn[0], mn[1], z1 - z0};
+      op->box_lo = lo;
+      op->box_n  = nn;
+      int rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, d.data(), s.data(), nb, nb, alpha, beta) :
+                                              dispatch_degree<3, float>(op, d.data(), s.data(), nb, nb, alpha, beta);
+      op->box_lo = op->box_n = nullptr;
+      if (rc != STFEM_OK) return rc;
+      STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_pool[2 * sl + 1], ctx->stream));
+      STFEM_CUDA_CHECK(cudaStreamWaitEvent(down, ctx->ev_pool[2 * sl + 1], 0));
+      // node planes [k z0, k z1) are complete now (the last slab also completes the top plane)
+      const size_t q0 = (size_t)k * z0, q1 = sl == n_slabs - 1 ? (size_t)k * z1 + 1 : (size_t)k * z1;
+      for (int b = 0; b < nb; ++b)
+        STFEM_CUDA_CHECK(cudaMemcpyAsync((char *)dst_host[b] + q0 * plane, (const char *)d[b] + q0 * plane, (q1 - q0) * plane, cudaMemcpyDeviceToHost, down));
+    }
+  STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_join, down));
+  STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   return STFEM_OK;
 }

@@ -57,6 +57,11 @@ struct stfem_ctx
   int          sm_count = 0;
   cudaEvent_t  ev0 = nullptr, ev1 = nullptr; // per-operator kernel timing
   cudaEvent_t  tm0 = nullptr, tm1 = nullptr; // stfem_ctx_timer_*
+  // auxiliary streams + events (created on first use): halo exchange overlapped with interior cells, and the
+  // upload / compute / download pipeline of the host-buffer entry point
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
   void        *nccl_comm = nullptr;          // ncclComm_t when the context is part of a multi-GPU run
   int          rank = 0, n_ranks = 1;
 };

@@ -50,9 +50,13 @@ namespace stfem
 
   using Partition = PartitionInfo;
 
+  // block pointers by value (kernel parameter): no host->device pointer upload, so the exchange can be captured
+  // in a CUDA graph
+  struct BlockPtrs { void *p[STFEM_MAX_BLOCKS]; };
+
   // pack / unpack-add one index plane of a [np2][np1][np0] array (all blocks), plane normal to `axis`
   template <typename T>
-  __global__ void k_pack_plane(const T *const *blocks, int nb, int np0, int np1, int np2, int axis, int index, T *__restrict__ out)
+  __global__ void k_pack_plane(BlockPtrs blocks, int nb, int np0, int np1, int np2, int axis, int index, T *__restrict__ out)
   {
     const int       a = axis == 0 ? np1 : np0, b = axis == 2 ? np1 : np2; // plane extents (fast, slow)
     const long long per = (long long)a * b, total = per * nb;
@@ -65,11 +69,11 @@ namespace stfem
         if (axis == 0) off = (long long)index + (long long)np0 * (u + (long long)np1 * v);
         else if (axis == 1) off = (long long)u + (long long)np0 * (index + (long long)np1 * v);
         else off = (long long)u + (long long)np0 * (v + (long long)np1 * index);
-        out[gid] = blocks[blk][off];
+        out[gid] = ((const T *)blocks.p[blk])[off];
       }
   }
   template <typename T>
-  __global__ void k_unpack_add_plane(T *const *blocks, int nb, int np0, int np1, int np2, int axis, int index, const T *__restrict__ in)
+  __global__ void k_unpack_add_plane(BlockPtrs blocks, int nb, int np0, int np1, int np2, int axis, int index, const T *__restrict__ in)
   {
     const int       a = axis == 0 ? np1 : np0, b = axis == 2 ? np1 : np2;
     const long long per = (long long)a * b, total = per * nb;
@@ -82,14 +86,14 @@ namespace stfem
         if (axis == 0) off = (long long)index + (long long)np0 * (u + (long long)np1 * v);
         else if (axis == 1) off = (long long)u + (long long)np0 * (index + (long long)np1 * v);
         else off = (long long)u + (long long)np0 * (v + (long long)np1 * index);
-        blocks[blk][off] += in[gid];
+        ((T *)blocks.p[blk])[off] += in[gid];
       }
   }
 
   // multiply the entries on rank-interface planes by 1/2 per shared direction (so that a sum over ranks of a
   // quantity that is complete on every rank counts it once): used before the restriction of a residual
   template <typename T>
-  __global__ void k_scale_interfaces(T *const *blocks, int nb, int np0, int np1, int np2, unsigned shared_faces)
+  __global__ void k_scale_interfaces(BlockPtrs blocks, int nb, int np0, int np1, int np2, unsigned shared_faces)
   {
     const long long per = (long long)np0 * np1 * np2, total = per * nb;
     for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
@@ -103,7 +107,7 @@ namespace stfem
         if (((shared_faces & 1u) && ix == 0) || ((shared_faces & 2u) && ix == np0 - 1)) w *= T(0.5);
         if (((shared_faces & 4u) && iy == 0) || ((shared_faces & 8u) && iy == np1 - 1)) w *= T(0.5);
         if (((shared_faces & 16u) && iz == 0) || ((shared_faces & 32u) && iz == np2 - 1)) w *= T(0.5);
-        if (w != T(1)) blocks[blk][gid % per] *= w;
+        if (w != T(1)) ((T *)blocks.p[blk])[gid % per] *= w;
       }
   }
 
@@ -111,8 +115,6 @@ namespace stfem
   {
     void  *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
     size_t bytes = 0;
-    void **d_ptrs = nullptr; // device copy of the block pointer array
-    int    nb_cap = 0;
     ~HaloBuffers()
     {
       for (int s = 0; s < 2; ++s)
@@ -120,13 +122,13 @@ namespace stfem
           if (send[s]) cudaFree(send[s]);
           if (recv[s]) cudaFree(recv[s]);
         }
-      if (d_ptrs) cudaFree(d_ptrs);
     }
   };
 
   // sum the partial values of the interface DoFs over the ranks sharing them (compress(add) + ghost update)
   template <typename T>
-  int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim);
+  int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim,
+                        cudaStream_t stream = nullptr);
   template <typename T>
   int halo_scale_interfaces(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim);
 } // namespace stfem

@@ -432,7 +432,8 @@ namespace stfem
       const bool part     = L[top].op->mesh->part.active;
       bool       timing   = false;
       for (auto &lv : L) timing = timing || lv.op->timing;
-      if (no_graph || part || timing || n_vcycles++ == 0) return v_step(top);
+      static const bool no_part_graph = std::getenv("STFEM_NO_PART_GRAPH") != nullptr;
+      if (no_graph || (part && no_part_graph) || timing || n_vcycles++ == 0) return v_step(top);
       if (!graph_exec)
         {
           cudaGraph_t     graph = nullptr;

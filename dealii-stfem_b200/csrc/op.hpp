@@ -20,12 +20,16 @@ struct stfem_op
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points
   std::vector<void *> d_part_scratch; // partitioned meshes: increment of an accumulating apply before the halo sum
   stfem::HaloBuffers halo;
+  // launch context of the next kernel dispatch (set by op_apply's callers inside this file): cell sub-box, stream
+  const int   *box_lo = nullptr, *box_n = nullptr;
+  cudaStream_t launch_stream = nullptr;
   bool  timing = false;
   float last_ms = 0.f;
 };
 
 namespace stfem
 {
+  int ctx_ensure_aux(stfem_ctx *ctx);
   // dst (+)= A src with explicit time matrices (device pointers in the operator's number type)
   int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                const void *beta, bool zero_dst);

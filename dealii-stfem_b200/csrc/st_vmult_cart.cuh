@@ -47,7 +47,8 @@ namespace stfem
     T         Ky[N1 * N1], Kz[N1 * N1];    // Kh / hy^2, Kh / hz^2
     T         Mx[N1 * N1], Kx[N1 * N1];    // vol * Mh, vol * Kh / hx^2
     int       n[3], np[3];
-    long long n_cells;
+    int       box_lo[3], box_n[3]; // sub-box of cells this launch processes (whole mesh: lo = 0, n = mesh)
+    long long n_cells;             // cells in the sub-box
     int       nb_src, nb_dst, cells_per_cta;
     unsigned  dirichlet;
     const T  *src[STFEM_MAX_BLOCKS];
@@ -82,10 +83,10 @@ namespace stfem
     if (active)
       {
         long long c = cell;
-        cx          = (int)(c % a.n[0]);
-        c /= a.n[0];
-        cy = (int)(c % a.n[1]);
-        cz = (int)(c / a.n[1]);
+        cx          = a.box_lo[0] + (int)(c % a.box_n[0]);
+        c /= a.box_n[0];
+        cy = a.box_lo[1] + (int)(c % a.box_n[1]);
+        cz = a.box_lo[2] + (int)(c / a.box_n[1]);
       }
     const unsigned dm  = a.dirichlet;
     const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;
@@ -105,7 +106,7 @@ namespace stfem
       for (int jy = 0; jy < N1; ++jy) v[k][jy] = w[k][jy] = T(0);
     if (active && !plane_constrained)
       {
-        const T coef = a.coeff_cell ? a.coeff_cell[cell] : T(1);
+        const T coef = a.coeff_cell ? a.coeff_cell[(long long)cx + (long long)a.n[0] * (cy + (long long)a.n[1] * cz)] : T(1);
         for (int s = 0; s < a.nb_src; ++s)
           {
             const T  be = a.beta[j * a.nb_src + s];

@@ -256,3 +256,23 @@ def test_cartesian_kernel_slice_and_cell_coefficient(ctx):
     op.vmult_slice_add(d_dst, d_src)
     assert _rel(d_dst.download(), ref_dst) < 1e-12
     d_src.free(); d_dst.free(); op.close(); gm.close()
+
+
+@pytest.mark.parametrize("cells,k", [([6, 5, 10], 3), ([4, 4, 37], 2), ([3, 3, 3], 4)])
+def test_host_buffer_entry_point_pipeline(ctx, cells, k):
+    """stfem_op_vmult_host (the e2e path of bench.py): upload / cell kernel / download pipelined over z slabs must give
+    the device-resident result, incl. slab counts that do not divide the mesh and the unpipelined small-mesh path."""
+    import dealii_stfem_b200 as st
+    mesh = S.Mesh(3, cells, 0)
+    space = S.Space(mesh, k)
+    A, B, _, _ = _time_matrices("CGP", 2, 1)
+    sysm = S.SystemMatrix(S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0), A, B)
+    src = _rand_block(2, space.n_dofs)
+    gm = st.Mesh(ctx, mesh.n)
+    op = st.Operator(gm, k, A, B)
+    out = np.full_like(src, np.nan)
+    for transpose, ref in ((False, sysm.vmult(src)), (True, sysm.Tvmult(src))):
+        op.vmult_host(out, src, transpose=transpose)
+        assert _rel(out, ref) < 1e-12
+        assert np.all(out[:, space.constrained] == 0)
+    op.close(); gm.close()
