@@ -213,7 +213,9 @@ namespace stfem
 
 
   // Cartesian 3D fast path (st_vmult_cart.cuh)
-  template <int N1, typename T, int MAXT, int MINB>
+  // PIPE = 0: one batch of cells per CTA; PIPE = NBS > 0: persistent software-pipelined kernel for NBS source blocks
+  // (register budget 65536 / (MAXT * MINB), rounded down to a multiple of 8)
+  template <int N1, typename T, int MAXT, int MINB, int PIPE = 0>
   static int launch_cart(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                          const void *beta)
   {
@@ -286,11 +288,26 @@ namespace stfem
     a.cells_per_cta      = best;
     const size_t smem    = best * per_cell;
     const int    threads = best * tpc;
-    auto         kern    = st_vmult_cart_kernel<N1, T, MAXT, MINB>;
-    if (smem > 48 * 1024)
-      STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = (a.n_cells + best - 1) / best;
-    kern<<<(unsigned)grid, threads, smem, stream>>>(a);
+    long long grid = (a.n_cells + best - 1) / best;
+    if constexpr (PIPE > 0)
+      {
+        STFEM_REQUIRE(nb_src == PIPE, "st_vmult: pipelined kernel instantiated for %d source blocks, got %d", PIPE, nb_src);
+        constexpr int budget = 65536 / (((MAXT + 31) / 32) * 32 * MINB);
+        constexpr int maxreg = budget > 255 ? 255 : (budget / 8) * 8;
+        auto kern = st_vmult_cart_pipe_kernel<N1, T, PIPE, maxreg, (sizeof(T) == 4)>;
+        if (smem > 48 * 1024)
+          STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long resident = (long long)m->ctx->sm_count * MINB;
+        if (grid > resident && op->variant != 24 && op->variant != 25) grid = resident; // 24/25: one batch per CTA (no prefetch)
+        kern<<<(unsigned)grid, threads, smem, stream>>>(a);
+      }
+    else
+      {
+        auto kern = st_vmult_cart_kernel<N1, T, MAXT, MINB>;
+        if (smem > 48 * 1024)
+          STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, threads, smem, stream>>>(a);
+      }
     m->ctx->launches++;
     STFEM_CUDA_CHECK(cudaGetLastError());
     return STFEM_OK;
@@ -328,10 +345,19 @@ namespace stfem
               if (op->variant == 12) return launch_cart<4, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<4, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 4:
+              if (op->variant == 24 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 25 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 2, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 20 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 21 && nb_src == 2 && nbd * 5 <= 160) return launch_cart<5, T, 160, 2, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 22 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 2, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 23 && nb_src == 2 && nbd * 5 <= 96) return launch_cart<5, T, 96, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 11 || nbd * 5 > 128) return launch_cart<5, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 12) return launch_cart<5, T, 160, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 13) return launch_cart<5, T, 192, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 14) return launch_cart<5, T, 96, 4>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              // FP32 (multigrid levels): persistent kernel with the next batch's gather prefetched before the x sweep
+              if (sizeof(T) == 4 && op->variant == 0 && nb_src == 2 && nbd * 5 <= 128)
+                return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<5, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 5: return launch_cart<6, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
             default: break;

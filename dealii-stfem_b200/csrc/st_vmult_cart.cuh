@@ -246,4 +246,257 @@ namespace stfem
           }
       }
   }
+  // ------------------------------------------------------------------------------------------------------------
+  // Software-pipelined persistent variant (NBS = number of source blocks, compile time, <= 2): every CTA loops over
+  // batches of cells; the gather of batch n+1 is issued (raw values into the registers the y/z sweeps have just
+  // released) BEFORE the x sweep and the scatter of batch n, so the global-load latency hides behind shared-memory
+  // and RED work instead of stalling the FP64 pipe.
+  template <typename T>
+  struct CartCell
+  {
+    long long base, cell_lin;
+    bool      active, plane_con, any_yz, ylo, yhi, zlo, zhi;
+  };
+
+  template <int N1, typename T>
+  __device__ __forceinline__ void cart_decode(const CartArgs<T, N1> &a, long long batch, int slot, int i, CartCell<T> &c)
+  {
+    constexpr int   K    = N1 - 1;
+    const long long cell = batch * a.cells_per_cta + slot;
+    c.active             = cell < a.n_cells;
+    int cx = 0, cy = 0, cz = 0;
+    if (c.active)
+      {
+        long long r = cell;
+        cx          = a.box_lo[0] + (int)(r % a.box_n[0]);
+        r /= a.box_n[0];
+        cy = a.box_lo[1] + (int)(r % a.box_n[1]);
+        cz = a.box_lo[2] + (int)(r / a.box_n[1]);
+      }
+    const unsigned dm  = a.dirichlet;
+    const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;
+    c.ylo = (dm & 4u) && cy == 0;
+    c.yhi = (dm & 8u) && cy == a.n[1] - 1;
+    c.zlo = (dm & 16u) && cz == 0;
+    c.zhi = (dm & 32u) && cz == a.n[2] - 1;
+    c.plane_con = (xlo && i == 0) || (xhi && i == K);
+    c.any_yz    = c.ylo || c.yhi || c.zlo || c.zhi;
+    c.base      = (long long)(cx * K + i) + (long long)a.np[0] * ((long long)(cy * K) + (long long)a.np[1] * (cz * K));
+    c.cell_lin  = (long long)cx + (long long)a.n[0] * (cy + (long long)a.n[1] * cz);
+  }
+
+  // raw values of source block 0 into v, of source block 1 (NBS == 2) into w
+  template <int N1, typename T, int NBS>
+  __device__ __forceinline__ void cart_gather(const CartArgs<T, N1> &a, const CartCell<T> &c, T (&v)[N1][N1], T (&w)[N1][N1])
+  {
+    constexpr int K  = N1 - 1;
+    const int     sy = a.np[0], sz = a.np[0] * a.np[1];
+    if (c.active && !c.plane_con)
+      {
+#pragma unroll
+        for (int s = 0; s < NBS; ++s)
+          {
+            const T *p = a.src[s] + c.base;
+            if (!c.any_yz)
+              {
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy) (s == 0 ? v : w)[k][jy] = p[jy * sy + k * sz];
+              }
+            else
+              {
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy)
+                    {
+                      const bool cn = (c.ylo && jy == 0) || (c.yhi && jy == K) || (c.zlo && k == 0) || (c.zhi && k == K);
+                      (s == 0 ? v : w)[k][jy] = cn ? T(0) : p[jy * sy + k * sz];
+                    }
+              }
+          }
+      }
+    else
+      {
+#pragma unroll
+        for (int k = 0; k < N1; ++k)
+#pragma unroll
+          for (int jy = 0; jy < N1; ++jy) v[k][jy] = w[k][jy] = T(0);
+      }
+  }
+
+  // EARLY: prefetch before the x sweep (longest overlap, needs the registers for it: fine in FP32), else after it
+  template <int N1, typename T, int NBS, int MAXREG, bool EARLY>
+  __global__ void __maxnreg__(MAXREG) st_vmult_cart_pipe_kernel(const __grid_constant__ CartArgs<T, N1> a)
+  {
+    using L           = ExchLayout<N1>;
+    constexpr int K   = N1 - 1;
+    constexpr int LS  = L::LS;
+    constexpr int CBS = L::CBS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *bufP = reinterpret_cast<T *>(smem_raw);
+    T *bufQ = bufP + (size_t)a.cells_per_cta * a.nb_dst * CBS;
+
+    const int tid  = threadIdx.x;
+    const int tpc  = a.nb_dst * N1;
+    const int slot = tid / tpc;
+    const int rem  = tid - slot * tpc;
+    const int j    = rem / N1;
+    const int i    = rem - j * N1;
+    const int cb   = tid / N1;
+    const int sy   = a.np[0];
+    const int sz   = a.np[0] * a.np[1];
+
+    T be[NBS], al0[NBS];
+#pragma unroll
+    for (int s = 0; s < NBS; ++s)
+      {
+        be[s]  = a.beta[j * NBS + s];
+        al0[s] = a.alpha[j * NBS + s];
+      }
+    const long long n_batches = (a.n_cells + a.cells_per_cta - 1) / a.cells_per_cta;
+    long long       batch     = blockIdx.x;
+    static_assert(NBS == 1 || NBS == 2, "pipelined kernel: one or two source blocks");
+    CartCell<T>     c;
+    T               v[N1][N1], w[N1][N1]; // [z][y]; hold the raw gathered values between iterations
+    cart_decode<N1, T>(a, batch, slot, i, c);
+    cart_gather<N1, T, NBS>(a, c, v, w);
+
+    for (; batch < n_batches; batch += gridDim.x)
+      {
+        // ---------------- temporal contraction of the gathered values
+        {
+          const T coef = (a.coeff_cell && c.active) ? a.coeff_cell[c.cell_lin] : T(1);
+#pragma unroll
+          for (int k = 0; k < N1; ++k)
+#pragma unroll
+            for (int jy = 0; jy < N1; ++jy)
+              {
+                const T u0 = v[k][jy], u1 = NBS == 2 ? w[k][jy] : T(0);
+                T       vv = be[0] * u0, ww = (al0[0] * coef) * u0;
+                if (NBS == 2)
+                  {
+                    vv += be[1] * u1;
+                    ww += (al0[1] * coef) * u1;
+                  }
+                v[k][jy] = vv;
+                w[k][jy] = ww;
+              }
+        }
+        // ---------------- y sweep
+#pragma unroll
+        for (int k = 0; k < N1; ++k)
+          {
+            T s_[N1], t_[N1];
+#pragma unroll
+            for (int q = 0; q < N1; ++q)
+              {
+                T ss = T(0), tt = T(0);
+#pragma unroll
+                for (int jy = 0; jy < N1; ++jy)
+                  {
+                    ss += a.M[q * N1 + jy] * v[k][jy];
+                    ss += a.Ky[q * N1 + jy] * w[k][jy];
+                    tt += a.M[q * N1 + jy] * w[k][jy];
+                  }
+                s_[q] = ss;
+                t_[q] = tt;
+              }
+#pragma unroll
+            for (int q = 0; q < N1; ++q)
+              {
+                v[k][q] = s_[q];
+                w[k][q] = t_[q];
+              }
+          }
+        // ---------------- z sweep + publish
+        {
+          T *pP = bufP + cb * CBS + i;
+          T *pQ = bufQ + cb * CBS + i;
+#pragma unroll
+          for (int jy = 0; jy < N1; ++jy)
+#pragma unroll
+            for (int q = 0; q < N1; ++q)
+              {
+                T pp = T(0), qq = T(0);
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+                  {
+                    pp += a.M[q * N1 + k] * v[k][jy];
+                    pp += a.Kz[q * N1 + k] * w[k][jy];
+                    qq += a.M[q * N1 + k] * w[k][jy];
+                  }
+                pP[(q * N1 + jy) * LS] = pp;
+                pQ[(q * N1 + jy) * LS] = qq;
+              }
+        }
+        __syncthreads();
+        // ---------------- prefetch: gather of the next batch into the registers the sweeps released
+        const CartCell<T> cur = c;
+        if (EARLY && batch + gridDim.x < n_batches)
+          {
+            cart_decode<N1, T>(a, batch + gridDim.x, slot, i, c);
+            cart_gather<N1, T, NBS>(a, c, v, w);
+          }
+        // ---------------- x sweep
+#pragma unroll
+        for (int m = 0; m < N1; ++m)
+          {
+            const int line = L::blocked ? N1 * i + m : i + N1 * m;
+            T        *pP   = bufP + cb * CBS + line * LS;
+            const T  *pQ   = bufQ + cb * CBS + line * LS;
+            T         P[N1], Q[N1];
+#pragma unroll
+            for (int x = 0; x < N1; ++x)
+              {
+                P[x] = pP[x];
+                Q[x] = pQ[x];
+              }
+#pragma unroll
+            for (int q = 0; q < N1; ++q)
+              {
+                T o = T(0);
+#pragma unroll
+                for (int x = 0; x < N1; ++x)
+                  {
+                    o += a.Mx[q * N1 + x] * P[x];
+                    o += a.Kx[q * N1 + x] * Q[x];
+                  }
+                pP[q] = o;
+              }
+          }
+        if (!EARLY && batch + gridDim.x < n_batches)
+          {
+            cart_decode<N1, T>(a, batch + gridDim.x, slot, i, c);
+            cart_gather<N1, T, NBS>(a, c, v, w);
+          }
+        __syncthreads();
+        // ---------------- scatter-add
+        if (cur.active && !cur.plane_con)
+          {
+            T       *d  = a.dst[j] + cur.base;
+            const T *pP = bufP + cb * CBS + i;
+            if (!cur.any_yz)
+              {
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy) atomicAdd(d + jy * sy + k * sz, pP[(k * N1 + jy) * LS]);
+              }
+            else
+              {
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy)
+                    {
+                      const bool cn = (cur.ylo && jy == 0) || (cur.yhi && jy == K) || (cur.zlo && k == 0) || (cur.zhi && k == K);
+                      if (!cn) atomicAdd(d + jy * sy + k * sz, pP[(k * N1 + jy) * LS]);
+                    }
+              }
+          }
+        __syncthreads(); // bufP is rewritten by the next batch
+      }
+  }
 } // namespace stfem
