@@ -28,6 +28,19 @@ namespace stfem
       }
   }
 
+  // all analytic functions are  amp(t) * prod_d sin(2 pi f x_d): the time factor alone
+  __host__ __device__ inline double analytic_amp(int fid, int dim, double t, double f)
+  {
+    switch (fid)
+      {
+        case 1: return sin(2 * ST_PI * f * t);
+        case 2: return dim * 4 * ST_PI * ST_PI * f * f * sin(2 * ST_PI * f * t) + 2 * ST_PI * f * cos(2 * ST_PI * f * t);
+        case 3: return 2 * ST_PI * f * cos(2 * ST_PI * f * t);
+        case 4: return pow(2.0, (double)dim) * (ST_PI * f) * (ST_PI * f) * sin(2 * ST_PI * f * t);
+        default: return 0.0;
+      }
+  }
+
   __device__ inline void exact_gradient(int dim, const double *x, double t, double f, double *g)
   {
     const double tv = 2 * ST_PI * f * sin(2 * ST_PI * f * t);
@@ -50,6 +63,9 @@ namespace stfem
     double        gll[7];   // FE support points
     double        xq[8], wq[8];
     double        S[56], D[56]; // [q*n1+i] values / derivatives of the GLL basis at xq
+    // Cartesian meshes: sin(2 pi f x) at the quadrature coordinates of every cell, per direction
+    // ([cell * nq1 + q]); null = evaluate the function at every quadrature point
+    const double *sin_tab[3] = {nullptr, nullptr, nullptr};
   };
 
   // MappingQ1: point and Jacobian at reference coordinates xi of a cell
@@ -141,10 +157,17 @@ namespace stfem
           {
             const int    qi[3] = {q % nq1, (q / nq1) % nq1, dim == 3 ? q / (nq1 * nq1) : 0};
             const double xi[3] = {g.xq[qi[0]], g.xq[qi[1]], dim == 3 ? g.xq[qi[2]] : 0.0};
+            const double w = g.wq[qi[0]] * g.wq[qi[1]] * (dim == 3 ? g.wq[qi[2]] : 1.0);
+            if (g.sin_tab[0])
+              {
+                double v = analytic_amp(fid, dim, t, freq) * g.h[0] * g.h[1] * (dim == 3 ? g.h[2] : 1.0);
+                for (int d = 0; d < dim; ++d) v *= g.sin_tab[d][c[d] * nq1 + qi[d]];
+                bufA[q] = v * w;
+                continue;
+              }
             double       x[3], J[3][3], inv[3][3];
             map_q1(g, c, xi, x, J);
             const double det = det_inv(dim, J, inv);
-            const double w   = g.wq[qi[0]] * g.wq[qi[1]] * (dim == 3 ? g.wq[qi[2]] : 1.0);
             bufA[q]          = analytic_value(fid, dim, x, t, freq) * det * w;
           }
         __syncthreads();

@@ -215,7 +215,7 @@ namespace stfem
   // Cartesian 3D fast path (st_vmult_cart.cuh)
   // PIPE = 0: one batch of cells per CTA; PIPE = NBS > 0: persistent software-pipelined kernel for NBS source blocks
   // (register budget 65536 / (MAXT * MINB), rounded down to a multiple of 8)
-  template <int N1, typename T, int MAXT, int MINB, int PIPE = 0>
+  template <int N1, typename T, int MAXT, int MINB, int PIPE = 0, int EXPERIMENT = 0>
   static int launch_cart(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                          const void *beta)
   {
@@ -303,7 +303,7 @@ namespace stfem
       }
     else
       {
-        auto kern = st_vmult_cart_kernel<N1, T, MAXT, MINB>;
+        auto kern = st_vmult_cart_kernel<N1, T, MAXT, MINB, EXPERIMENT>;
         if (smem > 48 * 1024)
           STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, threads, smem, stream>>>(a);
@@ -345,6 +345,13 @@ namespace stfem
               if (op->variant == 12) return launch_cart<4, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<4, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 4:
+              if (sizeof(T) == 8 && op->variant >= 31 && op->variant <= 34 && nbd * 5 <= 128)
+                {
+                  if (op->variant == 31) return launch_cart<5, T, 128, 3, 0, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                  if (op->variant == 32) return launch_cart<5, T, 128, 3, 0, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                  if (op->variant == 33) return launch_cart<5, T, 128, 3, 0, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                  return launch_cart<5, T, 128, 3, 0, 4>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                }
               if (op->variant == 24 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 25 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 2, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 20 && nb_src == 2 && nbd * 5 <= 128) return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);

@@ -50,6 +50,11 @@ struct stfem_time_integrator
   FgmresResult        last;
   AsmGeom             geom;
   BlockVec<double>    tmp; // one spatial vector
+  double             *d_sin_tab = nullptr;
+  ~stfem_time_integrator()
+  {
+    if (d_sin_tab) cudaFree(d_sin_tab);
+  }
 
   int assemble_force(void *const *rhs, double time, double tau)
   {
@@ -147,6 +152,24 @@ int stfem_ti_create(const stfem_ti_desc *d, stfem_ti_t *out)
     }
   fill_asm_geom(ti->geom, ti->matrix->mesh, ti->matrix->degree, ti->matrix->degree + 1);
   STFEM_FORWARD(ti->tmp.alloc(ti->matrix->mesh->ctx, 1, ti->matrix->N));
+  if (ti->fid != 0 && !ti->geom.vertices)
+    {
+      // separable source term on a Cartesian mesh: 1D tables of sin(2 pi f x_q) instead of 3 sin() per quadrature point
+      const AsmGeom      &g = ti->geom;
+      std::vector<double> tab;
+      size_t              off[3] = {0, 0, 0};
+      for (int d = 0; d < g.dim; ++d)
+        {
+          off[d] = tab.size();
+          for (int c = 0; c < g.n[d]; ++c)
+            for (int q = 0; q < g.nq1; ++q) tab.push_back(std::sin(2 * ST_PI * ti->freq * (g.lower[d] + g.h[d] * (c + g.xq[q]))));
+        }
+      stfem_ctx *ctx = ti->matrix->mesh->ctx;
+      STFEM_CUDA_CHECK(cudaMalloc(&ti->d_sin_tab, tab.size() * sizeof(double)));
+      STFEM_CUDA_CHECK(cudaMemcpyAsync(ti->d_sin_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      for (int d = 0; d < g.dim; ++d) ti->geom.sin_tab[d] = ti->d_sin_tab + off[d];
+    }
   *out = ti.release();
   return STFEM_OK;
 }

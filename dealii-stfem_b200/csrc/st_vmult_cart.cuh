@@ -58,7 +58,8 @@ namespace stfem
   };
 
   // MAXT / MINB: launch bounds (threads per CTA, resident CTAs per SM) = the register budget ptxas gets
-  template <int N1, typename T, int MAXT, int MINB>
+  // EXPERIMENT (tuning only, wrong results): 1 = no scatter, 2 = no gather (constants), 3 = neither, 4 = no x sweep
+  template <int N1, typename T, int MAXT, int MINB, int EXPERIMENT = 0>
   __global__ void __launch_bounds__(MAXT, MINB) st_vmult_cart_kernel(const __grid_constant__ CartArgs<T, N1> a)
   {
     using L           = ExchLayout<N1>;
@@ -119,7 +120,7 @@ namespace stfem
 #pragma unroll
                   for (int jy = 0; jy < N1; ++jy)
                     {
-                      const T u = p[jy * sy + k * sz];
+                      const T u = (EXPERIMENT == 2 || EXPERIMENT == 3) ? T(jy + k) + be : p[jy * sy + k * sz];
                       v[k][jy] += be * u;
                       w[k][jy] += al * u;
                     }
@@ -191,6 +192,7 @@ namespace stfem
     __syncthreads();
 
     // ---------------- phase B: x sweep on N1 lines of this cell-block, result overwrites P
+    if (EXPERIMENT != 4)
     {
 #pragma unroll
       for (int m = 0; m < N1; ++m)
@@ -226,7 +228,16 @@ namespace stfem
       {
         T       *d  = a.dst[j] + base;
         const T *pP = bufP + cb * CBS + i;
-        if (!any_yz)
+        if (EXPERIMENT == 1 || EXPERIMENT == 3)
+          {
+            T acc = T(0);
+#pragma unroll
+            for (int k = 0; k < N1; ++k)
+#pragma unroll
+              for (int jy = 0; jy < N1; ++jy) acc += pP[(k * N1 + jy) * LS];
+            if (acc == T(12345.678)) d[0] = acc;
+          }
+        else if (!any_yz)
           {
 #pragma unroll
             for (int k = 0; k < N1; ++k)

@@ -32,17 +32,18 @@ namespace stfem
   __global__ void k_transfer_1d(Transfer1D<T> tr, int mode, int axis, int on0, int on1, int on2, int in_len, long long blocks,
                                 const T *__restrict__ in, T *__restrict__ out, int final_add, unsigned dirichlet, int dim)
   {
+    // 3D launch: x = node index along the fastest direction, y = second index, z = (third index, time block):
+    // no 64-bit divisions per entry
     const long long out_per_block = (long long)on0 * on1 * on2;
-    const long long total         = out_per_block * blocks;
     const int       nc_loc        = tr.sc + 1;
-    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+    const int       i0            = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= on0) return;
+    const int i1 = blockIdx.y;
+    for (int zb = blockIdx.z; zb < on2 * (int)blocks; zb += gridDim.z)
       {
-        const long long b  = gid / out_per_block;
-        long long       r  = gid % out_per_block;
-        const int       i0 = (int)(r % on0);
-        r /= on0;
-        const int i1 = (int)(r % on1);
-        const int i2 = (int)(r / on1);
+        const int       b   = zb / on2;
+        const int       i2  = zb - b * on2;
+        const long long gid = (long long)b * out_per_block + (long long)i0 + (long long)on0 * (i1 + (long long)on1 * i2);
         int       idx[3] = {i0, i1, i2};
         const int o      = idx[axis];
         // input strides: same as output except along axis
@@ -157,9 +158,11 @@ namespace stfem
 
     void launch(int mode, int axis, const int *on, int in_len, int nb, const T *in, T *out, bool fin)
     {
-      const long long total = (long long)on[0] * on[1] * on[2] * nb;
-      k_transfer_1d<T><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(tr[axis], mode, axis, on[0], on[1], on[2], in_len, nb, in,
-                                                                            out, fin ? 1 : 0, dirichlet, dim);
+      const int  threads = on[0] >= 128 ? 128 : (on[0] >= 64 ? 64 : 32);
+      const long long nz = (long long)on[2] * nb;
+      const dim3 grid((on[0] + threads - 1) / threads, on[1], (unsigned)(nz < 65535 ? nz : 65535));
+      k_transfer_1d<T><<<grid, threads, 0, ctx->stream>>>(tr[axis], mode, axis, on[0], on[1], on[2], in_len, nb, in, out, fin ? 1 : 0,
+                                                          dirichlet, dim);
       ctx->launches++;
     }
 
