@@ -8,6 +8,7 @@
 #include "st_vmult_cart.cuh"
 #include "vec.cuh"
 #include "st_vmult_generic.cuh"
+#include "st_vmult_plane.cuh"
 
 namespace stfem
 {
@@ -313,6 +314,69 @@ namespace stfem
     return STFEM_OK;
   }
 
+  // general-geometry 3D path (st_vmult_plane.cuh)
+  template <int N1, typename T, int MAXT, int MINB>
+  static int launch_plane(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
+                          const void *beta)
+  {
+    stfem_mesh       *m = op->mesh;
+    PlaneArgs<T, N1>  a;
+    for (int q = 0; q < N1 * N1; ++q)
+      {
+        a.S[q]  = (T)op->shape->S[q];
+        a.Dc[q] = (T)op->shape->Dc[q];
+      }
+    a.n_cells = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        a.n[d]      = m->n[d];
+        a.np[d]     = op->np[d];
+        a.box_lo[d] = op->box_lo ? op->box_lo[d] : 0;
+        a.box_n[d]  = op->box_n ? op->box_n[d] : m->n[d];
+        a.n_cells *= a.box_n[d];
+      }
+    if (a.n_cells <= 0) return STFEM_OK;
+    cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
+    a.nb_src = nb_src;
+    a.nb_dst = nb_dst;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
+      {
+        a.src[b] = b < nb_src ? (const T *)src[b] : nullptr;
+        a.dst[b] = b < nb_dst ? (T *)dst[b] : nullptr;
+      }
+    a.alpha      = (const T *)alpha;
+    a.beta       = (const T *)beta;
+    a.coeff_cell = (const T *)op->d_coeff;
+    a.dirichlet  = m->dirichlet;
+    a.metric     = (const T *)op->d_metric_plane;
+    const int    tpc      = nb_dst * N1;
+    const size_t per_cell = (size_t)4 * nb_dst * ExchLayout<N1>::CBS * sizeof(T);
+    const size_t smem_cap = (size_t)(220 * 1024) / MINB;
+    STFEM_REQUIRE(tpc <= MAXT && per_cell <= smem_cap, "st_vmult (general): %d threads per cell / %zu bytes do not fit the CTA", tpc, per_cell);
+    int    best = 1;
+    double best_score = -1;
+    for (int c = 1; c * tpc <= MAXT; ++c)
+      {
+        if (c * per_cell > smem_cap) break;
+        const int    thr   = c * tpc;
+        const double score = (double)thr / (((thr + 31) / 32) * 32) + 1e-4 * thr;
+        if (score > best_score + 1e-9)
+          {
+            best_score = score;
+            best       = c;
+          }
+      }
+    a.cells_per_cta   = best;
+    const size_t smem = best * per_cell;
+    auto         kern = st_vmult_plane_kernel<N1, T, MAXT, MINB>;
+    if (smem > 48 * 1024) STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (a.n_cells + best - 1) / best;
+    kern<<<(unsigned)grid, best * tpc, smem, stream>>>(a);
+    m->ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
   // true if op_apply runs the Cartesian kernel (which supports cell sub-boxes / streams)
   static bool uses_cart(const stfem_op *op)
   {
@@ -370,6 +434,19 @@ namespace stfem
             default: break;
           }
       }
+    if (DIM == 3 && op->variant != 1 && op->d_metric_plane && nb_dst * (op->degree + 1) <= 128)
+      switch (op->degree)
+        {
+          case 1: return launch_plane<2, T, 128, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          case 2: return launch_plane<3, T, 128, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          case 3:
+            if (op->variant == 11) return launch_plane<4, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            return launch_plane<4, T, 128, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          case 4:
+            if (op->variant == 11) return launch_plane<5, T, 128, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            return launch_plane<5, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          default: break;
+        }
     switch (op->degree)
       {
         case 1: return launch_generic<DIM, 2, T>(op, dst, src, nb_src, nb_dst, alpha, beta);
@@ -580,6 +657,19 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
         STFEM_FORWARD(compute_metric<double>(op.get(), &op->d_metric));
       else
         STFEM_FORWARD(compute_metric<float>(op.get(), &op->d_metric));
+      if (mesh->dim == 3 && op->degree <= 4)
+        {
+          const size_t nvals = (size_t)mesh->n_cells * nq * 8;
+          STFEM_CUDA_CHECK(cudaMalloc(&op->d_metric_plane, nvals * (f64 ? 8 : 4) + 16));
+          const long long tot = mesh->n_cells * nq;
+          if (f64)
+            k_metric_to_plane_layout<double><<<grid_for(ctx, tot, 256), 256, 0, ctx->stream>>>((const double *)op->d_metric, mesh->n_cells, n1, (double *)op->d_metric_plane);
+          else
+            k_metric_to_plane_layout<float><<<grid_for(ctx, tot, 256), 256, 0, ctx->stream>>>((const float *)op->d_metric, mesh->n_cells, n1, (float *)op->d_metric_plane);
+          ctx->launches++;
+          STFEM_CUDA_CHECK(cudaGetLastError());
+          STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        }
     }
   *out = op.release();
   return STFEM_OK;
@@ -590,7 +680,7 @@ int stfem_op_destroy(stfem_op_t op)
   if (!op) return STFEM_OK;
   cudaSetDevice(op->mesh->ctx->device);
   cudaStreamSynchronize(op->mesh->ctx->stream);
-  for (void *p : {op->d_alpha, op->d_beta, op->d_alphaT, op->d_betaT, op->d_alpha_neg, op->d_beta_neg, op->d_metric, op->d_coeff})
+  for (void *p : {op->d_alpha, op->d_beta, op->d_alphaT, op->d_betaT, op->d_alpha_neg, op->d_beta_neg, op->d_metric, op->d_metric_plane, op->d_coeff})
     if (p) cudaFree(p);
   for (void *p : op->d_scratch)
     if (p) cudaFree(p);

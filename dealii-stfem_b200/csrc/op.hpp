@@ -15,6 +15,7 @@ struct stfem_op
   void *d_alpha = nullptr, *d_beta = nullptr, *d_alphaT = nullptr, *d_betaT = nullptr;
   void *d_alpha_neg = nullptr, *d_beta_neg = nullptr; // -Alpha, -Beta: residual r = b - A x in one cell loop
   void *d_metric = nullptr; // general geometry: per cell, per q-point metric (+JxW)
+  void *d_metric_plane = nullptr; // the same in the order st_vmult_plane_kernel reads it (3D, degree <= 4)
   void *d_coeff = nullptr;  // per-cell Laplace coefficient
   std::vector<double> h_coeff_cell, h_coeff_q; // host copies (Vanka set-up works in double)
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points

@@ -16,7 +16,17 @@ variants = [int(v) for v in sys.argv[4:]] or [0]
 ttype, tdeg = os.environ.get("TT", "CGP"), int(os.environ.get("TR", "2"))
 A, B = ft.get_fe_time_weights(ttype, tdeg, 2.0 ** -6, int(os.environ.get("NTS", "1")))[:2]
 ctx = st.Context(0)
-mesh = st.Mesh(ctx, [cells] * 3)
+distort = float(os.environ.get("DISTORT", "0"))
+if distort > 0:
+    # perturbed mesh: interior vertices moved by up to distort * h in every direction (deterministic)
+    n1 = cells + 1
+    g = np.linspace(0.0, 1.0, n1)
+    V = np.stack(np.meshgrid(g, g, g, indexing="ij")[::-1], axis=-1)          # [z][y][x][xyz]
+    d = np.random.RandomState(1).uniform(-1, 1, V.shape) * distort / cells
+    d[0, :, :, :] = d[-1, :, :, :] = 0; d[:, 0, :, :] = d[:, -1, :, :] = 0; d[:, :, 0, :] = d[:, :, -1, :] = 0
+    mesh = st.Mesh(ctx, [cells] * 3, vertices=(V + d).reshape(-1, 3))
+else:
+    mesh = st.Mesh(ctx, [cells] * 3)
 ref = None
 for variant in variants:
     op = st.Operator(mesh, degree, A, B, number_type=nt, variant=variant)

@@ -276,3 +276,51 @@ def test_host_buffer_entry_point_pipeline(ctx, cells, k):
         assert _rel(out, ref) < 1e-12
         assert np.all(out[:, space.constrained] == 0)
     op.close(); gm.close()
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("k,sub,ttype,r,nts,mask", [(1, [3, 2, 2], "DG", 1, 1, 0x3f), (2, [2, 3, 2], "CGP", 2, 1, 0x3f),
+                                                    (3, [3, 3, 2], "DG", 2, 1, 0x15), (4, [2, 2, 3], "CGP", 2, 1, 0x3f),
+                                                    (4, [3, 1, 2], "DG", 1, 2, 0x00)])
+def test_general_geometry_plane_kernel(ctx, k, sub, ttype, r, nts, mask, number_type):
+    """csrc/st_vmult_plane.cuh (perturbed MappingQ1 cells + per-q coefficient) against the oracle and against the
+    generic q-point kernel (variant 1), incl. Tvmult, partial Dirichlet masks and rectangular slice operators."""
+    import dealii_stfem_b200 as st
+    mesh = S.Mesh(3, sub, 0, lower=[0, 0, 0], upper=[1.0, 1.2, 0.8], distort=0.15)
+    space = S.Space(mesh, k, dirichlet_faces=mask)
+    A, B, G, Z = _time_matrices(ttype, r, nts)
+    nb = A.shape[0]
+    dt = np.float64 if number_type == 0 else np.float32
+    Kop = S.MatrixFreeOperator(space, 0.0, 1.0)
+    rng = np.random.RandomState(11)
+    cq = rng.uniform(0.5, 2.0, (mesh.n_cells, (k + 1) ** 3))
+    Kop.laplace_coeff = cq
+    Mop = S.MatrixFreeOperator(space, 1.0, 0.0)
+    sysm = S.SystemMatrix(Kop, Mop, A, B)
+    src = _rand_block(nb, space.n_dofs).astype(dt)
+    ref_dst, ref_t = sysm.vmult(src.astype(np.float64)), sysm.Tvmult(src.astype(np.float64))
+    gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper, vertices=mesh.vertices.reshape(-1, 3), dirichlet_faces=mask)
+    outs = {}
+    for variant in (0, 1):
+        op = st.Operator(gm, k, A, B, number_type=number_type, laplace_coeff_q=cq, variant=variant)
+        d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+        op.vmult(d_dst, d_src)
+        outs[variant] = d_dst.download()
+        assert _rel(outs[variant].astype(np.float64), ref_dst) < TOL[number_type], "variant %d" % variant
+        assert np.all(outs[variant][:, space.constrained] == 0)
+        op.Tvmult(d_dst, d_src)
+        assert _rel(d_dst.download().astype(np.float64), ref_t) < TOL[number_type], "variant %d (T)" % variant
+        d_src.free(); d_dst.free(); op.close()
+    assert _rel(outs[0].astype(np.float64), outs[1].astype(np.float64)) < TOL[number_type]
+    if number_type == 0:
+        sl = S.SystemMatrix(Kop, Mop, G, Z)
+        src0 = _rand_block(1, space.n_dofs, seed=7)
+        dst0 = _rand_block(G.shape[0], space.n_dofs, seed=9)
+        dst0[:, space.constrained] = 0
+        ref_sl = sl.vmult_slice_add(dst0.copy(), src0[0])
+        op = st.Operator(gm, k, G, Z, laplace_coeff_q=cq)
+        d_src, d_dst = op.new_vector(1).upload(src0), op.new_vector(G.shape[0]).upload(dst0)
+        op.vmult_slice_add(d_dst, d_src)
+        assert _rel(d_dst.download(), ref_sl) < 1e-12
+        d_src.free(); d_dst.free(); op.close()
+    gm.close()
