@@ -128,6 +128,38 @@ def ncu_traffic(n_cells):
     return json.load(open(p)).get("dram_bytes_per_launch")
 
 
+def perturbed_leg(st, ctx, n, steps=20):
+    """The same operator on a randomly perturbed mesh (GridTools::distort_random-style, factor 0.15) with a per-q
+    coefficient table: general-geometry kernel (csrc/st_vmult_plane.cuh) with the precomputed metric."""
+    A, B = time_weights()
+    n1 = n + 1
+    g = np.linspace(0.0, 1.0, n1)
+    V = np.stack(np.meshgrid(g, g, g, indexing="ij")[::-1], axis=-1)
+    d = np.random.RandomState(1).uniform(-1, 1, V.shape) * 0.15 / n
+    d[0] = d[-1] = 0
+    d[:, 0] = d[:, -1] = 0
+    d[:, :, 0] = d[:, :, -1] = 0
+    mesh = st.Mesh(ctx, [n, n, n], vertices=(V + d).reshape(-1, 3))
+    op = st.Operator(mesh, DEGREE, A, B, number_type=st.F64)
+    nb = op.nb_rows
+    x, y = op.new_vector(), op.new_vector()
+    x.upload(np.sin(0.1 * np.arange(op.n)[None, :] + np.arange(nb)[:, None]))
+    for _ in range(3):
+        op.vmult(y, x)
+    ctx.timer_start()
+    for _ in range(steps):
+        op.vmult(y, x)
+    ms = ctx.timer_stop() / steps
+    dofs = op.n * nb
+    # algorithmic bytes: vectors + the metric the kernel streams (8 numbers per quadrature point)
+    alg = dofs * BYTES_PER_DOF + n ** 3 * (DEGREE + 1) ** 3 * 8 * 8
+    out = {"metric": "space-time DoFs/s, operator vmult on a perturbed mesh (MappingQ1 cells, precomputed metric), FP64",
+           "value": dofs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "cells": n ** 3, "distortion": 0.15,
+           "achieved_GBs": alg / (ms * 1e-3) / 1e9, "algorithmic_bytes_per_launch": alg}
+    x.free(); y.free(); op.close(); mesh.close()
+    return out
+
+
 def solve_leg(st, ctx, refinement, n_steps=3, grid=None, coords=None, reduce_max=None):
     """Full STMG-preconditioned FGMRES time steps of configs[1] (3D heat, Q4 x cG(2), float multigrid) through the
     product driver: rhs assembly + solve per step, all on the device (tests/tp_01.cc:646-669)."""
@@ -174,6 +206,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the STMG-FGMRES solve leg")
+    ap.add_argument("--no-perturbed", action="store_true", help="skip the perturbed-mesh operator leg")
     ap.add_argument("--solve-refinement", type=int, default=5, help="solve leg: subdivisions 3, this many refinements (5 = 96^3 cells)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -313,6 +346,8 @@ def main():
             "e2e": {"value": total_dofs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(dofs_rank * 8), "d2h_bytes_per_step": int(dofs_rank * 8)},
             "gpu_launches": int(launches), "clocks": clocks}
+    if world == 1 and not args.no_perturbed:
+        line["perturbed_mesh"] = perturbed_leg(st, ctx, n)
     if not args.no_solve:
         for v in (x, y):
             v.free()

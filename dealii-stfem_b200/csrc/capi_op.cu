@@ -377,6 +377,71 @@ namespace stfem
     return STFEM_OK;
   }
 
+  // TMA variant of the Cartesian kernel (whole mesh rows, n_x divisible by CPC)
+  template <int N1, typename T, int CPC, int MAXT, int MINB>
+  static int launch_cart_tma(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
+                             const void *beta)
+  {
+    stfem_mesh      *m = op->mesh;
+    CartArgs<T, N1>  a;
+    const ShapeHost &sh = *op->shape;
+    double           h[3], vol = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        h[d] = (m->upper[d] - m->lower[d]) / m->n[d];
+        vol *= h[d];
+        a.n[d]      = m->n[d];
+        a.np[d]     = op->np[d];
+        a.box_lo[d] = 0;
+        a.box_n[d]  = m->n[d];
+      }
+    for (int i = 0; i < N1; ++i)
+      for (int j = 0; j < N1; ++j)
+        {
+          long double mm = 0, kk = 0;
+          for (int q = 0; q < N1; ++q)
+            {
+              mm += (long double)sh.wq[q] * sh.S[q * N1 + i] * sh.S[q * N1 + j];
+              kk += (long double)sh.wq[q] * sh.D[q * N1 + i] * sh.D[q * N1 + j];
+            }
+          a.M[i * N1 + j]  = (T)mm;
+          a.Ky[i * N1 + j] = (T)(kk / (h[1] * h[1]));
+          a.Kz[i * N1 + j] = (T)(kk / (h[2] * h[2]));
+          a.Mx[i * N1 + j] = (T)(mm * vol);
+          a.Kx[i * N1 + j] = (T)(kk * vol / (h[0] * h[0]));
+        }
+    a.n_cells = m->n_cells;
+    a.nb_src  = nb_src;
+    a.nb_dst  = nb_dst;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
+      {
+        a.src[b] = b < nb_src ? (const T *)src[b] : nullptr;
+        a.dst[b] = b < nb_dst ? (T *)dst[b] : nullptr;
+      }
+    a.alpha         = (const T *)alpha;
+    a.beta          = (const T *)beta;
+    a.coeff_cell    = (const T *)op->d_coeff;
+    a.dirichlet     = m->dirichlet;
+    a.cells_per_cta = CPC;
+    constexpr int EPV    = 16 / (int)sizeof(T);
+    constexpr int ROWLEN = CPC * (N1 - 1) + 1;
+    constexpr int COPY   = ((ROWLEN + EPV - 1 + EPV - 1) / EPV) * EPV;
+    const int     tpc    = nb_dst * N1;
+    const size_t  smem   = 16 + (size_t)N1 * N1 * nb_src * COPY * sizeof(T) + (size_t)2 * CPC * nb_dst * ExchLayout<N1>::CBS * sizeof(T);
+    const int     threads = ((CPC * tpc + 31) / 32) * 32;
+    STFEM_REQUIRE(threads <= MAXT && m->n[0] % CPC == 0 && smem <= (size_t)(220 * 1024) / MINB, "st_vmult (TMA): configuration does not fit");
+    auto kern = st_vmult_cart_tma_kernel<N1, T, CPC, MAXT, MINB>;
+    if (smem > 48 * 1024) STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long       grid     = m->n_cells / CPC;
+    const long long resident = (long long)m->ctx->sm_count * MINB;
+    if (grid > resident) grid = resident;
+    cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
+    kern<<<(unsigned)grid, threads, smem, stream>>>(a);
+    m->ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
   // true if op_apply runs the Cartesian kernel (which supports cell sub-boxes / streams)
   static bool uses_cart(const stfem_op *op)
   {
@@ -409,6 +474,16 @@ namespace stfem
               if (op->variant == 12) return launch_cart<4, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<4, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 4:
+              if (op->variant >= 40 && op->variant <= 42 && !op->box_lo)
+                {
+                  if (nbd * 5 * 12 <= 128 && op->mesh->n[0] % 12 == 0)
+                    {
+                      if (op->variant == 40) return launch_cart_tma<5, T, 12, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                      if (op->variant == 41) return launch_cart_tma<5, T, 12, 128, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                    }
+                  if (nbd * 5 * 8 <= 128 && op->mesh->n[0] % 8 == 0)
+                    return launch_cart_tma<5, T, 8, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
+                }
               if (sizeof(T) == 8 && op->variant >= 31 && op->variant <= 34 && nbd * 5 <= 128)
                 {
                   if (op->variant == 31) return launch_cart<5, T, 128, 3, 0, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);

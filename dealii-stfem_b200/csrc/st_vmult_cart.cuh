@@ -511,3 +511,254 @@ namespace stfem
       }
   }
 } // namespace stfem
+
+// ----------------------------------------------------------------------------------------------------------------
+// TMA variant of the Cartesian kernel (sm_90+/sm_100a: cp.async.bulk + mbarrier).  Persistent CTAs; a batch is
+// CPC x-adjacent cells of one mesh row, whose source values are CPC*K+1 consecutive numbers per (block, y, z): the
+// 25*nb_src rows of a batch are fetched by bulk asynchronous copies (global -> shared, completion counted on an
+// mbarrier) issued by warp 0 as soon as the previous batch has been consumed, i.e. they land while the x sweep and
+// the scatter of the previous batch run.  No register staging and no LSU gather traffic: phase A reads the rows
+// from shared memory (conflict-free, lanes = consecutive x).  Rows are only 8-byte aligned in the block vectors
+// (odd numbers of DoFs per line); every copy starts at the enclosing 16-byte boundary and moves one extra element,
+// the parity of each row is recomputed when it is read.  The last element of the last row may lie one number past
+// the end of a block vector: allocations are padded (stfem_dev_alloc).
+namespace stfem
+{
+  __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  }
+  __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+  {
+    unsigned ok;
+    do
+      {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n"
+                     "}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+      }
+    while (!ok);
+  }
+  __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+  {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+
+  // CPC cells per batch (compile time: row length), requires n_x % CPC == 0 and a launch over whole mesh rows
+  template <int N1, typename T, int CPC, int MAXT, int MINB>
+  __global__ void __launch_bounds__(MAXT, MINB) st_vmult_cart_tma_kernel(const __grid_constant__ CartArgs<T, N1> a)
+  {
+    using L              = ExchLayout<N1>;
+    constexpr int K      = N1 - 1;
+    constexpr int LS     = L::LS;
+    constexpr int CBS    = L::CBS;
+    constexpr int EPV    = 16 / (int)sizeof(T);                    // elements per 16 bytes
+    constexpr int ROWLEN = CPC * K + 1;                            // numbers per row
+    constexpr int COPY   = ((ROWLEN + EPV - 1 + EPV - 1) / EPV) * EPV; // copied numbers: worst misalignment included
+    constexpr int RSTR   = COPY;                                   // row stride in the tile (multiple of 16 bytes)
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    unsigned long long *bar  = reinterpret_cast<unsigned long long *>(smem_tma);
+    T                  *tile = reinterpret_cast<T *>(smem_tma + 16);
+    const int           n_rows = N1 * N1 * a.nb_src;
+    T                  *bufP = tile + (size_t)n_rows * RSTR;
+    T                  *bufQ = bufP + (size_t)CPC * a.nb_dst * CBS;
+
+    const int tid  = threadIdx.x;
+    const int tpc  = a.nb_dst * N1;
+    const int slot = tid / tpc;
+    const int rem  = tid - slot * tpc;
+    const int j    = rem / N1;
+    const int i    = rem - j * N1;
+    const int cb   = tid / N1;
+    const bool worker = slot < CPC; // threads beyond CPC*tpc (warp padding) only take part in barriers
+    const int sy   = a.np[0];
+    const int sz   = a.np[0] * a.np[1];
+    const int bpr  = a.n[0] / CPC;                                 // batches per mesh row
+    const long long n_batches = (long long)bpr * a.n[1] * a.n[2];
+
+    // row r = (s, k, jy) of batch b: source address, rounded down to 16 bytes
+    auto issue = [&](long long b) {
+      const int bx = (int)(b % bpr);
+      long long r2 = b / bpr;
+      const int cy = (int)(r2 % a.n[1]), cz = (int)(r2 / a.n[1]);
+      const long long e0 = (long long)bx * CPC * K + (long long)sy * (cy * K) + (long long)sz * (cz * K);
+      if (tid == 0) mbar_expect_tx(bar, (unsigned)(n_rows * COPY * sizeof(T)));
+      // the copies are warp-uniform instructions (one per lane, serialised): spread the rows over all warps
+      const int n_warps = blockDim.x >> 5;
+      for (int r = (tid >> 5) + n_warps * (tid & 31); r < n_rows; r += n_warps * 32)
+        {
+          const int s = r / (N1 * N1), kj = r - s * (N1 * N1);
+          const int k = kj / N1, jy = kj - k * N1;
+          const unsigned long long addr = (unsigned long long)(a.src[s] + e0 + (long long)jy * sy + (long long)k * sz);
+          bulk_g2s(tile + (size_t)r * RSTR, (const void *)(addr & ~15ull), COPY * sizeof(T), bar);
+        }
+    };
+
+    if (tid == 0)
+      {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+    __syncthreads();
+    long long batch = blockIdx.x;
+    if (batch < n_batches) issue(batch);
+    unsigned phase = 0;
+
+    for (; batch < n_batches; batch += gridDim.x)
+      {
+        const int bx = (int)(batch % bpr);
+        long long r2 = batch / bpr;
+        const int cy = (int)(r2 % a.n[1]), cz = (int)(r2 / a.n[1]);
+        const int cx = bx * CPC + slot;
+        const unsigned dm  = a.dirichlet;
+        const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;
+        const bool     ylo = (dm & 4u) && cy == 0, yhi = (dm & 8u) && cy == a.n[1] - 1;
+        const bool     zlo = (dm & 16u) && cz == 0, zhi = (dm & 32u) && cz == a.n[2] - 1;
+        const bool     plane_constrained = (xlo && i == 0) || (xhi && i == K);
+        const bool     any_yz            = ylo || yhi || zlo || zhi;
+        const long long e0   = (long long)bx * CPC * K + (long long)sy * (cy * K) + (long long)sz * (cz * K);
+        const long long base = e0 + slot * K + i;
+
+        // ---------------- phase A: contraction straight from the tile
+        T v[N1][N1], w[N1][N1];
+#pragma unroll
+        for (int k = 0; k < N1; ++k)
+#pragma unroll
+          for (int jy = 0; jy < N1; ++jy) v[k][jy] = w[k][jy] = T(0);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        if (worker && !plane_constrained)
+          {
+            const T coef = a.coeff_cell ? a.coeff_cell[(long long)cx + (long long)a.n[0] * (cy + (long long)a.n[1] * cz)] : T(1);
+            for (int s = 0; s < a.nb_src; ++s)
+              {
+                const T be = a.beta[j * a.nb_src + s];
+                const T al = a.alpha[j * a.nb_src + s] * coef;
+                // misalignment (in numbers) of the row (k = 0, jy = 0) and its change per row
+                const unsigned long long a0 = (unsigned long long)(a.src[s] + e0);
+                const int                m0 = (int)((a0 & 15ull) / sizeof(T));
+                const T                 *tp = tile + (size_t)s * (N1 * N1) * RSTR + slot * K + i;
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+#pragma unroll
+                  for (int jy = 0; jy < N1; ++jy)
+                    {
+                      const int  mis = (m0 + jy * sy + k * sz) & (EPV - 1);
+                      const bool c   = any_yz && ((ylo && jy == 0) || (yhi && jy == K) || (zlo && k == 0) || (zhi && k == K));
+                      const T    u   = c ? T(0) : tp[(k * N1 + jy) * RSTR + mis];
+                      v[k][jy] += be * u;
+                      w[k][jy] += al * u;
+                    }
+              }
+          }
+        // ---------------- y sweep
+#pragma unroll
+        for (int k = 0; k < N1; ++k)
+          {
+            T s_[N1], t_[N1];
+#pragma unroll
+            for (int q = 0; q < N1; ++q)
+              {
+                T ss = T(0), tt = T(0);
+#pragma unroll
+                for (int jy = 0; jy < N1; ++jy)
+                  {
+                    ss += a.M[q * N1 + jy] * v[k][jy];
+                    ss += a.Ky[q * N1 + jy] * w[k][jy];
+                    tt += a.M[q * N1 + jy] * w[k][jy];
+                  }
+                s_[q] = ss;
+                t_[q] = tt;
+              }
+#pragma unroll
+            for (int q = 0; q < N1; ++q)
+              {
+                v[k][q] = s_[q];
+                w[k][q] = t_[q];
+              }
+          }
+        // ---------------- z sweep + publish
+        if (worker)
+          {
+            T *pP = bufP + cb * CBS + i;
+            T *pQ = bufQ + cb * CBS + i;
+#pragma unroll
+            for (int jy = 0; jy < N1; ++jy)
+#pragma unroll
+              for (int q = 0; q < N1; ++q)
+                {
+                  T pp = T(0), qq = T(0);
+#pragma unroll
+                  for (int k = 0; k < N1; ++k)
+                    {
+                      pp += a.M[q * N1 + k] * v[k][jy];
+                      pp += a.Kz[q * N1 + k] * w[k][jy];
+                      qq += a.M[q * N1 + k] * w[k][jy];
+                    }
+                  pP[(q * N1 + jy) * LS] = pp;
+                  pQ[(q * N1 + jy) * LS] = qq;
+                }
+          }
+        __syncthreads(); // tile consumed by everybody, P/Q complete
+        if (batch + gridDim.x < n_batches) issue(batch + gridDim.x);
+        // ---------------- x sweep
+        if (worker)
+          {
+#pragma unroll
+            for (int m = 0; m < N1; ++m)
+              {
+                const int line = L::blocked ? N1 * i + m : i + N1 * m;
+                T        *pP   = bufP + cb * CBS + line * LS;
+                const T  *pQ   = bufQ + cb * CBS + line * LS;
+                T         P[N1], Q[N1];
+#pragma unroll
+                for (int x = 0; x < N1; ++x)
+                  {
+                    P[x] = pP[x];
+                    Q[x] = pQ[x];
+                  }
+#pragma unroll
+                for (int q = 0; q < N1; ++q)
+                  {
+                    T o = T(0);
+#pragma unroll
+                    for (int x = 0; x < N1; ++x)
+                      {
+                        o += a.Mx[q * N1 + x] * P[x];
+                        o += a.Kx[q * N1 + x] * Q[x];
+                      }
+                    pP[q] = o;
+                  }
+              }
+          }
+        __syncthreads();
+        // ---------------- scatter-add
+        if (worker && !plane_constrained)
+          {
+            T       *d  = a.dst[j] + base;
+            const T *pP = bufP + cb * CBS + i;
+#pragma unroll
+            for (int k = 0; k < N1; ++k)
+#pragma unroll
+              for (int jy = 0; jy < N1; ++jy)
+                {
+                  const bool cn = any_yz && ((ylo && jy == 0) || (yhi && jy == K) || (zlo && k == 0) || (zhi && k == K));
+                  if (!cn) atomicAdd(d + jy * sy + k * sz, pP[(k * N1 + jy) * LS]);
+                }
+          }
+        __syncthreads(); // P/Q are rewritten by the next batch
+      }
+  }
+} // namespace stfem

@@ -324,3 +324,28 @@ def test_general_geometry_plane_kernel(ctx, k, sub, ttype, r, nts, mask, number_
         assert _rel(d_dst.download(), ref_sl) < 1e-12
         d_src.free(); d_dst.free(); op.close()
     gm.close()
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("cells,variant", [([12, 2, 3], 40), ([24, 2, 2], 41), ([8, 3, 2], 42), ([12, 3, 2], 20)])
+def test_cartesian_kernel_tma_and_pipelined_variants(ctx, cells, variant, number_type):
+    """Tuning variants of the Cartesian Q4 kernel (cp.async.bulk + mbarrier gather: 40-42; register-prefetch
+    persistent kernel: 20) must reproduce the oracle like the default one (odd row lengths: every second row of the
+    block vectors is only 8-byte aligned, which the bulk-copy path has to handle)."""
+    import dealii_stfem_b200 as st
+    k = 4
+    mesh = S.Mesh(3, cells, 0, lower=[0, 0, 0], upper=[1.0, 0.5, 0.75])
+    space = S.Space(mesh, k, dirichlet_faces=0x1b)
+    A, B, _, _ = _time_matrices("CGP", 2, 1)
+    dt = np.float64 if number_type == 0 else np.float32
+    sysm = S.SystemMatrix(S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0), A, B)
+    src = _rand_block(2, space.n_dofs).astype(dt)
+    ref_dst = sysm.vmult(src.astype(np.float64))
+    gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper, dirichlet_faces=0x1b)
+    op = st.Operator(gm, k, A, B, number_type=number_type, variant=variant)
+    d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+    op.vmult(d_dst, d_src)
+    out = d_dst.download()
+    assert _rel(out.astype(np.float64), ref_dst) < TOL[number_type]
+    assert np.all(out[:, space.constrained] == 0)
+    d_src.free(); d_dst.free(); op.close(); gm.close()
