@@ -254,6 +254,7 @@ namespace stfem
         a.n_cells *= a.box_n[d];
       }
     if (a.n_cells <= 0) return STFEM_OK;
+    STFEM_REQUIRE(a.n_cells < (1ll << 31), "st_vmult: more than 2^31 cells per GPU are not supported");
     cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
     a.nb_src  = nb_src;
     a.nb_dst  = nb_dst;
@@ -277,7 +278,9 @@ namespace stfem
         if (c * per_cell > smem_cap) break;
         const int    thr = c * tpc;
         const double eff = (double)thr / (((thr + 31) / 32) * 32);
-        const double score = eff + 1e-4 * thr; // fill warps first, then prefer the larger CTA
+        // one-warp CTAs are fastest (barriers become warp-local, more independent CTAs per SM): take the smallest
+        // CTA whose warps are >= 90 % full, else the fullest one; variant 17 keeps the old "largest CTA" rule
+        const double score = op->variant == 17 ? eff + 1e-4 * thr : (eff >= 0.9 ? 2.0 - 1e-4 * thr : eff);
         if (score > best_score + 1e-9)
           {
             best_score = score;
@@ -336,6 +339,7 @@ namespace stfem
         a.n_cells *= a.box_n[d];
       }
     if (a.n_cells <= 0) return STFEM_OK;
+    STFEM_REQUIRE(a.n_cells < (1ll << 31), "st_vmult: more than 2^31 cells per GPU are not supported");
     cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
     a.nb_src = nb_src;
     a.nb_dst = nb_dst;
@@ -359,7 +363,9 @@ namespace stfem
       {
         if (c * per_cell > smem_cap) break;
         const int    thr   = c * tpc;
-        const double score = (double)thr / (((thr + 31) / 32) * 32) + 1e-4 * thr;
+        const double eff   = (double)thr / (((thr + 31) / 32) * 32);
+        // unlike the Cartesian kernel this one is faster with large CTAs (variant 17: smallest well-filled CTA)
+        const double score = op->variant != 17 ? eff + 1e-4 * thr : (eff >= 0.9 ? 2.0 - 1e-4 * thr : eff);
         if (score > best_score + 1e-9)
           {
             best_score = score;
@@ -501,8 +507,12 @@ namespace stfem
               if (op->variant == 12) return launch_cart<5, T, 160, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 13) return launch_cart<5, T, 192, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 14) return launch_cart<5, T, 96, 4>(op, dst, src, nb_src, nb_dst, alpha, beta);
-              // FP32 (multigrid levels): persistent kernel with the next batch's gather prefetched before the x sweep
-              if (sizeof(T) == 4 && op->variant == 0 && nb_src == 2 && nbd * 5 <= 128)
+              if (op->variant == 19 && nbd * 5 <= 32) return launch_cart<5, T, 32, 14>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 26 && nbd * 5 <= 32) return launch_cart<5, T, 32, 16>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 15 && nbd * 5 <= 64) return launch_cart<5, T, 64, 6>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 16 && nbd * 5 <= 32) return launch_cart<5, T, 32, 12>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              // variant 18: FP32 persistent kernel with the next batch's gather prefetched before the x sweep
+              if (sizeof(T) == 4 && op->variant == 18 && nb_src == 2 && nbd * 5 <= 128)
                 return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<5, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 5: return launch_cart<6, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);

@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "../../include/stfem_b200.h"
 
 namespace stfem
@@ -83,11 +85,11 @@ namespace stfem
     int             cx = 0, cy = 0, cz = 0;
     if (active)
       {
-        long long c = cell;
-        cx          = a.box_lo[0] + (int)(c % a.box_n[0]);
-        c /= a.box_n[0];
-        cy = a.box_lo[1] + (int)(c % a.box_n[1]);
-        cz = a.box_lo[2] + (int)(c / a.box_n[1]);
+        unsigned c = (unsigned)cell; // < 2^31 cells (checked by the launcher): 32-bit divisions
+        cx          = a.box_lo[0] + (int)(c % (unsigned)a.box_n[0]);
+        c /= (unsigned)a.box_n[0];
+        cy = a.box_lo[1] + (int)(c % (unsigned)a.box_n[1]);
+        cz = a.box_lo[2] + (int)(c / (unsigned)a.box_n[1]);
       }
     const unsigned dm  = a.dirichlet;
     const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;
@@ -101,44 +103,77 @@ namespace stfem
 
     // ---------------- phase A: gather + temporal contraction (read_dof_values: constrained -> 0)
     T v[N1][N1], w[N1][N1]; // [z][y]
-#pragma unroll
-    for (int k = 0; k < N1; ++k)
-#pragma unroll
-      for (int jy = 0; jy < N1; ++jy) v[k][jy] = w[k][jy] = T(0);
     if (active && !plane_constrained)
       {
         const T coef = a.coeff_cell ? a.coeff_cell[(long long)cx + (long long)a.n[0] * (cy + (long long)a.n[1] * cz)] : T(1);
-        for (int s = 0; s < a.nb_src; ++s)
+        // the first source block initialises the accumulators (no zero fill), the others accumulate
+        auto gather = [&](int s, auto first) {
+          const T  be = a.beta[j * a.nb_src + s];
+          const T  al = a.alpha[j * a.nb_src + s] * coef;
+          const T *p  = a.src[s] + base;
+          if (!any_yz)
+            {
+#pragma unroll
+              for (int k = 0; k < N1; ++k)
+#pragma unroll
+                for (int jy = 0; jy < N1; ++jy)
+                  {
+                    const T u = (EXPERIMENT == 2 || EXPERIMENT == 3) ? T(jy + k) + be : p[jy * sy + k * sz];
+                    v[k][jy]  = decltype(first)::value ? be * u : v[k][jy] + be * u;
+                    w[k][jy]  = decltype(first)::value ? al * u : w[k][jy] + al * u;
+                  }
+            }
+          else
+            {
+#pragma unroll
+              for (int k = 0; k < N1; ++k)
+#pragma unroll
+                for (int jy = 0; jy < N1; ++jy)
+                  {
+                    const bool c = (ylo && jy == 0) || (yhi && jy == K) || (zlo && k == 0) || (zhi && k == K);
+                    const T    u = c ? T(0) : p[jy * sy + k * sz];
+                    v[k][jy]     = decltype(first)::value ? be * u : v[k][jy] + be * u;
+                    w[k][jy]     = decltype(first)::value ? al * u : w[k][jy] + al * u;
+                  }
+            }
+        };
+        if (a.nb_src == 2 && !any_yz && EXPERIMENT == 0)
           {
-            const T  be = a.beta[j * a.nb_src + s];
-            const T  al = a.alpha[j * a.nb_src + s] * coef;
-            const T *p  = a.src[s] + base;
-            if (!any_yz)
-              {
+            // two source blocks (the common case): all 2 N1^2 loads are issued back to back into the v / w registers,
+            // the 2x2 contraction then happens in place -> one exposed load latency instead of two
+            const T  be0 = a.beta[j * 2], be1 = a.beta[j * 2 + 1];
+            const T  al0 = a.alpha[j * 2] * coef, al1 = a.alpha[j * 2 + 1] * coef;
+            const T *p0 = a.src[0] + base, *p1 = a.src[1] + base;
 #pragma unroll
-                for (int k = 0; k < N1; ++k)
+            for (int k = 0; k < N1; ++k)
 #pragma unroll
-                  for (int jy = 0; jy < N1; ++jy)
-                    {
-                      const T u = (EXPERIMENT == 2 || EXPERIMENT == 3) ? T(jy + k) + be : p[jy * sy + k * sz];
-                      v[k][jy] += be * u;
-                      w[k][jy] += al * u;
-                    }
-              }
-            else
-              {
+              for (int jy = 0; jy < N1; ++jy)
+                {
+                  v[k][jy] = p0[jy * sy + k * sz];
+                  w[k][jy] = p1[jy * sy + k * sz];
+                }
 #pragma unroll
-                for (int k = 0; k < N1; ++k)
+            for (int k = 0; k < N1; ++k)
 #pragma unroll
-                  for (int jy = 0; jy < N1; ++jy)
-                    {
-                      const bool c = (ylo && jy == 0) || (yhi && jy == K) || (zlo && k == 0) || (zhi && k == K);
-                      const T    u = c ? T(0) : p[jy * sy + k * sz];
-                      v[k][jy] += be * u;
-                      w[k][jy] += al * u;
-                    }
-              }
+              for (int jy = 0; jy < N1; ++jy)
+                {
+                  const T u0 = v[k][jy], u1 = w[k][jy];
+                  v[k][jy]   = be0 * u0 + be1 * u1;
+                  w[k][jy]   = al0 * u0 + al1 * u1;
+                }
           }
+        else
+          {
+            gather(0, std::true_type());
+            for (int s = 1; s < a.nb_src; ++s) gather(s, std::false_type());
+          }
+      }
+    else
+      {
+#pragma unroll
+        for (int k = 0; k < N1; ++k)
+#pragma unroll
+          for (int jy = 0; jy < N1; ++jy) v[k][jy] = w[k][jy] = T(0);
       }
 
     // ---------------- y sweep (registers):  s = Mh v + Ky w,  t = Mh w
@@ -278,11 +313,11 @@ namespace stfem
     int cx = 0, cy = 0, cz = 0;
     if (c.active)
       {
-        long long r = cell;
-        cx          = a.box_lo[0] + (int)(r % a.box_n[0]);
-        r /= a.box_n[0];
-        cy = a.box_lo[1] + (int)(r % a.box_n[1]);
-        cz = a.box_lo[2] + (int)(r / a.box_n[1]);
+        unsigned r = (unsigned)cell;
+        cx         = a.box_lo[0] + (int)(r % (unsigned)a.box_n[0]);
+        r /= (unsigned)a.box_n[0];
+        cy = a.box_lo[1] + (int)(r % (unsigned)a.box_n[1]);
+        cz = a.box_lo[2] + (int)(r / (unsigned)a.box_n[1]);
       }
     const unsigned dm  = a.dirichlet;
     const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;

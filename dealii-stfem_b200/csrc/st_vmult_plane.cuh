@@ -95,11 +95,11 @@ namespace stfem
     int             cx = 0, cy = 0, cz = 0;
     if (active)
       {
-        long long c = cell_in_box;
-        cx          = a.box_lo[0] + (int)(c % a.box_n[0]);
-        c /= a.box_n[0];
-        cy = a.box_lo[1] + (int)(c % a.box_n[1]);
-        cz = a.box_lo[2] + (int)(c / a.box_n[1]);
+        unsigned c = (unsigned)cell_in_box; // < 2^31 cells (checked by the launcher): 32-bit divisions
+        cx          = a.box_lo[0] + (int)(c % (unsigned)a.box_n[0]);
+        c /= (unsigned)a.box_n[0];
+        cy = a.box_lo[1] + (int)(c % (unsigned)a.box_n[1]);
+        cz = a.box_lo[2] + (int)(c / (unsigned)a.box_n[1]);
       }
     const long long cell = (long long)cx + (long long)a.n[0] * (cy + (long long)a.n[1] * cz);
     const unsigned  dm   = a.dirichlet;

@@ -687,7 +687,8 @@ namespace stfem
     for (int c = 1; c * tpc <= 256; ++c)
       {
         const int    thr = c * tpc;
-        const double score = (double)thr / (((thr + 31) / 32) * 32) + (thr >= 96 && thr <= 160 ? 0.01 : 0.0);
+        const double eff = (double)thr / (((thr + 31) / 32) * 32);
+        const double score = eff >= 0.9 ? 2.0 - 1e-4 * thr : eff; // smallest CTA with well-filled warps (see launch_cart)
         if (score > best_score + 1e-9) { best_score = score; best = c; }
       }
     a.cells_per_cta = best;

@@ -90,11 +90,11 @@ namespace stfem
     int             c[3] = {0, 0, 0};
     if (active)
       {
-        long long cc = cell;
-        c[0]         = (int)(cc % a.n[0]);
-        cc /= a.n[0];
-        c[1] = (int)(cc % a.n[1]);
-        c[2] = (int)(cc / a.n[1]);
+        unsigned cc = (unsigned)cell; // < 2^31 cells: 32-bit divisions
+        c[0]        = (int)(cc % (unsigned)a.n[0]);
+        cc /= (unsigned)a.n[0];
+        c[1] = (int)(cc % (unsigned)a.n[1]);
+        c[2] = (int)(cc / (unsigned)a.n[1]);
       }
     int  cls[3];
     bool lo_shared[3], hi_shared[3], lo_con[3], hi_con[3];
