@@ -507,6 +507,8 @@ namespace stfem
               if (op->variant == 12) return launch_cart<5, T, 160, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 13) return launch_cart<5, T, 192, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 14) return launch_cart<5, T, 96, 4>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 27 && nbd * 5 <= 32) return launch_cart<5, T, 32, 13>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              if (op->variant == 28 && nbd * 5 <= 32) return launch_cart<5, T, 32, 20>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 19 && nbd * 5 <= 32) return launch_cart<5, T, 32, 14>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 26 && nbd * 5 <= 32) return launch_cart<5, T, 32, 16>(op, dst, src, nb_src, nb_dst, alpha, beta);
               if (op->variant == 15 && nbd * 5 <= 64) return launch_cart<5, T, 64, 6>(op, dst, src, nb_src, nb_dst, alpha, beta);
@@ -514,6 +516,8 @@ namespace stfem
               // variant 18: FP32 persistent kernel with the next batch's gather prefetched before the x sweep
               if (sizeof(T) == 4 && op->variant == 18 && nb_src == 2 && nbd * 5 <= 128)
                 return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              // FP32: 128 registers suffice without spills -> 16 one-warp CTAs per SM
+              if (sizeof(T) == 4 && op->variant == 0 && nbd * 5 <= 32) return launch_cart<5, T, 32, 16>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<5, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 5: return launch_cart<6, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
             default: break;
