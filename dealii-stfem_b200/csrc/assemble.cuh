@@ -160,7 +160,7 @@ namespace stfem
             const double w = g.wq[qi[0]] * g.wq[qi[1]] * (dim == 3 ? g.wq[qi[2]] : 1.0);
             if (g.sin_tab[0])
               {
-                double v = analytic_amp(fid, dim, t, freq) * g.h[0] * g.h[1] * (dim == 3 ? g.h[2] : 1.0);
+                double v = (fid < 0 ? 1.0 : analytic_amp(fid, dim, t, freq)) * g.h[0] * g.h[1] * (dim == 3 ? g.h[2] : 1.0); // fid < 0: spatial factor only
                 for (int d = 0; d < dim; ++d) v *= g.sin_tab[d][c[d] * nq1 + qi[d]];
                 bufA[q] = v * w;
                 continue;

@@ -50,6 +50,7 @@ struct stfem_time_integrator
   FgmresResult        last;
   AsmGeom             geom;
   BlockVec<double>    tmp; // one spatial vector
+  BlockVec<double>    force_space; // Cartesian meshes: time-independent spatial part of the source term
   double             *d_sin_tab = nullptr;
   ~stfem_time_integrator()
   {
@@ -62,8 +63,23 @@ struct stfem_time_integrator
     stfem_ctx *ctx = matrix->mesh->ctx;
     if (fid == 0) return STFEM_OK;
     const long long total = geom.n_cells * (geom.dim == 3 ? geom.n1 * geom.n1 * geom.n1 : geom.n1 * geom.n1);
+    // Cartesian mesh: f(x, t) = amp(t) * prod sin(2 pi f x_d)  ->  the spatial integral (f_space, phi_i) is computed ONCE
+    // and reused for every quadrature point in time and every time step; each call reduces to rhs_b += coeff_b * F
+    const bool          separable = geom.sin_tab[0] != nullptr;
+    std::vector<double> coeff(nts * nd, 0.0);
+    if (separable && !force_space.d)
+      {
+        STFEM_FORWARD(force_space.alloc(ctx, 1, matrix->N));
+        k_integrate_function<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(geom, -1, 0.0, freq, 1.0, force_space.d);
+        ctx->launches++;
+      }
     auto add = [&](int block, double scale, double t) {
       if (scale == 0.0) return;
+      if (separable)
+        {
+          coeff[block] += scale * analytic_amp(fid, geom.dim, t, freq);
+          return;
+        }
       k_integrate_function<<<grid_for(ctx, total, 128), 128, 0, ctx->stream>>>(geom, fid, t, freq, scale, (double *)rhs[block]);
       ctx->launches++;
     };
@@ -78,6 +94,13 @@ struct stfem_time_integrator
           else
             add(it * nd + (int)j - 1, A1((int)j - 1, (int)j - 1), t);
         }
+    if (separable)
+      for (int b = 0; b < nts * nd; ++b)
+        if (coeff[b] != 0.0)
+          {
+            k_axpy<double><<<grid_for(ctx, matrix->N, 256), 256, 0, ctx->stream>>>(matrix->N, coeff[b], force_space.d, (double *)rhs[b]);
+            ctx->launches++;
+          }
     STFEM_CUDA_CHECK(cudaGetLastError());
     return STFEM_OK;
   }

@@ -8,6 +8,8 @@
 //   TimeTransfer  : MGTwoLevelTransferTime (stmg.h:114-247): small dense matrix across the time blocks,
 //                   one streaming pass (the reference does nnz(P) vector updates, operators.h:252-265).
 #pragma once
+#include <cstdlib>
+
 #include "basis_host.hpp"
 #include "fe_time.hpp"
 #include "vec.cuh"
@@ -92,6 +94,118 @@ namespace stfem
       }
   }
 
+  // One tensor direction, one thread per COARSE CELL along the axis (compile-time sizes: SC = coarse intervals per
+  // cell, SF = fine intervals per coarse cell; all P entries are immediate constant-bank operands):
+  //   prolongation: SC+1 loads -> SF (last cell SF+1) outputs;  restriction: 2 SF+1 loads -> SC (last cell SC+1) outputs
+  // 3D launch (x: fastest remaining index or cell, y, z x blocks), no divisions, no atomics.
+  template <typename T, int SC, int SF>
+  struct TransferLine
+  {
+    T P[(SF + 1) * (SC + 1)]; // P[lf * (SC+1) + a]
+  };
+
+  template <typename T, int SC, int SF, int MODE>
+  __global__ void k_transfer_line(const __grid_constant__ TransferLine<T, SC, SF> tr, int axis, int n_cells, int on0, int on1, int on2,
+                                  int in_len, int blocks, const T *__restrict__ in, T *__restrict__ out, int final_add, unsigned dirichlet,
+                                  int dim)
+  {
+    // thread coordinates: along `axis` the index is the coarse cell, along the others the node index
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t1 = blockIdx.y;
+    const int ext0 = axis == 0 ? n_cells : on0;
+    if (t0 >= ext0) return;
+    const int ext2 = axis == 2 ? n_cells : on2;
+    const int in0 = axis == 0 ? in_len : on0, in1 = axis == 1 ? in_len : on1, in2 = axis == 2 ? in_len : on2;
+    const long long out_per_block = (long long)on0 * on1 * on2, in_per_block = (long long)in0 * in1 * in2;
+    const long long os = axis == 0 ? 1 : (axis == 1 ? on0 : (long long)on0 * on1); // output stride along the axis
+    const long long is = axis == 0 ? 1 : (axis == 1 ? in0 : (long long)in0 * in1);
+    const int       on_axis = axis == 0 ? on0 : (axis == 1 ? on1 : on2);
+    for (int zb = blockIdx.z; zb < ext2 * blocks; zb += gridDim.z)
+      {
+        const int b  = zb / ext2;
+        const int t2 = zb - b * ext2;
+        const int c  = axis == 0 ? t0 : (axis == 1 ? t1 : t2); // coarse cell along the axis
+        int       idx[3] = {t0, t1, t2};
+        idx[axis]        = 0;
+        const T  *src = in + b * in_per_block + (long long)idx[0] + (long long)in0 * (idx[1] + (long long)in1 * idx[2]);
+        T        *dst = out + b * out_per_block + (long long)idx[0] + (long long)on0 * (idx[1] + (long long)on1 * idx[2]);
+        const bool last = c == n_cells - 1;
+        // constraint of the two fixed coordinates (final pass only)
+        bool fixed_con = false;
+        if (final_add)
+          {
+            const int onn[3] = {on0, on1, on2};
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              if (d != axis && d < dim)
+                {
+                  if (((dirichlet >> (2 * d)) & 1u) && idx[d] == 0) fixed_con = true;
+                  if (((dirichlet >> (2 * d + 1)) & 1u) && idx[d] == onn[d] - 1) fixed_con = true;
+                }
+          }
+        const bool axis_lo = (dirichlet >> (2 * axis)) & 1u, axis_hi = (dirichlet >> (2 * axis + 1)) & 1u;
+        if (MODE == 0)
+          {
+            T v[SC + 1];
+#pragma unroll
+            for (int a = 0; a <= SC; ++a) v[a] = src[is * (c * SC + a)];
+#pragma unroll
+            for (int lf = 0; lf <= SF; ++lf)
+              {
+                if (lf == SF && !last) break;
+                T s = T(0);
+#pragma unroll
+                for (int a = 0; a <= SC; ++a) s += tr.P[lf * (SC + 1) + a] * v[a];
+                const int o = c * SF + lf;
+                if (final_add)
+                  {
+                    const bool con = fixed_con || (axis_lo && o == 0) || (axis_hi && o == on_axis - 1);
+                    if (!con) dst[os * o] += s;
+                  }
+                else
+                  dst[os * o] = s;
+              }
+          }
+        else
+          {
+            T f[SF + 1], left[SF];
+#pragma unroll
+            for (int lf = 0; lf <= SF; ++lf) f[lf] = src[is * (c * SF + lf)];
+            if (c > 0)
+              {
+#pragma unroll
+                for (int lf = 0; lf < SF; ++lf) left[lf] = src[is * ((c - 1) * SF + lf)];
+              }
+            else
+              {
+#pragma unroll
+                for (int lf = 0; lf < SF; ++lf) left[lf] = T(0);
+              }
+#pragma unroll
+            for (int a = 0; a <= SC; ++a)
+              {
+                if (a == SC && !last) break;
+                T s = T(0);
+#pragma unroll
+                for (int lf = 0; lf <= SF; ++lf) s += tr.P[lf * (SC + 1) + a] * f[lf];
+                if (a == 0)
+                  {
+#pragma unroll
+                    for (int lf = 0; lf < SF; ++lf) s += tr.P[lf * (SC + 1) + SC] * left[lf];
+                  }
+                const int o = c * SC + a;
+                if (final_add)
+                  {
+                    const bool con = fixed_con || (axis_lo && o == 0) || (axis_hi && o == on_axis - 1);
+                    if (!con) dst[os * o] += s;
+                  }
+                else
+                  dst[os * o] = s;
+              }
+          }
+      }
+  }
+
   template <typename T>
   struct SpaceTransfer
   {
@@ -156,8 +270,34 @@ namespace stfem
       return STFEM_OK;
     }
 
+    template <int SC, int SF>
+    void launch_line(int mode, int axis, const int *on, int in_len, int nb, const T *in, T *out, bool fin)
+    {
+      TransferLine<T, SC, SF> tl;
+      for (int i = 0; i < (SF + 1) * (SC + 1); ++i) tl.P[i] = tr[axis].P[i];
+      const int nc   = tr[axis].n_cells;
+      const int ext0 = axis == 0 ? nc : on[0], ext1 = axis == 1 ? nc : on[1], ext2 = axis == 2 ? nc : on[2];
+      const int threads = ext0 >= 128 ? 128 : (ext0 >= 64 ? 64 : 32);
+      const long long nz = (long long)ext2 * nb;
+      const dim3 grid((ext0 + threads - 1) / threads, ext1, (unsigned)(nz < 65535 ? nz : 65535));
+      if (mode == 0)
+        k_transfer_line<T, SC, SF, 0><<<grid, threads, 0, ctx->stream>>>(tl, axis, nc, on[0], on[1], on[2], in_len, nb, in, out, fin ? 1 : 0, dirichlet, dim);
+      else
+        k_transfer_line<T, SC, SF, 1><<<grid, threads, 0, ctx->stream>>>(tl, axis, nc, on[0], on[1], on[2], in_len, nb, in, out, fin ? 1 : 0, dirichlet, dim);
+      ctx->launches++;
+    }
+
     void launch(int mode, int axis, const int *on, int in_len, int nb, const T *in, T *out, bool fin)
     {
+      // compile-time sized per-cell kernel for the h transfers of degree 1..6 and the common p transfers
+      const int sc = tr[axis].sc, sf = tr[axis].sf;
+      static const bool legacy = std::getenv("STFEM_LEGACY_TRANSFER") != nullptr;
+#define STFEM_TL(SC_, SF_) \
+  if (!legacy && sc == SC_ && sf == SF_) return launch_line<SC_, SF_>(mode, axis, on, in_len, nb, in, out, fin);
+      STFEM_TL(1, 2) STFEM_TL(2, 4) STFEM_TL(3, 6) STFEM_TL(4, 8) STFEM_TL(5, 10) STFEM_TL(6, 12)
+      STFEM_TL(1, 2) STFEM_TL(1, 3) STFEM_TL(1, 4) STFEM_TL(2, 3) STFEM_TL(2, 4) STFEM_TL(2, 5) STFEM_TL(3, 4) STFEM_TL(3, 5) STFEM_TL(3, 6)
+      STFEM_TL(4, 5) STFEM_TL(4, 6) STFEM_TL(5, 6) STFEM_TL(1, 5) STFEM_TL(1, 6) STFEM_TL(2, 6)
+#undef STFEM_TL
       const int  threads = on[0] >= 128 ? 128 : (on[0] >= 64 ? 64 : 32);
       const long long nz = (long long)on[2] * nb;
       const dim3 grid((on[0] + threads - 1) / threads, on[1], (unsigned)(nz < 65535 ? nz : 65535));
