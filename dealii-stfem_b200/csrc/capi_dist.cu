@@ -31,6 +31,7 @@ namespace stfem
     g_nccl.Send           = (int (*)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t))sym("ncclSend");
     g_nccl.Recv           = (int (*)(void *, size_t, int, int, nccl_comm_t, cudaStream_t))sym("ncclRecv");
     g_nccl.AllReduce      = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))sym("ncclAllReduce");
+    g_nccl.Broadcast      = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))sym("ncclBroadcast");
     g_nccl.GroupStart     = (int (*)())sym("ncclGroupStart");
     g_nccl.GroupEnd       = (int (*)())sym("ncclGroupEnd");
     g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");

@@ -28,6 +28,7 @@ namespace stfem
     int (*Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -108,6 +109,28 @@ namespace stfem
         if (((shared_faces & 4u) && iy == 0) || ((shared_faces & 8u) && iy == np1 - 1)) w *= T(0.5);
         if (((shared_faces & 16u) && iz == 0) || ((shared_faces & 32u) && iz == np2 - 1)) w *= T(0.5);
         if (w != T(1)) ((T *)blocks.p[blk])[gid % per] *= w;
+      }
+  }
+
+  // brick <-> global copies of the coarse-level agglomeration (csrc/mg.cuh): the local brick [b][bz][by][bx] sits at
+  // node offset (o0, o1, o2) of the global array [b][gz][gy][gx]
+  template <typename T, bool TO_GLOBAL>
+  __global__ void k_brick_global(T *__restrict__ brick, T *__restrict__ global, int nb, int b0, int b1, int b2, int g0, int g1, int g2, int o0,
+                                 int o1, int o2)
+  {
+    const long long per = (long long)b0 * b1 * b2, total = per * nb;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const int blk = (int)(gid / per);
+        long long r   = gid % per;
+        const int ix  = (int)(r % b0);
+        r /= b0;
+        const int       iy = (int)(r % b1), iz = (int)(r / b1);
+        const long long g  = (long long)blk * g0 * g1 * g2 + (long long)(ix + o0) + (long long)g0 * ((iy + o1) + (long long)g1 * (iz + o2));
+        if (TO_GLOBAL)
+          global[g] += brick[gid];
+        else
+          brick[gid] = global[g];
       }
   }
 

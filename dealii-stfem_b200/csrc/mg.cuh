@@ -61,6 +61,11 @@ namespace stfem
     TimeTransfer<T>           tt;
     BlockVec<T>               sol, defect, t, r, d, d2;
     int                       steps = 1;
+    // coarse-level agglomeration: this level is partitioned, the next coarser one is the GLOBAL mesh held (and
+    // solved redundantly) by every rank.  brick = this rank's part of the coarse level.
+    bool        agglo = false;
+    BlockVec<T> brick;
+    int         brick_np[3] = {1, 1, 1}, brick_off[3] = {0, 0, 0};
   };
 
   struct MGOptions
@@ -207,6 +212,23 @@ namespace stfem
       const PartitionInfo &part = lv.op->mesh->part;
       if (part.active)
         STFEM_FORWARD(halo_scale_interfaces<T>(ctx, part, lv.op->halo, fine.block_ptrs(), fine.nb, lv.op->np, lv.op->mesh->dim));
+      if (lv.agglo)
+        {
+          // restrict into this rank's brick of the coarse level, add the bricks into the global coarse vector
+          // (interface partial sums included) with ONE all-reduce; all coarser levels need no communication
+          stfem_op *oc  = L[l - 1].op;
+          NcclApi  *api = nccl_api();
+          STFEM_REQUIRE(api && ctx->nccl_comm, "multigrid: coarse-level agglomeration needs a communicator");
+          STFEM_FORWARD(lv.brick.zero());
+          STFEM_FORWARD(lv.st.restrict_and_add(lv.brick, fine));
+          k_brick_global<T, true><<<grid_for(ctx, lv.brick.size(), 256), 256, 0, ctx->stream>>>(lv.brick.d, coarse.d, coarse.nb, lv.brick_np[0], lv.brick_np[1],
+                                                                                               lv.brick_np[2], oc->np[0], oc->np[1], oc->np[2],
+                                                                                               lv.brick_off[0], lv.brick_off[1], lv.brick_off[2]);
+          ctx->launches++;
+          STFEM_NCCL_CHECK(api->AllReduce(coarse.d, coarse.d, (size_t)coarse.size(), std::is_same<T, double>::value ? NcclApi::kDouble : NcclApi::kFloat,
+                                          NcclApi::kSum, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+          return STFEM_OK;
+        }
       STFEM_FORWARD(lv.st.restrict_and_add(coarse, fine));
       if (part.active)
         {
@@ -214,6 +236,33 @@ namespace stfem
           STFEM_FORWARD(halo_compress_add<T>(ctx, oc->mesh->part, oc->halo, coarse.block_ptrs(), coarse.nb, oc->np, oc->mesh->dim));
         }
       return STFEM_OK;
+    }
+
+    // fine += P coarse.  Agglomerated coarse level: rank 0's (redundantly computed) coarse solution is made the common
+    // one by a broadcast - the redundant solves differ in the last bits (atomic summation order) and the copies of an
+    // interface DoF must stay identical on all ranks - then this rank's brick is cut out and prolongated locally.
+    int prolongate_level(int l, BlockVec<T> &fine, BlockVec<T> &coarse)
+    {
+      MGLevel<T> &lv = L[l];
+      if (lv.ttype != 'h' && lv.ttype != 'p')
+        {
+          lv.tt.prolongate_and_add(fine, coarse);
+          return STFEM_OK;
+        }
+      if (lv.agglo)
+        {
+          stfem_op *oc  = L[l - 1].op;
+          NcclApi  *api = nccl_api();
+          STFEM_REQUIRE(api && ctx->nccl_comm, "multigrid: coarse-level agglomeration needs a communicator");
+          STFEM_NCCL_CHECK(api->Broadcast(coarse.d, coarse.d, (size_t)coarse.size(), std::is_same<T, double>::value ? NcclApi::kDouble : NcclApi::kFloat, 0,
+                                          (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+          k_brick_global<T, false><<<grid_for(ctx, lv.brick.size(), 256), 256, 0, ctx->stream>>>(lv.brick.d, coarse.d, coarse.nb, lv.brick_np[0], lv.brick_np[1],
+                                                                                                lv.brick_np[2], oc->np[0], oc->np[1], oc->np[2],
+                                                                                                lv.brick_off[0], lv.brick_off[1], lv.brick_off[2]);
+          ctx->launches++;
+          return lv.st.prolongate_and_add(fine, lv.brick);
+        }
+      return lv.st.prolongate_and_add(fine, coarse);
     }
 
     // Multigrid::level_v_step; defect in L[l].defect, result in L[l].sol
@@ -233,10 +282,7 @@ namespace stfem
       STFEM_FORWARD(v_step(l - 1));
       {
         MGLevel<T> &lc = L[l - 1];
-        if (lv.ttype == 'h' || lv.ttype == 'p')
-          STFEM_FORWARD(lv.st.prolongate_and_add(lv.sol, lc.sol));
-        else
-          lv.tt.prolongate_and_add(lv.sol, lc.sol);
+        STFEM_FORWARD(prolongate_level(l, lv.sol, lc.sol));
       }
       for (int s = 0; s < lv.steps; ++s) STFEM_FORWARD(smooth_step(l, lv.sol, lv.defect));
       return STFEM_OK;
@@ -352,13 +398,38 @@ namespace stfem
             {
               lv.ttype = types[l - 1];
               stfem_op *oc = ops[l - 1];
+              const bool boundary = lv.op->mesh->part.active && !oc->mesh->part.active; // partitioned above, global below
               if (lv.ttype == 'h' || lv.ttype == 'p')
                 {
                   STFEM_REQUIRE(oc->nb_rows == nb, "mg: space transfer between levels with different block counts");
-                  STFEM_FORWARD(lv.st.init(ctx, lv.op->mesh->dim, oc->mesh->n, oc->degree, lv.op->mesh->n, lv.op->degree, lv.op->mesh->dirichlet));
+                  if (boundary)
+                    {
+                      // the coarse level is the global mesh on every rank: transfers act on this rank's brick of it
+                      const PartitionInfo &part = lv.op->mesh->part;
+                      const int            dim  = lv.op->mesh->dim;
+                      int                  nloc[3] = {1, 1, 1};
+                      long long            nbrick = 1;
+                      for (int d = 0; d < 3; ++d)
+                        {
+                          if (d < dim)
+                            {
+                              nloc[d] = lv.ttype == 'h' ? lv.op->mesh->n[d] / 2 : lv.op->mesh->n[d];
+                              STFEM_REQUIRE(nloc[d] * part.grid[d] == oc->mesh->n[d], "mg: global coarse mesh does not match the partitioned fine level");
+                            }
+                          lv.brick_np[d]  = d < dim ? oc->degree * nloc[d] + 1 : 1;
+                          lv.brick_off[d] = d < dim ? oc->degree * nloc[d] * part.coords[d] : 0;
+                          nbrick *= lv.brick_np[d];
+                        }
+                      lv.agglo = true;
+                      STFEM_FORWARD(lv.brick.alloc(ctx, nb, nbrick));
+                      STFEM_FORWARD(lv.st.init(ctx, dim, nloc, oc->degree, lv.op->mesh->n, lv.op->degree, lv.op->mesh->dirichlet));
+                    }
+                  else
+                    STFEM_FORWARD(lv.st.init(ctx, lv.op->mesh->dim, oc->mesh->n, oc->degree, lv.op->mesh->n, lv.op->degree, lv.op->mesh->dirichlet));
                 }
               else
                 {
+                  STFEM_REQUIRE(!boundary, "mg: the switch from partitioned to agglomerated levels must be a space (h/p) transfer");
                   STFEM_REQUIRE(oc->N == lv.op->N, "mg: time transfer between levels with different spatial size");
                   STFEM_FORWARD(lv.tt.init(time_type, lv_nts[l], lv_nd[l], lv_nts[l - 1], lv_nd[l - 1], opt.restrict_is_transpose_prolongate, lv.ttype));
                 }
@@ -499,8 +570,7 @@ namespace stfem
             STFEM_REQUIRE(l > 0, "no coarser level");
             STFEM_FORWARD(load(L[l - 1].sol, src));
             STFEM_FORWARD(lv.sol.zero());
-            if (lv.ttype == 'h' || lv.ttype == 'p') STFEM_FORWARD(lv.st.prolongate_and_add(lv.sol, L[l - 1].sol));
-            else lv.tt.prolongate_and_add(lv.sol, L[l - 1].sol);
+            STFEM_FORWARD(prolongate_level(l, lv.sol, L[l - 1].sol));
             return store(dst, lv.sol);
           case 4: // level operator
             STFEM_FORWARD(load(lv.defect, src));

@@ -268,7 +268,7 @@ namespace stfem
         k_multi_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0, sc.mask);
         ctx->launches++;
       }
-    if (ctx->n_ranks > 1 && ctx->nccl_comm)
+    if (sc.mask.active && ctx->n_ranks > 1 && ctx->nccl_comm) // vectors on agglomerated (global) levels are complete on every rank
       {
         NcclApi *api = nccl_api();
         STFEM_REQUIRE(api, "multi_dot: NCCL unavailable");
