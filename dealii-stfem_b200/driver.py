@@ -48,7 +48,7 @@ def default_parameters(dim=2):
         "subdivisions": [1] * dim, "distortGrid": 0.0, "distortCoeff": 0.0, "endTime": 1.0, "smoother": "relaxation",
         "smoothingSteps": 1, "smoothingRange": 1.0, "relaxation": 0.0, "coarseGridSmootherType": "Smoother",
         "restrictIsTransposeProlongate": True, "variable": True, "smoothingEigCgNIterations": 20,
-        "agglomerateBelow": 8,      # multi-GPU only (not a reference key): see HeatWaveProblem
+        "agglomerateBelow": 16,     # multi-GPU only (not a reference key): see HeatWaveProblem
     }
 
 
@@ -169,7 +169,7 @@ class HeatWaveProblem:
             # direction are kept as the GLOBAL mesh on every rank (solved redundantly, one all-reduce + one broadcast per
             # V-cycle at the switch) instead of exchanging latency-bound halos on tiny bricks
             agglomerate = partition is not None and rf != refinement and \
-                min(nn // g for nn, g in zip(n, partition[0])) < self.p.get("agglomerateBelow", 8)
+                min(nn // g for nn, g in zip(n, partition[0])) < self.p.get("agglomerateBelow", 16)
             if partition is None or agglomerate:
                 self.meshes[rf] = capi.Mesh(ctx, n, lower=lo, upper=up, vertices=v)
             else:

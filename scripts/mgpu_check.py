@@ -21,7 +21,7 @@ dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.dev
 ref = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 k, r, tt = 2, 1, "DG"
 pj = {"timeType": tt, "problemType": "heat", "feDegree": r, "refinement": ref, "subdivisions": "2,2,2", "mgTimeBeforeSpace": "true",
-      "smoother": "relaxation", "spaceTimeConvergenceTest": "true", "agglomerateBelow": os.environ.get("AGGLO", "8")}
+      "smoother": "relaxation", "spaceTimeConvergenceTest": "true", "agglomerateBelow": os.environ.get("AGGLO", "16")}
 p = st.parse_parameters(pj, 3)
 grid = st.dist.proc_grid_for(world, 3)
 coords = st.dist.coords_of(rank, grid)
