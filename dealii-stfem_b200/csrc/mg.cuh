@@ -689,28 +689,22 @@ namespace stfem
               for (int pass = 0; pass < 2; ++pass)
                 {
                   std::vector<const BlockVec<double> *> q = basis;
-                  q.push_back(&w);
+                  if (pass == 0) q.push_back(&w); // ||w||^2 is only informative in the first pass
                   STFEM_FORWARD(v_multi_dot(sc, w, q, h.data()));
                   std::vector<double> c(j + 1);
-                  double              sub = 0;
                   for (int i = 0; i <= j; ++i)
                     {
                       c[i] = -h[i];
                       Hm(i, j) += h[i];
-                      sub += h[i] * h[i];
                     }
-                  v_multi_axpy(w, basis, c.data());
-                  wnorm2 = h[j + 1] - sub;
+                  if (pass == 0)
+                    v_multi_axpy(w, basis, c.data());
+                  else // second pass: the norm of the orthogonalised vector is accumulated in the same sweep
+                    STFEM_FORWARD(v_multi_axpy_norm(sc, w, basis, c.data(), &wnorm2));
                 }
-              // the subtraction above loses accuracy when w is almost in the span: recompute the norm
-              STFEM_FORWARD(v_dot(sc, w, w, &wnorm2));
               const double hn = std::sqrt(std::max(wnorm2, 0.0));
               Hm(j + 1, j)    = hn;
-              if (hn != 0.0)
-                {
-                  STFEM_FORWARD(v_copy(V[j + 1], w));
-                  v_scale(V[j + 1], 1.0 / hn);
-                }
+              if (hn != 0.0) v_scale_copy(V[j + 1], 1.0 / hn, w);
               for (int i = 0; i < j; ++i)
                 {
                   const double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);

@@ -105,6 +105,49 @@ namespace stfem
         w[i] = s;
       }
   }
+  // w += sum_k c[k] V_k  and  *nrm2 += ||w_new||^2 in the same pass (Gram-Schmidt: the norm of the orthogonalised
+  // vector comes for free); mask: see DotMask
+  template <typename T>
+  __global__ void k_multi_axpy_norm(long long n, MultiCoef<T> mc, T *__restrict__ w, double *__restrict__ nrm2, int mask_active, int np0, int np1,
+                                    int np2, unsigned skip_high, long long n_block)
+  {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        T s = w[i];
+#pragma unroll 4
+        for (int k = 0; k < mc.m; ++k) s += mc.c[k] * mc.v[k][i];
+        w[i] = s;
+        bool skip = false;
+        if (mask_active)
+          {
+            long long r  = i % n_block;
+            const int ix = (int)(r % np0);
+            r /= np0;
+            const int iy = (int)(r % np1), iz = (int)(r / np1);
+            skip = ((skip_high & 1u) && ix == np0 - 1) || ((skip_high & 2u) && iy == np1 - 1) || ((skip_high & 4u) && iz == np2 - 1);
+          }
+        if (!skip) acc += (double)s * (double)s;
+      }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      {
+        double v = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sh[wv];
+        atomicAdd(nrm2, v);
+      }
+  }
+  // y = a * x
+  template <typename T>
+  __global__ void k_scale_copy(long long n, T a, const T *__restrict__ x, T *__restrict__ y)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      y[i] = a * x[i];
+  }
   // multi-GPU: interface DoFs are duplicated on both ranks; a dot product counts them on the lower rank only
   struct DotMask
   {
@@ -302,6 +345,49 @@ namespace stfem
         k_multi_axpy<T><<<grid_for(w.ctx, w.size(), 256), 256, 0, w.ctx->stream>>>(w.size(), mc, w.d);
         w.ctx->launches++;
       }
+  }
+  // w += sum_k c[k] V[k] (<= MAXK vectors per launch; the last launch also accumulates ||w||^2), returns the norm^2
+  template <typename T>
+  inline int v_multi_axpy_norm(DotScratch &sc, BlockVec<T> &w, const std::vector<const BlockVec<T> *> &V, const double *c, double *nrm2)
+  {
+    STFEM_FORWARD(sc.init());
+    stfem_ctx *ctx = w.ctx;
+    const int  m   = (int)V.size();
+    STFEM_CUDA_CHECK(cudaMemsetAsync(sc.d, 0, sizeof(double), ctx->stream));
+    for (int k0 = 0; k0 < m || k0 == 0; k0 += MAXK)
+      {
+        MultiCoef<T> mc;
+        mc.m = std::max(0, std::min(MAXK, m - k0));
+        for (int k = 0; k < mc.m; ++k)
+          {
+            mc.v[k] = V[k0 + k]->d;
+            mc.c[k] = (T)c[k0 + k];
+          }
+        const bool last = k0 + MAXK >= m;
+        if (last)
+          k_multi_axpy_norm<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d, sc.mask.active, sc.mask.np[0], sc.mask.np[1],
+                                                                                       sc.mask.np[2], sc.mask.skip_high, sc.mask.n_block);
+        else
+          k_multi_axpy<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d);
+        ctx->launches++;
+        if (last) break;
+      }
+    if (sc.mask.active && ctx->n_ranks > 1 && ctx->nccl_comm)
+      {
+        NcclApi *api = nccl_api();
+        STFEM_REQUIRE(api, "multi_axpy_norm: NCCL unavailable");
+        STFEM_NCCL_CHECK(api->AllReduce(sc.d, sc.d, 1, NcclApi::kDouble, NcclApi::kSum, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+      }
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(sc.h, sc.d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *nrm2 = sc.h[0];
+    return STFEM_OK;
+  }
+  template <typename T>
+  inline void v_scale_copy(BlockVec<T> &y, T a, const BlockVec<T> &x)
+  {
+    k_scale_copy<T><<<grid_for(y.ctx, y.size(), 256), 256, 0, y.ctx->stream>>>(y.size(), a, x.d, y.d);
+    y.ctx->launches++;
   }
   // dst (+)= P src across blocks; dst has P.m blocks, src P.n blocks, same n
   template <typename T>
