@@ -216,7 +216,7 @@ namespace stfem
   // Cartesian 3D fast path (st_vmult_cart.cuh)
   // PIPE = 0: one batch of cells per CTA; PIPE = NBS > 0: persistent software-pipelined kernel for NBS source blocks
   // (register budget 65536 / (MAXT * MINB), rounded down to a multiple of 8)
-  template <int N1, typename T, int MAXT, int MINB, int PIPE = 0, int EXPERIMENT = 0>
+  template <int N1, typename T, int MAXT, int MINB, int PIPE = 0, int EXPERIMENT = 0, bool PACKED = false>
   static int launch_cart(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                          const void *beta)
   {
@@ -307,7 +307,7 @@ namespace stfem
       }
     else
       {
-        auto kern = st_vmult_cart_kernel<N1, T, MAXT, MINB, EXPERIMENT>;
+        auto kern = st_vmult_cart_kernel<N1, T, MAXT, MINB, EXPERIMENT, PACKED>;
         if (smem > 48 * 1024)
           STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, threads, smem, stream>>>(a);
@@ -473,7 +473,9 @@ namespace stfem
         switch (op->degree)
           {
             case 1: return launch_cart<2, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
-            case 2: return launch_cart<3, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            case 2:
+              if (sizeof(T) == 8 && op->variant != 51) return launch_cart<3, T, 256, 2, 0, 0, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              return launch_cart<3, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 3:
               // variants 10.. = tuning configurations (launch bounds) of the same kernel
               if (op->variant == 11 || nbd * 4 > 128) return launch_cart<4, T, 256, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
@@ -518,6 +520,8 @@ namespace stfem
                 return launch_cart<5, T, 128, 3, 2>(op, dst, src, nb_src, nb_dst, alpha, beta);
               // FP32: 128 registers suffice without spills -> 16 one-warp CTAs per SM
               if (sizeof(T) == 4 && op->variant == 0 && nbd * 5 <= 32) return launch_cart<5, T, 32, 16>(op, dst, src, nb_src, nb_dst, alpha, beta);
+              // FP64: P/Q exchanged as 16-byte pairs (conflict-free 128-bit accesses); variant 51 = two 8-byte fields
+              if (sizeof(T) == 8 && op->variant != 51) return launch_cart<5, T, 128, 3, 0, 0, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<5, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 5: return launch_cart<6, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
             default: break;
