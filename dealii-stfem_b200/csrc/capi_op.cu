@@ -253,6 +253,24 @@ namespace stfem
         a.box_n[d]  = op->box_n ? op->box_n[d] : m->n[d];
         a.n_cells *= a.box_n[d];
       }
+    a.n_xbox = PIPE > 0 ? 0 : op->n_xbox;
+    if (a.n_xbox > 0)
+      {
+        a.n_cells = 0;
+        for (int b = 0; b < a.n_xbox; ++b)
+          {
+            a.xbox_start[b] = (int)a.n_cells;
+            long long nb_ = 1;
+            for (int d = 0; d < 3; ++d)
+              {
+                a.xbox_lo[b][d] = op->xbox_lo[b][d];
+                a.xbox_n[b][d]  = op->xbox_n[b][d];
+                nb_ *= op->xbox_n[b][d];
+              }
+            a.n_cells += nb_;
+          }
+        a.xbox_start[a.n_xbox] = (int)a.n_cells;
+      }
     if (a.n_cells <= 0) return STFEM_OK;
     STFEM_REQUIRE(a.n_cells < (1ll << 31), "st_vmult: more than 2^31 cells per GPU are not supported");
     cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
@@ -417,6 +435,7 @@ namespace stfem
           a.Kx[i * N1 + j] = (T)(kk * vol / (h[0] * h[0]));
         }
     a.n_cells = m->n_cells;
+    a.n_xbox  = 0;
     a.nb_src  = nb_src;
     a.nb_dst  = nb_dst;
     for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
@@ -602,24 +621,32 @@ namespace stfem
             ilo[d] = part.neighbor[d][0] >= 0 ? 1 : 0;
             ihi[d] = part.neighbor[d][1] >= 0 ? mn[d] - 1 : mn[d];
           }
-        // shell: z slabs (full x, y), y slabs (z interior), x slabs (y, z interior)
+        // shell: z slabs (full x, y), y slabs (z interior), x slabs (y, z interior) - all in ONE launch
         int rlo[3] = {0, 0, 0}, rhi[3] = {mn[0], mn[1], mn[2]};
+        op->n_xbox = 0;
         for (int d = 2; d >= 0; --d)
           {
             for (int sd = 0; sd < 2; ++sd)
               {
                 if (part.neighbor[d][sd] < 0) continue;
-                int lo[3] = {rlo[0], rlo[1], rlo[2]}, nn[3] = {rhi[0] - rlo[0], rhi[1] - rlo[1], rhi[2] - rlo[2]};
-                lo[d]      = sd == 0 ? 0 : mn[d] - 1;
-                nn[d]      = 1;
-                op->box_lo = lo;
-                op->box_n  = nn;
-                const int rc = dispatch();
-                op->box_lo = op->box_n = nullptr;
-                if (rc != STFEM_OK) return rc;
+                int *lo = op->xbox_lo[op->n_xbox], *nn = op->xbox_n[op->n_xbox];
+                for (int e = 0; e < 3; ++e)
+                  {
+                    lo[e] = rlo[e];
+                    nn[e] = rhi[e] - rlo[e];
+                  }
+                lo[d] = sd == 0 ? 0 : mn[d] - 1;
+                nn[d] = 1;
+                op->n_xbox++;
               }
             rlo[d] = ilo[d];
             rhi[d] = ihi[d];
+          }
+        if (op->n_xbox > 0)
+          {
+            const int rc = dispatch();
+            op->n_xbox   = 0;
+            if (rc != STFEM_OK) return rc;
           }
         STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));

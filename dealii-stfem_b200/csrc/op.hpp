@@ -23,6 +23,8 @@ struct stfem_op
   stfem::HaloBuffers halo;
   // launch context of the next kernel dispatch (set by op_apply's callers inside this file): cell sub-box, stream
   const int   *box_lo = nullptr, *box_n = nullptr;
+  int          n_xbox = 0;           // > 0: a list of boxes in one launch (Cartesian kernel only)
+  int          xbox_lo[6][3], xbox_n[6][3];
   cudaStream_t launch_stream = nullptr;
   bool  timing = false;
   float last_ms = 0.f;

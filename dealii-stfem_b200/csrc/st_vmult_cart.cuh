@@ -50,6 +50,10 @@ namespace stfem
     T         Mx[N1 * N1], Kx[N1 * N1];    // vol * Mh, vol * Kh / hx^2
     int       n[3], np[3];
     int       box_lo[3], box_n[3]; // sub-box of cells this launch processes (whole mesh: lo = 0, n = mesh)
+    // further boxes of the same launch (shell of cells along rank interfaces: up to 6 slabs in ONE launch instead of
+    // six small ones with their own tails); box b covers the linear cell range [xbox_start[b], xbox_start[b+1])
+    int       n_xbox;
+    int       xbox_lo[6][3], xbox_n[6][3], xbox_start[7];
     long long n_cells;             // cells in the sub-box
     int       nb_src, nb_dst, cells_per_cta;
     unsigned  dirichlet;
@@ -98,10 +102,23 @@ namespace stfem
     if (active)
       {
         unsigned c = (unsigned)cell; // < 2^31 cells (checked by the launcher): 32-bit divisions
-        cx          = a.box_lo[0] + (int)(c % (unsigned)a.box_n[0]);
-        c /= (unsigned)a.box_n[0];
-        cy = a.box_lo[1] + (int)(c % (unsigned)a.box_n[1]);
-        cz = a.box_lo[2] + (int)(c / (unsigned)a.box_n[1]);
+        if (a.n_xbox > 0)
+          {
+            int bx = 0;
+            while (bx + 1 < a.n_xbox && (int)c >= a.xbox_start[bx + 1]) ++bx;
+            c -= (unsigned)a.xbox_start[bx];
+            cx = a.xbox_lo[bx][0] + (int)(c % (unsigned)a.xbox_n[bx][0]);
+            c /= (unsigned)a.xbox_n[bx][0];
+            cy = a.xbox_lo[bx][1] + (int)(c % (unsigned)a.xbox_n[bx][1]);
+            cz = a.xbox_lo[bx][2] + (int)(c / (unsigned)a.xbox_n[bx][1]);
+          }
+        else
+          {
+            cx = a.box_lo[0] + (int)(c % (unsigned)a.box_n[0]);
+            c /= (unsigned)a.box_n[0];
+            cy = a.box_lo[1] + (int)(c % (unsigned)a.box_n[1]);
+            cz = a.box_lo[2] + (int)(c / (unsigned)a.box_n[1]);
+          }
       }
     const unsigned dm  = a.dirichlet;
     const bool     xlo = (dm & 1u) && cx == 0, xhi = (dm & 2u) && cx == a.n[0] - 1;

@@ -93,7 +93,12 @@ typedef struct stfem_op_desc {
   const double *laplace_coeff_q;    /* host pointer, n_cells * (degree+1)^dim values (cell-major, q-points
                                        lexicographic) = the reference's Table [cell][q]
                                        (operators.h:1060-1087, 1185-1186); may be NULL */
-  int kernel_variant;               /* 0 = default; >0 selects an implementation (tuning/tests) */
+  int kernel_variant;               /* 0 = default.  Tuning / cross-check selectors (all produce the same operator):
+                                       1 generic q-point kernel; 2 (level operators) dense Vanka patches instead of the
+                                       Kronecker form; 11-19, 26-28 launch-bound configurations of the Cartesian kernel;
+                                       17 largest-CTA rule; 18, 20-25 software-pipelined persistent kernel; 31-34 ablation
+                                       experiments (WRONG results, timing only); 40-42 cp.async.bulk + mbarrier gather;
+                                       51 two 8-byte exchange fields instead of 16-byte pairs */
 } stfem_op_desc;
 
 int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *out);
