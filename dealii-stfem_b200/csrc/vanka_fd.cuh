@@ -54,21 +54,64 @@ namespace stfem
       }
   }
 
-  // dispatch on the (warp-uniform in the interior) class so that every copy uses immediate constant-bank operands
-  template <typename T, int N1>
+  // INTERIOR (all cells of the CTA are interior cells in every direction - the bulk of the mesh): the class-1 matrices
+  // are immediate constant-bank operands.  Otherwise the matrix of the thread's class is addressed at run time (LDC per
+  // entry): slower, but only the CTAs touching the boundary take this path and the kernel stays small (one unrolled copy
+  // of every sweep instead of four).
+  template <typename T, int N1, bool INTERIOR>
   __device__ __forceinline__ void fd_apply_cls(const T (&Mats)[4][N1 * N1], int cls, const T (&in)[N1], T (&out)[N1])
   {
-    switch (cls)
+    if (INTERIOR)
+      fd_apply<T, N1>(Mats[1], in, out);
+    else
       {
-        case 0: fd_apply<T, N1>(Mats[0], in, out); break;
-        case 1: fd_apply<T, N1>(Mats[1], in, out); break;
-        case 2: fd_apply<T, N1>(Mats[2], in, out); break;
-        default: fd_apply<T, N1>(Mats[3], in, out); break;
+        const T *M = Mats[cls];
+#pragma unroll
+        for (int q = 0; q < N1; ++q)
+          {
+            T s = T(0);
+#pragma unroll
+            for (int a = 0; a < N1; ++a) s += M[q * N1 + a] * in[a];
+            out[q] = s;
+          }
       }
   }
 
+  template <int N1, int NB, typename T, bool INTERIOR>
+  __device__ __forceinline__ void vanka_fd_body(const VankaFdArgs<T, N1> &a, const int (&c)[3], bool active);
+
   template <int N1, int NB, typename T>
   __global__ void __launch_bounds__(256, 2) k_vanka_fd(const __grid_constant__ VankaFdArgs<T, N1> a)
+  {
+    const int       tpc    = NB * N1;
+    const int       slot   = threadIdx.x / tpc;
+    const long long cell   = (long long)blockIdx.x * a.cells_per_cta + slot;
+    const bool      active = cell < a.n_cells;
+    int             c[3] = {0, 0, 0};
+    if (active)
+      {
+        unsigned cc = (unsigned)cell; // < 2^31 cells: 32-bit divisions
+        c[0]        = (int)(cc % (unsigned)a.n[0]);
+        cc /= (unsigned)a.n[0];
+        c[1] = (int)(cc % (unsigned)a.n[1]);
+        c[2] = (int)(cc / (unsigned)a.n[1]);
+      }
+    bool interior = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      {
+        const bool has_lo = c[d] > 0 || ((a.neighbor_mask >> (2 * d)) & 1u);
+        const bool has_hi = c[d] < a.n[d] - 1 || ((a.neighbor_mask >> (2 * d + 1)) & 1u);
+        interior          = interior && has_lo && has_hi;
+      }
+    if (__syncthreads_and(interior || !active ? 1 : 0) && a.n_cells > 0)
+      vanka_fd_body<N1, NB, T, true>(a, c, active);
+    else
+      vanka_fd_body<N1, NB, T, false>(a, c, active);
+  }
+
+  template <int N1, int NB, typename T, bool INTERIOR>
+  __device__ __forceinline__ void vanka_fd_body(const VankaFdArgs<T, N1> &a, const int (&c)[3], bool active)
   {
     using L           = ExchLayout<N1>;
     constexpr int K   = N1 - 1;
@@ -85,17 +128,6 @@ namespace stfem
     const int i    = rem - b * N1;
     const int cb   = tid / N1;
 
-    const long long cell   = (long long)blockIdx.x * a.cells_per_cta + slot;
-    const bool      active = cell < a.n_cells;
-    int             c[3] = {0, 0, 0};
-    if (active)
-      {
-        unsigned cc = (unsigned)cell; // < 2^31 cells: 32-bit divisions
-        c[0]        = (int)(cc % (unsigned)a.n[0]);
-        cc /= (unsigned)a.n[0];
-        c[1] = (int)(cc % (unsigned)a.n[1]);
-        c[2] = (int)(cc / (unsigned)a.n[1]);
-      }
     int  cls[3];
     bool lo_shared[3], hi_shared[3], lo_con[3], hi_con[3];
 #pragma unroll
@@ -133,7 +165,7 @@ namespace stfem
     for (int k = 0; k < N1; ++k)
       {
         T t[N1];
-        fd_apply_cls<T, N1>(a.ST[1], cls[1], x[k], t);
+        fd_apply_cls<T, N1, INTERIOR>(a.ST[1], cls[1], x[k], t);
 #pragma unroll
         for (int q = 0; q < N1; ++q) x[k][q] = t[q];
       }
@@ -145,7 +177,7 @@ namespace stfem
           T in[N1], t[N1];
 #pragma unroll
           for (int k = 0; k < N1; ++k) in[k] = x[k][jy];
-          fd_apply_cls<T, N1>(a.ST[2], cls[2], in, t);
+          fd_apply_cls<T, N1, INTERIOR>(a.ST[2], cls[2], in, t);
 #pragma unroll
           for (int q = 0; q < N1; ++q) pb[(q * N1 + jy) * LS] = t[q];
         }
@@ -165,7 +197,7 @@ namespace stfem
               T        in[N1];
 #pragma unroll
               for (int xx = 0; xx < N1; ++xx) in[xx] = pl[xx];
-              fd_apply_cls<T, N1>(a.ST[0], cls[0], in, t[bb]);
+              fd_apply_cls<T, N1, INTERIOR>(a.ST[0], cls[0], in, t[bb]);
             }
           const T *cm = a.modes + ((size_t)type * N1 * N1 + pos) * N1 * NB * NB;
           T        u[NB][N1];
@@ -185,7 +217,7 @@ namespace stfem
           for (int bb = 0; bb < NB; ++bb)
             {
               T out[N1];
-              fd_apply_cls<T, N1>(a.S[0], cls[0], u[bb], out);
+              fd_apply_cls<T, N1, INTERIOR>(a.S[0], cls[0], u[bb], out);
               T *pl = buf + (slot * NB + bb) * CBS + pos * LS;
 #pragma unroll
               for (int xx = 0; xx < N1; ++xx) pl[xx] = out[xx];
@@ -203,7 +235,7 @@ namespace stfem
           T in[N1], t[N1];
 #pragma unroll
           for (int q = 0; q < N1; ++q) in[q] = pb[(q * N1 + jy) * LS];
-          fd_apply_cls<T, N1>(a.S[2], cls[2], in, t);
+          fd_apply_cls<T, N1, INTERIOR>(a.S[2], cls[2], in, t);
 #pragma unroll
           for (int k = 0; k < N1; ++k) x[k][jy] = t[k];
         }
@@ -216,7 +248,7 @@ namespace stfem
         for (int k = 0; k < N1; ++k)
           {
             T t[N1];
-            fd_apply_cls<T, N1>(a.S[1], cls[1], x[k], t);
+            fd_apply_cls<T, N1, INTERIOR>(a.S[1], cls[1], x[k], t);
             const bool kc = (k == 0 && lo_con[2]) || (k == K && hi_con[2]);
 #pragma unroll
             for (int jy = 0; jy < N1; ++jy)
