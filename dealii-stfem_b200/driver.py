@@ -105,7 +105,7 @@ class HeatWaveProblem:
     """One (refinement, degree) run of the reference's convergence_test lambda."""
 
     def __init__(self, ctx, params, dim, refinement, fe_degree, vertices_fn=None, mg_number_type=capi.F32, space_degree=None,
-                 partition=None):
+                 partition=None, gmres_tolerance=1e-12, abs_tol=1e-12):
         """partition = (proc_grid, coords): this rank owns one brick of the box partition (multi-GPU runs; the context
         must hold a communicator, dist.init_comm).  params describe the GLOBAL mesh."""
         self.ctx, self.p, self.dim = ctx, params, dim
@@ -211,7 +211,7 @@ class HeatWaveProblem:
         conv = p["spaceTimeConvergenceTest"]
         d.rhs_function_id = (F_RHS_WAVE if self.wave else F_RHS_HEAT) if conv else F_ZERO
         d.frequency, d.extrapolate = self.freq, int(p["extrapolate"])
-        d.gmres_tolerance, d.abs_tol, d.max_iterations, d.max_basis_size = 1e-12, 1e-12, 200, 100
+        d.gmres_tolerance, d.abs_tol, d.max_iterations, d.max_basis_size = gmres_tolerance, abs_tol, 200, 100   # time_integrators.h:56-59
         self.ti = C.c_void_p()
         capi.check(capi.lib().stfem_ti_create(C.byref(d), C.byref(self.ti)))
         self.n = self.matrix.n

@@ -281,7 +281,7 @@ def build_levels(p, dim, refinement, fe_degree, tau, mg_dtype, coeff=None, mesh=
 
 
 def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=True, max_steps=None,
-                     solver="fgmres"):
+                     solver="fgmres", reduce=1e-12, abstol=1e-12):
     """One (refinement, degree) run of tests/tp_01.cc:56-725.  Returns the table row."""
     ttype = p["timeType"]
     is_cgp = ttype == ft.CGP
@@ -375,7 +375,7 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
                         rhs[it * nt_dofs + j - 1] += A1[j - 1, j - 1] * fv
         # extrapolate (time_integrators.h:180-190)
         x0 = np.tile(prev_x, (nb, 1)) if p["extrapolate"] else np.zeros_like(x)
-        x, its, _ = stmg.fgmres(Aop, x0, rhs, Mop)
+        x, its, _ = stmg.fgmres(Aop, x0, rhs, Mop, abstol=abstol, reduce=reduce)
         total_it += its
         if wave:
             v = np.zeros_like(x)

@@ -26,7 +26,11 @@ def test_tp01_rows_match_reference_output_and_oracle(ctx, name, deg_idx, ref):
     p = st.parse_parameters(G["params"][name], 2)
     k = p["feDegree"] + deg_idx
     gold = G["tables"][name][deg_idx]["runs"][ref - p["refinement"]]
-    prob = st.HeatWaveProblem(ctx, p, 2, ref, k)
+    # Both sides solve 10x tighter than the reference's ReductionControl(1e-12): two FGMRES runs that stop at 1e-12
+    # differ by O(1e-14) in the solution, which is the size of the 1e-10 relative bar on the smallest errors (1e-4);
+    # the algebraic noise must be below the quantity compared.  Goldens and iteration parity are unaffected.
+    TOL = dict(gmres_tolerance=1e-13, abs_tol=1e-13)
+    prob = st.HeatWaveProblem(ctx, p, 2, ref, k, **TOL)
     row = prob.run()
     prob.close()
     assert row["cells"] == gold["cells"] and row["s_dofs"] == gold["s_dofs"] and row["t_dofs"] == gold["t_dofs"]
@@ -34,7 +38,7 @@ def test_tp01_rows_match_reference_output_and_oracle(ctx, name, deg_idx, ref):
     assert _close6(row["l2"], gold["l2"]), (row["l2"], gold["l2"])
     assert _close6(row["linf"], gold["linf"]), (row["linf"], gold["linf"])
     assert _close6(row["h1"], gold["h1"]), (row["h1"], gold["h1"])
-    o = tp_01.convergence_test(tp_01.parse_parameters(G["params"][name], 2), 2, ref, k, mg_dtype=np.float32)
+    o = tp_01.convergence_test(tp_01.parse_parameters(G["params"][name], 2), 2, ref, k, mg_dtype=np.float32, reduce=1e-13, abstol=1e-13)
     assert row["levels"] == o["levels"]
     assert abs(row["l2"] - o["l2"]) <= 1e-10 * o["l2"], (row["l2"], o["l2"])
     assert abs(row["h1"] - o["h1"]) <= 1e-9 * o["h1"]
@@ -60,9 +64,9 @@ def test_3d_heat_short_run_matches_oracle(ctx):
     import dealii_stfem_b200 as st
     pj = dict(G["params"]["tf03"])
     p = st.parse_parameters(pj, 3)
-    prob = st.HeatWaveProblem(ctx, p, 3, 2, 1)
+    prob = st.HeatWaveProblem(ctx, p, 3, 2, 1, gmres_tolerance=1e-13, abs_tol=1e-13)
     row = prob.run(max_steps=2)
     prob.close()
-    o = tp_01.convergence_test(tp_01.parse_parameters(pj, 3), 3, 2, 1, mg_dtype=np.float32, max_steps=2)
+    o = tp_01.convergence_test(tp_01.parse_parameters(pj, 3), 3, 2, 1, mg_dtype=np.float32, max_steps=2, reduce=1e-13, abstol=1e-13)
     assert abs(row["l2"] - o["l2"]) <= 1e-10 * o["l2"]
     assert abs(row["iterations"] - o["iterations"]) <= 2
