@@ -100,3 +100,75 @@ def test_box_partition_reproduces_global_operator(world, dim, n_global, k):
         err, derr = results[r]
         assert err < 1e-13, (r, err)
         assert derr < 1e-13, (r, derr)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Partitioned multigrid transfers (csrc/mg.cuh restrict_level / prolongate_level): the global restriction must equal
+#   sum over ranks of [ local restriction of the local residual with interface entries weighted by 1/multiplicity ]
+# placed at the rank's brick of the coarse level and summed (halo sum on partitioned coarse levels, all-reduce of the
+# global coarse vector when the coarse level is agglomerated), and the global prolongation restricted to a brick
+# must equal the local prolongation of the brick of the coarse vector.
+def _transfer_worker(rank, world, port, dim, n_fine, k, results):
+    import dealii_stfem_b200 as st
+    from oracle import spatial as S, stmg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grid = st.dist.proc_grid_for(world, dim)
+    coords = st.dist.coords_of(rank, grid)
+    lower, upper = [0.0] * dim, [1.0] * dim
+    n_coarse = [n // 2 for n in n_fine]
+    # global levels and the global transfer (every rank builds them; small)
+    gf = S.Space(S.Mesh(dim, n_fine, 0), k)
+    gc = S.Space(S.Mesh(dim, n_coarse, 0), k)
+    P = stmg.space_prolongation(gc, gf, np.float64)
+    rng = np.random.RandomState(5)
+    r_f = rng.uniform(-1, 1, gf.n_dofs) * (~gf.constrained)
+    x_c = rng.uniform(-1, 1, gc.n_dofs) * (~gc.constrained)
+    R_ref = P.T @ r_f
+    Px_ref = P @ x_c
+    # local bricks
+    nlf, off_f, llo, lup, mask = st.dist.partition_brick(n_fine, lower, upper, grid, coords)
+    nlc, off_c, _, _, _ = st.dist.partition_brick(n_coarse, lower, upper, grid, coords)
+    lf = S.Space(S.Mesh(dim, nlf, 0, lower=llo, upper=lup), k, dirichlet_faces=mask)
+    lc = S.Space(S.Mesh(dim, nlc, 0, lower=llo, upper=lup), k, dirichlet_faces=mask)
+    Pl = stmg.space_prolongation(lc, lf, np.float64)
+
+    def brick(arr, space_g, space_l, off):
+        sl = tuple(slice(k * off[dim - 1 - ax], k * off[dim - 1 - ax] + space_l.np[dim - 1 - ax]) for ax in range(dim))
+        return arr.reshape(space_g.np[::-1])[sl]
+
+    # restriction: weight interface entries, restrict locally, add the bricks into the global coarse vector
+    rl = brick(r_f, gf, lf, off_f).copy()
+    for d in range(dim):
+        ax = dim - 1 - d
+        for s, has in ((0, coords[d] > 0), (-1, coords[d] < grid[d] - 1)):
+            if has:
+                idx = [slice(None)] * dim
+                idx[ax] = s
+                rl[tuple(idx)] *= 0.5
+    Rl = (Pl.T @ rl.reshape(-1)).reshape(lc.np[::-1])
+    glob = np.zeros(gc.np[::-1])
+    sl_c = tuple(slice(k * off_c[dim - 1 - ax], k * off_c[dim - 1 - ax] + lc.np[dim - 1 - ax]) for ax in range(dim))
+    glob[sl_c] += Rl
+    t = torch.from_numpy(glob)
+    dist.all_reduce(t)                                   # = agglomerated switch; = halo sums on a partitioned level
+    err_r = np.abs(t.numpy().reshape(-1) - R_ref).max() / np.abs(R_ref).max()
+    # prolongation: brick of the coarse vector, local prolongation == brick of the global prolongation
+    xl = brick(x_c, gc, lc, off_c).reshape(-1)
+    err_p = np.abs((Pl @ xl) - brick(Px_ref, gf, lf, off_f).reshape(-1)).max() / np.abs(Px_ref).max()
+    results[rank] = (err_r, err_p)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dim,n_fine,k", [(2, 2, [8, 4], 2), (4, 2, [4, 8], 1), (4, 3, [4, 4, 4], 2), (2, 3, [4, 2, 2], 3)])
+def test_partitioned_transfers_reproduce_global_transfers(world, dim, n_fine, k):
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = _free_port()
+    mp.spawn(_transfer_worker, args=(world, port, dim, n_fine, k, results), nprocs=world, join=True)
+    assert len(results) == world
+    for r in range(world):
+        err_r, err_p = results[r]
+        assert err_r < 1e-13, (r, err_r)
+        assert err_p < 1e-13, (r, err_p)
