@@ -281,8 +281,9 @@ def build_levels(p, dim, refinement, fe_degree, tau, mg_dtype, coeff=None, mesh=
 
 
 def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=True, max_steps=None,
-                     solver="fgmres", reduce=1e-12, abstol=1e-12):
-    """One (refinement, degree) run of tests/tp_01.cc:56-725.  Returns the table row."""
+                     solver="fgmres", reduce=1e-12, abstol=1e-12, tau=None):
+    """One (refinement, degree) run of tests/tp_01.cc:56-725.  Returns the table row.
+    tau: overrides the time step size of tp_01.cc:106-109 (tests/transfer_01.cc:429 uses 2^-(i+1) on a fixed mesh)."""
     ttype = p["timeType"]
     is_cgp = ttype == ft.CGP
     nts = p["nTimestepsAtOnce"]
@@ -298,7 +299,8 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
     spc_step = diam / math.sqrt(dim)
     time, end_time = 0.0, p["endTime"]
     n_steps = int((end_time - time) / spc_step)
-    tau = (end_time - time) * 2.0 ** (-(refinement + 1)) / n_steps
+    if tau is None:
+        tau = (end_time - time) * 2.0 ** (-(refinement + 1)) / n_steps
     wave = p["problemType"] == "wave"
     coeff = None
     if not p["spaceTimeConvergenceTest"]:

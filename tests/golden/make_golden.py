@@ -10,6 +10,9 @@ Inputs (read-only, never copied verbatim):
   tests/tp04.cc             get_mg_sequence / smoother-type expectations
                             (exact integer pins, stated in the test source)  -> tp04.json
   tests/tp_01.output        cells / dofs / iterations / error tables -> tp_01.json
+  tests/transfer_01.output  error tables of the (stale) time-multigrid test: 2x2 cells, tau = 2^-(i+1),
+                            i = 2..4, DG(j) / CGP(j+1), j = 1..3, 1 and 2 time steps at once
+                            (tests/transfer_01.cc:395-396, 429, 731-737, 772-776) -> transfer_01.json
 
 A printed matrix entry is '%7.2f', blank when |x| < 0.01
 (reference tests/tp_02.cc:19-27); blank entries are stored as null.
@@ -197,11 +200,41 @@ def golden_tp_01():
     return {"tables": out, "params": params}
 
 
+def golden_transfer_01():
+    """Tables in the order main() runs them (tests/transfer_01.cc:772-776): DG, CGP with one time step per solve,
+    then DG, CGP with two; inside each, degree index j = 1..3 and i = 2..4 (tau = 2^-(i+1))."""
+    txt = open(os.path.join(REF, "tests/transfer_01.output")).read().splitlines()
+    tables = []
+    i = 0
+    while i < len(txt):
+        if txt[i].startswith("cells s-dofs"):
+            rows = []
+            j = i + 1
+            while j < len(txt) and txt[j].strip():
+                vals = [x for x in txt[j].split() if x != "-"]
+                cells, sd, td, std = (int(v) for v in vals[:4])
+                errs = [float(v) for v in vals[4:] if "e" in v]
+                rows.append(dict(cells=cells, s_dofs=sd, t_dofs=td, st_dofs=std, linf=errs[0], l2=errs[1], h1=errs[2]))
+                j += 1
+            tables.append(rows)
+            i = j
+            continue
+        i += 1
+    assert len(tables) == 12 and all(len(t) == 3 for t in tables), [len(t) for t in tables]
+    out = []
+    for s, (ttype, nts) in enumerate((("DG", 1), ("CGP", 1), ("DG", 2), ("CGP", 2))):
+        for j in range(1, 4):
+            rows = tables[3 * s + j - 1]
+            out.append(dict(timeType=ttype, nTimestepsAtOnce=nts, feDegree=j if ttype == "DG" else j + 1,
+                            runs=[dict(r, tau_exponent=-(i + 1)) for i, r in zip(range(2, 5), rows)]))
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference tree not found at %s (fixtures are committed; nothing to do)" % REF)
     for name, fn in (("tp_02", golden_tp_02), ("transfer_02", golden_transfer_02),
-                     ("tp04", golden_tp04), ("tp_01", golden_tp_01)):
+                     ("tp04", golden_tp04), ("tp_01", golden_tp_01), ("transfer_01", golden_transfer_01)):
         data = fn()
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(data, f, indent=0, separators=(",", ":"))

@@ -21,6 +21,10 @@ def _close6(a, b):
 CASES = [("tf03", 0, 2), ("tf03", 0, 3), ("tf03", 1, 2), ("tf04", 0, 2), ("tf04", 0, 3), ("tf07", 0, 2),
          ("tf07", 0, 3), ("tf08", 0, 2), ("tf08", 0, 3), ("tf01", 0, 2), ("tf02", 0, 2), ("tf05", 0, 2),
          ("tf06", 0, 2)]
+# the higher-degree tables (k = feDegree + 1, + 2) of every configuration at the first refinement: cheap, and they pin
+# the time weights / error functional for cG(2..4) and dG(1..3) through the full driver
+CASES += [(n, d, 2) for n in ("tf01", "tf02", "tf03", "tf04", "tf05", "tf06", "tf07", "tf08") for d in (1, 2)
+          if (n, d, 2) not in CASES]
 
 
 @pytest.mark.parametrize("name,deg_idx,ref", CASES)
@@ -45,3 +49,22 @@ def test_iteration_counts_soft_pin(name, ref):
     gold = G["tables"][name][0]["runs"][ref - p["refinement"]]
     r = tp_01.convergence_test(p, 2, ref, p["feDegree"], mg_dtype=np.float32)
     assert abs(r["iterations"] - gold["iterations"]) <= r["timesteps"], (r["iterations"], gold["iterations"])
+
+
+# tests/transfer_01.output: the reference's (stale) time-multigrid test still pins the space-time errors of the heat
+# problem on a fixed 2 x 2 mesh (hyper_cube, refine_global(1)) for tau = 2^-3, 2^-4, 2^-5, DG(1..3) and CGP(2..4), one and
+# two time steps per solve (tests/transfer_01.cc:395-396, 429, 731-737).  Errors do not depend on the preconditioner.
+T01 = load("transfer_01")
+
+
+@pytest.mark.parametrize("case", range(len(T01)))
+def test_errors_match_transfer_01_output(case):
+    c = T01[case]
+    p = tp_01.parse_parameters({"timeType": c["timeType"], "problemType": "heat",
+                                "nTimestepsAtOnce": str(c["nTimestepsAtOnce"])}, 2)
+    for gold in c["runs"]:
+        r = tp_01.convergence_test(p, 2, 1, c["feDegree"], use_mg=False, tau=2.0 ** gold["tau_exponent"])
+        assert (r["cells"], r["s_dofs"], r["t_dofs"]) == (gold["cells"], gold["s_dofs"], gold["t_dofs"])
+        assert r["timesteps"] * r["s_dofs"] * r["t_dofs"] == gold["st_dofs"]
+        for key in ("linf", "l2", "h1"):
+            assert _close6(r[key], gold[key]), (key, r[key], gold[key])
