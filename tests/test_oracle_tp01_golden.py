@@ -39,7 +39,7 @@ def test_errors_match_reference_output(name, deg_idx, ref):
     assert _close6(r["linf"], gold["linf"]), (r["linf"], gold["linf"])
     assert _close6(r["h1"], gold["h1"]), (r["h1"], gold["h1"])
     # converged solves: FGMRES(100) with ReductionControl(200, 1e-12, 1e-12)
-    assert r["iterations"] < 30 * r["timesteps"]
+    assert r["iterations"] < 40 * r["timesteps"]
 
 
 @pytest.mark.parametrize("name,ref", [("tf03", 3), ("tf03", 4), ("tf07", 3), ("tf07", 4), ("tf05", 3)])
