@@ -9,6 +9,7 @@ import numpy as np
 
 from . import capi
 from . import fe_time_host as ft
+from . import problem_host
 
 _vp, _vpp, _dp = C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double)
 
@@ -48,6 +49,10 @@ def default_parameters(dim=2):
         "subdivisions": [1] * dim, "distortGrid": 0.0, "distortCoeff": 0.0, "endTime": 1.0, "smoother": "relaxation",
         "smoothingSteps": 1, "smoothingRange": 1.0, "relaxation": 0.0, "coarseGridSmootherType": "Smoother",
         "restrictIsTransposeProlongate": True, "variable": True, "smoothingEigCgNIterations": 20,
+        "sourcePoint": [0.5] * dim,  # parameters.h:79: midpoint of the DEFAULT box (member initialiser order)
+        "functionalFile": "functionals.txt", "doOutput": False, "printTiming": False,
+        # accepted and ignored like in tests/tp_01.cc (unused there): relativeTolerance, timeRefineOffset, deltaTime
+        "relativeTolerance": 1.0e-12, "timeRefineOffset": 1, "deltaTime": 0.0,
         "agglomerateBelow": 16,     # multi-GPU only (not a reference key): see HeatWaveProblem
     }
 
@@ -158,6 +163,7 @@ class HeatWaveProblem:
         fetw = level_time_weights(self.ttype, self.tau, self.nts, self.mg_type_level, self.poly_time, self.wave)
         # ---- meshes per refinement (geometric coarsening sequence: every second vertex)
         self.meshes = {}
+        mesh_desc = {}              # refinement -> (n_cells, lower, upper, vertices) of the (local) mesh, for host set-up helpers
         fine_vertices = vertices_fn(self.n_cells) if vertices_fn is not None else None
         for rf in sorted(set(level_ref)):
             n = [s * (1 << rf) for s in sub]
@@ -172,14 +178,18 @@ class HeatWaveProblem:
                 min(nn // g for nn, g in zip(n, partition[0])) < self.p.get("agglomerateBelow", 16)
             if partition is None or agglomerate:
                 self.meshes[rf] = capi.Mesh(ctx, n, lower=lo, upper=up, vertices=v)
+                mesh_desc[rf] = (n, lo, up, v)
             else:
                 from . import dist
                 assert v is None, "partitioned runs support Cartesian meshes only"
                 n_loc, _, llo, lup, mask = dist.partition_brick(n, lo, up, partition[0], partition[1])
                 self.meshes[rf] = capi.Mesh(ctx, n_loc, lower=llo, upper=lup, dirichlet_faces=mask)
                 dist.set_partition(self.meshes[rf], partition[0], partition[1])
-        self.level_ops = [capi.Operator(self.meshes[level_ref[l]], level_degree[l], fetw[l][0], fetw[l][1], number_type=mg_number_type)
-                          for l in range(nl)]
+                mesh_desc[rf] = (list(n_loc), list(llo), list(lup), None)
+        self.mesh_desc = mesh_desc
+        self._coeff_cache = {}
+        self.level_ops = [capi.Operator(self.meshes[level_ref[l]], level_degree[l], fetw[l][0], fetw[l][1], number_type=mg_number_type,
+                                        **self._laplace_coefficient(level_ref[l], level_degree[l])) for l in range(nl)]
         self.mg = capi.Multigrid(ctx, self.level_ops, self.mg_type_level, self.ptypes, self.ttype, self.nts, self.poly_time,
                                  smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
                                  eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
@@ -193,13 +203,13 @@ class HeatWaveProblem:
         self.rhs_matrix_v = None
         if self.wave:
             lhs_uK, lhs_uM, rhs_uK, rhs_uM, rhs_vM = ft.get_fe_time_weights_wave(self.ttype, A1, B1, G1, Z1, self.nts)
-            self.rhs_matrix_v = capi.Operator(fmesh, self.k, zero, rhs_vM)
+            self.rhs_matrix_v = capi.Operator(fmesh, self.k, zero, rhs_vM, **self._laplace_coefficient(refinement, self.k))
         else:
             lhs_uK, lhs_uM = A, B
             rhs_uK = G if self.is_cgp else zero
             rhs_uM = Z if self.is_cgp else G
-        self.matrix = capi.Operator(fmesh, self.k, lhs_uK, lhs_uM)
-        self.rhs_matrix = capi.Operator(fmesh, self.k, rhs_uK, rhs_uM)
+        self.matrix = capi.Operator(fmesh, self.k, lhs_uK, lhs_uM, **self._laplace_coefficient(refinement, self.k))
+        self.rhs_matrix = capi.Operator(fmesh, self.k, rhs_uK, rhs_uM, **self._laplace_coefficient(refinement, self.k))
         self._w = [np.ascontiguousarray(m, np.float64) for m in (A1, B1, G1, Z1)]
         d = TiDesc()
         d.time_type = 1 if self.is_cgp else 2
@@ -223,14 +233,40 @@ class HeatWaveProblem:
         self.prev_v = capi.DeviceBlockVector(ctx, 1, self.n) if self.wave else None
         self.x.zero()
         L = capi.lib()
-        capi.check(L.stfem_interpolate(fmesh.h, self.k, F_EXACT, self.freq, 0.0, self.x.ptrs[nbv - 1]))      # tp_01.cc:551
         if self.wave:
             self.v.zero()
-            capi.check(L.stfem_interpolate(fmesh.h, self.k, F_EXACT_V, self.freq, 0.0, self.v.ptrs[nbv - 1]))
+        if conv:
+            capi.check(L.stfem_interpolate(fmesh.h, self.k, F_EXACT, self.freq, 0.0, self.x.ptrs[nbv - 1]))      # tp_01.cc:551
+            if self.wave:
+                capi.check(L.stfem_interpolate(fmesh.h, self.k, F_EXACT_V, self.freq, 0.0, self.v.ptrs[nbv - 1]))
+        else:
+            # tp_01.cc:374-381: u(0) = C-infinity bump of radius 1e-2 around sourcePoint, v(0) = 0, no source term
+            n_, lo_, up_, v_ = mesh_desc[refinement]
+            u0 = problem_host.cutoff_cinfty_interpolate(n_, lo_, up_, self.k, p["sourcePoint"], vertices=v_)
+            capi.check(L.stfem_dev_upload(ctx.h, self.x.ptrs[nbv - 1], u0.ctypes.data, u0.nbytes))
+            ctx.synchronize()
         self.time = 0.0
         self.total_iterations = 0
         self.n_solves = 0
         self.err = np.array([0.0, -1.0, 0.0])
+
+    def _laplace_coefficient(self, rf, degree):
+        """K_mf.evaluate_coefficient(coeff) when !spaceTimeConvergenceTest (tp_01.cc:118-119, 279-280): keyword arguments
+        for capi.Operator.  On Cartesian meshes whose cells do not straddle a coefficient jump the table is constant per
+        cell and the per-cell path (Cartesian kernel) is taken."""
+        p = self.p
+        if p["spaceTimeConvergenceTest"]:
+            return {}
+        key = (rf, degree)
+        if key not in self._coeff_cache:
+            n, lo, up, v = self.mesh_desc[rf]
+            cq = problem_host.coefficient_at_qpoints(n, lo, up, degree, p["subdivisions"], p["hyperRectLowerLeft"],
+                                                     p["hyperRectUpperRight"], p["distortCoeff"], vertices=v)
+            if v is None and np.all(cq == cq[:, :1]):
+                self._coeff_cache[key] = {"laplace_coeff_cell": np.ascontiguousarray(cq[:, 0])}
+            else:
+                self._coeff_cache[key] = {"laplace_coeff_q": cq}
+        return self._coeff_cache[key]
 
     def _copy(self, dst_ptr, src_ptr):
         # device-to-device copy of one spatial vector on the library stream

@@ -276,6 +276,25 @@ int stfem_precondition_stmg_types(const char *seq, int coarsening_type, int time
 /* 1D rules on [0,1]: kind 0 QGauss, 1 QGaussLobatto, 2 QGaussRadau(right) */
 int stfem_quadrature_rule(int kind, int n, double *x, double *w);
 
+/* ---- host-side problem data of the "practical" runs (spaceTimeConvergenceTest = false, tests/tp_01.cc:118-119,
+ *      279-280, 374-381; tests/json/practical01.json).  Set-up work, no GPU.  Meshes are described like in
+ *      stfem_mesh_create (n_cells, box, optional lexicographic vertices). ---- */
+/* Coefficient<dim>'s per-coarse-cell factors (include/operators.h:905-921): prod(subdivisions) values
+ * U(1-dc, 1+dc) from boost::mt19937(default_seed), one 32-bit draw each, in Table order (last index fastest) */
+int stfem_coefficient_distortion(int dim, const int *subdivisions, double distort_coeff, double *table);
+/* MatrixFreeOperator::evaluate_coefficient(Coefficient<dim>) (operators.h:1060-1087, 870-965): the coefficient at the
+ * QGauss(degree+1) points of every cell, out[n_cells * (degree+1)^dim] in the layout stfem_op_desc::laplace_coeff_q
+ * takes.  c123: NULL = {1, 9, 16}.  subdivisions / coeff_lower / coeff_upper: Parameters::subdivisions and
+ * hyperrect corners (the table's grid, operators.h:922-925); ignored when distort_coeff == 0 */
+int stfem_coefficient_at_qpoints(int dim, const int *n_cells, const double *lower, const double *upper,
+                                 const double *vertices, int degree, const int *subdivisions, const double *coeff_lower,
+                                 const double *coeff_upper, double distort_coeff, const double *c123, double *out);
+/* VectorTools::interpolate of Functions::CutOffFunctionCinfty<dim>(radius, center, 1, invalid, integrate_to_one)
+ * (tests/tp_01.cc:376-378, 393-400, 551) on the FE_Q(degree) support points: out[N], lexicographic */
+int stfem_cutoff_cinfty_interpolate(int dim, const int *n_cells, const double *lower, const double *upper,
+                                    const double *vertices, int degree, double radius, const double *center,
+                                    int integrate_to_one, double *out);
+
 #ifdef __cplusplus
 }
 #endif

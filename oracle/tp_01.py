@@ -33,12 +33,14 @@ def default_parameters(dim=2):
         "endTime": 1.0, "smoother": "relaxation", "smoothingSteps": 1, "smoothingRange": 1.0,
         "relaxation": 0.0, "coarseGridSmootherType": "Smoother", "restrictIsTransposeProlongate": True,
         "variable": True, "smoothingEigCgNIterations": 20,
+        "sourcePoint": None,         # parameters.h:79: midpoint of the DEFAULT box (member initialiser order)
     }
 
 
 def parse_parameters(json_dict, dim=2):
     """Parameters<dim>::parse (parameters.h:85-176): strings -> typed values + derived defaults."""
     p = default_parameters(dim)
+    p["sourcePoint"] = [0.5] * dim
     for k, v in json_dict.items():
         if k not in p:
             continue
@@ -103,6 +105,27 @@ def rhs_wave(pts, t, f=1.0):
     d = pts.shape[-1]
     v = (2.0 ** d) * (PI * f) ** 2 * math.sin(2 * PI * f * t)
     return v * np.prod(np.sin(2 * PI * f * pts), axis=-1)
+
+
+# Integral of e * exp(-1/(1-|x|^2)) over the unit ball in 1, 2, 3 dimensions (deal.II function_lib_cutoff.cc,
+# integral_Cinfty; re-derived here by quadrature to all printed digits, see tests/test_problem_host.py)
+INTEGRAL_CINFTY = (1.20690032243787617533623799633, 1.26811216112759608094632335664, 1.1990039070192139033798473858)
+
+
+def cutoff_cinfty(pts, center, radius=1.0e-2, integrate_to_one=True):
+    """Functions::CutOffFunctionCinfty<dim>(radius, center, 1, invalid, integrate_to_one)::value (deal.II 9.6
+    base/function_lib_cutoff.cc; constructed at tests/tp_01.cc:376-378): rescaling * e * exp(-r^2 / (r^2 - d^2)) for
+    d < r (0 where the exponent is below -50), rescaling = 1 / (integral_Cinfty[dim-1] * r^dim).
+    Third-party algorithm (deal.II is not vendored): parity unpinned by the reference's own outputs."""
+    dim = pts.shape[-1]
+    d = np.sqrt(np.sum((pts - np.asarray(center, float)) ** 2, axis=-1))
+    r = radius
+    resc = 1.0 / (INTEGRAL_CINFTY[dim - 1] * r ** dim) if integrate_to_one else 1.0
+    out = np.zeros(d.shape)
+    inside = d < r
+    e = -r * r / (r * r - d[inside] ** 2)
+    out[inside] = np.where(e < -50, 0.0, resc * math.e * np.exp(e))
+    return out
 
 
 # ----------------------------------------------------------------------------- spatial helpers
@@ -281,7 +304,7 @@ def build_levels(p, dim, refinement, fe_degree, tau, mg_dtype, coeff=None, mesh=
 
 
 def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=True, max_steps=None,
-                     solver="fgmres", reduce=1e-12, abstol=1e-12, tau=None):
+                     solver="fgmres", reduce=1e-12, abstol=1e-12, tau=None, return_state=False):
     """One (refinement, degree) run of tests/tp_01.cc:56-725.  Returns the table row.
     tau: overrides the time step size of tp_01.cc:106-109 (tests/transfer_01.cc:429 uses 2^-(i+1) on a fixed mesh)."""
     ttype = p["timeType"]
@@ -340,9 +363,14 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
 
     x = np.zeros((nb, space.n_dofs))
     v = np.zeros((nb, space.n_dofs))
-    x[-1] = interpolate(space, lambda pts: exact_solution(pts, 0.0, f))
+    if p["spaceTimeConvergenceTest"]:
+        x[-1] = interpolate(space, lambda pts: exact_solution(pts, 0.0, f))
+    else:
+        # tp_01.cc:374-381, 551-553: initial value = C-infinity bump of radius 1e-2 around sourcePoint, v(0) = 0, f = 0
+        x[-1] = interpolate(space, lambda pts: cutoff_cinfty(pts, p["sourcePoint"]))
     if wave:
-        v[-1] = interpolate(space, lambda pts: exact_velocity(pts, 0.0, f))
+        if p["spaceTimeConvergenceTest"]:
+            v[-1] = interpolate(space, lambda pts: exact_velocity(pts, 0.0, f))
         Ainv = np.linalg.inv(A1)
         AixB, AixG, AixZ = Ainv @ B1, Ainv @ G1, Ainv @ Z1
         if ttype == ft.DG:
@@ -353,6 +381,7 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
     l8 = -1.0
     total_it = 0
     n_solves = 0
+    its_per_solve = []
     Aop = fine.vmult
     Mop = gmg.vmult if gmg is not None else (lambda r: r.copy())
     while time < end_time:
@@ -379,6 +408,7 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
         x0 = np.tile(prev_x, (nb, 1)) if p["extrapolate"] else np.zeros_like(x)
         x, its, _ = stmg.fgmres(Aop, x0, rhs, Mop, abstol=abstol, reduce=reduce)
         total_it += its
+        its_per_solve.append(its)
         if wave:
             v = np.zeros_like(x)
             for it in range(nts):
@@ -400,6 +430,7 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
         time += nts * tau
         if max_steps is not None and n_solves >= max_steps:
             break
-    return dict(cells=mesh.n_cells, s_dofs=space.n_dofs, t_dofs=nb, iterations=total_it, timesteps=n_solves,
+    state = dict(x=x, v=v if wave else None, iterations_per_solve=its_per_solve) if return_state else {}
+    return dict(state, cells=mesh.n_cells, s_dofs=space.n_dofs, t_dofs=nb, iterations=total_it, timesteps=n_solves,
                 linf=l8, l2=math.sqrt(l2), h1=math.sqrt(h1), tau=tau,
                 levels="".join(lv["mg_type_level"]) if lv else "", n_levels=(len(lv["mg_type_level"]) + 1) if lv else 0)
