@@ -200,6 +200,27 @@ def golden_tp_01():
     return {"tables": out, "params": params}
 
 
+def golden_tp_01_text():
+    """The printed text of tests/tp_01.output, one block per parameter file (each block ends after its "Iteration count
+    table"): fixture for the product's output formatter (dealii-stfem_b200/tp_01.py)."""
+    txt = open(os.path.join(REF, "tests/tp_01.output")).read().splitlines()
+    names = ["tf01", "tf02", "tf03", "tf04", "tf05", "tf06", "tf07", "tf08"]
+    blocks, cur, i = [], [], 0
+    while i < len(txt):
+        cur.append(txt[i])
+        if txt[i].startswith("Iteration count table"):
+            i += 1
+            while i < len(txt) and txt[i].strip():
+                cur.append(txt[i])
+                i += 1
+            cur.append("")
+            blocks.append(cur)
+            cur = []
+        i += 1
+    assert len(blocks) == 8, len(blocks)
+    return dict(zip(names, blocks))
+
+
 def golden_transfer_01():
     """Tables in the order main() runs them (tests/transfer_01.cc:772-776): DG, CGP with one time step per solve,
     then DG, CGP with two; inside each, degree index j = 1..3 and i = 2..4 (tau = 2^-(i+1))."""
@@ -234,7 +255,7 @@ def main():
     if not os.path.isdir(REF):
         sys.exit("reference tree not found at %s (fixtures are committed; nothing to do)" % REF)
     for name, fn in (("tp_02", golden_tp_02), ("transfer_02", golden_transfer_02),
-                     ("tp04", golden_tp04), ("tp_01", golden_tp_01), ("transfer_01", golden_transfer_01)):
+                     ("tp04", golden_tp04), ("tp_01", golden_tp_01), ("transfer_01", golden_transfer_01), ("tp_01_text", golden_tp_01_text)):
         data = fn()
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(data, f, indent=0, separators=(",", ":"))

@@ -66,3 +66,26 @@ def test_practical_2d_perturbed_mesh_per_q_coefficient(ctx):
     # about 70 iterations per solve (rough data on a perturbed mesh): +-3
     for a, b in zip(its, o["iterations_per_solve"]):
         assert abs(a - b) <= 3, (its, o["iterations_per_solve"])
+
+
+def test_tp01_front_end_prints_reference_tables(ctx):
+    """python -m dealii_stfem_b200.tp_01 --file tf03.json: the printed convergence table of the first degree agrees with
+    tests/tp_01.output in every column that does not depend on the (stale) iteration totals."""
+    import io
+
+    from dealii_stfem_b200 import tp_01 as front
+    from golden_util import load
+    G, T = load("tp_01"), load("tp_01_text")
+    pj = dict(G["params"]["tf03"], nDegCycles="1", nRefCycles="2")
+    out = io.StringIO()
+    rows = front.run(pj, 2, out=out, ctx=ctx)
+    got = out.getvalue().split("\n")
+    want = T["tf03"]
+    i, j = got.index("Convergence table k=1"), want.index("Convergence table k=1")
+    assert got[i + 1].split() == want[j + 1].split()                      # header
+    for r in (2, 3):
+        g, w = got[i + r].split(), want[j + r].split()
+        assert g[:4] == w[:4] and g[5:] == w[5:], (got[i + r], want[j + r])
+    assert got[0] == ":: Number of active cells: 16" and got[2].startswith(":: Min Level 0  Max Level ")
+    assert "Iteration count table" in got
+    assert len(rows) == 1 and len(rows[0]) == 2
