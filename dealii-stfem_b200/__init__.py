@@ -9,5 +9,5 @@ problem_host.py  coefficient tables / cut-off initial value of the practical run
 Import as `dealii_stfem_b200` (the hyphenated directory is re-exported by that shim).
 """
 from .capi import *  # noqa: F401,F403
-from . import capi, dist, driver, fe_time_host, problem_host, tp_01  # noqa: F401
+from . import capi, dist, driver, fe_time_host, problem_host  # noqa: F401
 from .driver import HeatWaveProblem, parse_parameters  # noqa: F401

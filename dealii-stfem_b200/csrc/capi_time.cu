@@ -364,3 +364,196 @@ int stfem_evaluate_error(stfem_mesh_t mesh, int degree, int time_type, int time_
 }
 
 } // extern "C"
+
+// ---- point evaluation functionals (tests/tp_01.cc:455-481, 584-635: Utilities::MPI::RemotePointEvaluation +
+//      FEPointEvaluation of every time DoF at a few fixed points).  The host locates each point (cell + reference
+//      coordinates, Newton inversion of the MappingQ1 map on perturbed meshes) and tabulates the (degree+1)^dim basis
+//      values and DoF indices; one warp per (block, point) gathers and reduces on the device.
+namespace
+{
+  struct PointPtrs { const double *p[STFEM_MAX_BLOCKS]; };
+
+  __global__ void k_point_eval(int n_items, int n_points, int nc, PointPtrs blocks, const long long *__restrict__ idx,
+                               const double *__restrict__ w, double *__restrict__ out)
+  {
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n_items) return; // whole warps leave together
+    const int     b = item / n_points, p = item - b * n_points;
+    const double *u = blocks.p[b];
+    double        s = 0.0;
+    for (int i = lane; i < nc; i += 32) s += w[(long long)p * nc + i] * u[idx[(long long)p * nc + i]];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[item] = s;
+  }
+
+  // reference coordinates of x in cell c of a MappingQ1 mesh; false if Newton does not converge inside the cell
+  bool invert_q1(const stfem_mesh *m, const int *c, const double *x, double *xi)
+  {
+    const int dim = m->dim;
+    for (int a = 0; a < dim; ++a) xi[a] = 0.5;
+    for (int it = 0; it < 30; ++it)
+      {
+        double f[3] = {0, 0, 0}, J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int v = 0; v < (1 << dim); ++v)
+          {
+            const int vb[3] = {v & 1, (v >> 1) & 1, (v >> 2) & 1};
+            long long vid   = (long long)(c[0] + vb[0]) + (long long)(m->n[0] + 1) * (c[1] + vb[1]);
+            if (dim == 3) vid += (long long)(m->n[0] + 1) * (m->n[1] + 1) * (c[2] + vb[2]);
+            double N[3] = {1, 1, 1}, dN[3] = {0, 0, 0};
+            for (int a = 0; a < dim; ++a)
+              {
+                N[a]  = vb[a] ? xi[a] : 1.0 - xi[a];
+                dN[a] = vb[a] ? 1.0 : -1.0;
+              }
+            const double sh = N[0] * N[1] * N[2];
+            for (int a = 0; a < dim; ++a) f[a] += m->h_vertices[vid * dim + a] * sh;
+            for (int b = 0; b < dim; ++b)
+              {
+                double d = dN[b];
+                for (int e = 0; e < dim; ++e)
+                  if (e != b) d *= N[e];
+                for (int a = 0; a < dim; ++a) J[a][b] += m->h_vertices[vid * dim + a] * d;
+              }
+          }
+        double r[3] = {0, 0, 0}, nrm = 0;
+        for (int a = 0; a < dim; ++a)
+          {
+            r[a] = x[a] - f[a];
+            nrm += r[a] * r[a];
+          }
+        double dx[3] = {0, 0, 0};
+        if (dim == 2)
+          {
+            const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            dx[0]            = (J[1][1] * r[0] - J[0][1] * r[1]) / det;
+            dx[1]            = (-J[1][0] * r[0] + J[0][0] * r[1]) / det;
+          }
+        else
+          {
+            const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                         c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+            // Cramer's rule, column by column
+            auto det3 = [](const double A[3][3]) {
+              return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                     A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+            };
+            for (int col = 0; col < 3; ++col)
+              {
+                double A[3][3];
+                for (int a = 0; a < 3; ++a)
+                  for (int b = 0; b < 3; ++b) A[a][b] = b == col ? r[a] : J[a][b];
+                dx[col] = det3(A) / det;
+              }
+          }
+        for (int a = 0; a < dim; ++a) xi[a] += dx[a];
+        if (std::sqrt(nrm) < 1e-14 * (1.0 + std::fabs(x[0]) + std::fabs(x[1]))) break;
+      }
+    for (int a = 0; a < dim; ++a)
+      if (!(xi[a] >= -1e-10 && xi[a] <= 1.0 + 1e-10)) return false;
+    return true;
+  }
+} // namespace
+
+extern "C" {
+
+int stfem_point_evaluate(stfem_mesh_t mesh, int degree, int n_points, const double *points, int nb, const void *const *x,
+                         double *out)
+{
+  STFEM_REQUIRE(mesh && points && x && out, "stfem_point_evaluate: null argument");
+  STFEM_REQUIRE(degree >= 1 && degree <= 6, "stfem_point_evaluate: degree %d out of range", degree);
+  STFEM_REQUIRE(n_points >= 1 && nb >= 1 && nb <= STFEM_MAX_BLOCKS, "stfem_point_evaluate: bad counts");
+  STFEM_REQUIRE(!mesh->part.active, "stfem_point_evaluate: partitioned meshes are not supported yet");
+  stfem_ctx *ctx = mesh->ctx;
+  const int  dim = mesh->dim, n1 = degree + 1;
+  const int  nc  = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+  const Rule gl  = gauss_lobatto(n1);
+  long long  np[3] = {1, 1, 1};
+  for (int a = 0; a < dim; ++a) np[a] = (long long)degree * mesh->n[a] + 1;
+  std::vector<long long> idx((size_t)n_points * nc);
+  std::vector<double>    w((size_t)n_points * nc);
+  for (int p = 0; p < n_points; ++p)
+    {
+      const double *xp = points + (size_t)p * dim;
+      int           c[3] = {0, 0, 0};
+      double        xi[3] = {0, 0, 0};
+      bool          found = false;
+      int           guess[3] = {0, 0, 0};
+      for (int a = 0; a < dim; ++a)
+        {
+          const double h = (mesh->upper[a] - mesh->lower[a]) / mesh->n[a];
+          int          g = (int)std::floor((xp[a] - mesh->lower[a]) / h);
+          guess[a]       = g < 0 ? 0 : (g >= mesh->n[a] ? mesh->n[a] - 1 : g);
+          xi[a]          = (xp[a] - mesh->lower[a]) / h - guess[a];
+        }
+      if (mesh->cartesian)
+        {
+          found = true;
+          for (int a = 0; a < dim; ++a)
+            {
+              c[a] = guess[a];
+              if (!(xi[a] >= -1e-12 && xi[a] <= 1.0 + 1e-12)) found = false;
+            }
+        }
+      else
+        {
+          // vertices move by less than half a cell (GridTools::distort_random): the cell is the Cartesian guess or a neighbour;
+          // candidates in lexicographic order, first hit wins (a point on a cell boundary has the same value from both sides)
+          const int zlo = dim == 3 ? -1 : 0, zhi = dim == 3 ? 1 : 0;
+          for (int dz = zlo; dz <= zhi && !found; ++dz)
+            for (int dy = -1; dy <= 1 && !found; ++dy)
+              for (int dx = -1; dx <= 1 && !found; ++dx)
+                {
+                  const int cc[3] = {guess[0] + dx, guess[1] + dy, guess[2] + dz};
+                  bool      ok    = true;
+                  for (int a = 0; a < dim; ++a)
+                    if (cc[a] < 0 || cc[a] >= mesh->n[a]) ok = false;
+                  if (!ok) continue;
+                  double t[3];
+                  if (invert_q1(mesh, cc, xp, t))
+                    {
+                      found = true;
+                      for (int a = 0; a < 3; ++a) { c[a] = cc[a]; xi[a] = a < dim ? t[a] : 0.0; }
+                    }
+                }
+        }
+      STFEM_REQUIRE(found, "stfem_point_evaluate: point %d lies outside the mesh", p);
+      double L[3][8];
+      for (int a = 0; a < dim; ++a)
+        for (int i = 0; i < n1; ++i) L[a][i] = lagrange_value(gl.x, i, xi[a]);
+      const int n1z = dim == 3 ? n1 : 1;
+      int       o   = 0;
+      for (int iz = 0; iz < n1z; ++iz)
+        for (int iy = 0; iy < n1; ++iy)
+          for (int ix = 0; ix < n1; ++ix, ++o)
+            {
+              const long long gx = (long long)c[0] * degree + ix, gy = (long long)c[1] * degree + iy,
+                              gz = dim == 3 ? (long long)c[2] * degree + iz : 0;
+              idx[(size_t)p * nc + o] = gx + np[0] * (gy + np[1] * gz);
+              w[(size_t)p * nc + o]   = L[0][ix] * L[1][iy] * (dim == 3 ? L[2][iz] : 1.0);
+            }
+    }
+  long long *d_idx = nullptr;
+  double    *d_w = nullptr, *d_out = nullptr;
+  const int  n_items = nb * n_points;
+  STFEM_CUDA_CHECK(cudaMalloc(&d_idx, sizeof(long long) * idx.size()));
+  STFEM_CUDA_CHECK(cudaMalloc(&d_w, sizeof(double) * w.size()));
+  STFEM_CUDA_CHECK(cudaMalloc(&d_out, sizeof(double) * n_items));
+  STFEM_CUDA_CHECK(cudaMemcpyAsync(d_idx, idx.data(), sizeof(long long) * idx.size(), cudaMemcpyHostToDevice, ctx->stream));
+  STFEM_CUDA_CHECK(cudaMemcpyAsync(d_w, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice, ctx->stream));
+  PointPtrs bp;
+  for (int b = 0; b < nb; ++b) bp.p[b] = (const double *)x[b];
+  const int warps_per_cta = 4;
+  k_point_eval<<<(n_items + warps_per_cta - 1) / warps_per_cta, 32 * warps_per_cta, 0, ctx->stream>>>(n_items, n_points, nc, bp, d_idx,
+                                                                                                   d_w, d_out);
+  ctx->launches++;
+  STFEM_CUDA_CHECK(cudaGetLastError());
+  STFEM_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * n_items, cudaMemcpyDeviceToHost, ctx->stream));
+  STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_idx);
+  cudaFree(d_w);
+  cudaFree(d_out);
+  return STFEM_OK;
+}
+
+} // extern "C"

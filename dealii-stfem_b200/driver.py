@@ -31,6 +31,7 @@ capi.SYMBOLS.update({
     "stfem_ti_last_residuals": (C.c_int, [_vp, _dp, _dp]),
     "stfem_interpolate": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp]),
     "stfem_integrate_rhs": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _vp]),
+    "stfem_point_evaluate": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _vpp, _dp]),
     "stfem_evaluate_error": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vpp, _vp, C.c_double, C.c_double, C.c_double,
                                        C.c_int, _dp]),
 })
@@ -249,6 +250,13 @@ class HeatWaveProblem:
         self.total_iterations = 0
         self.n_solves = 0
         self.err = np.array([0.0, -1.0, 0.0])
+        # point-evaluation functionals of the practical runs (tp_01.cc:455-459, 559-583)
+        self.real_points = np.array([[0.75, 0.0]] if dim == 2 else [[0.75, 0.0, 0.0], [0.0, 0.0, 0.75], [0.75, 0.1, 0.75]])
+        self.functional_rows = []           # (t, value at every point), in the order the reference writes them
+        self.functional_file = None         # set to a path to append the reference's text format
+        self._prev_pt = None
+        if not conv and partition is None:
+            self._prev_pt = self.point_evaluate([self.x.ptrs[nbv - 1]])[0]
 
     def _laplace_coefficient(self, rf, degree):
         """K_mf.evaluate_coefficient(coeff) when !spaceTimeConvergenceTest (tp_01.cc:118-119, 279-280): keyword arguments
@@ -267,6 +275,39 @@ class HeatWaveProblem:
             else:
                 self._coeff_cache[key] = {"laplace_coeff_q": cq}
         return self._coeff_cache[key]
+
+    def point_evaluate(self, block_ptrs):
+        """u_b(real_points[p]) for the given device vectors: [len(block_ptrs), n_points]."""
+        nbk, npt = len(block_ptrs), len(self.real_points)
+        out = np.zeros((nbk, npt))
+        ptrs = (C.c_void_p * nbk)(*block_ptrs)
+        pts = np.ascontiguousarray(self.real_points, np.float64)
+        capi.check(capi.lib().stfem_point_evaluate(self.fmesh.h, self.k, npt, capi._dptr(pts), nbk, ptrs, capi._dptr(out)))
+        return out
+
+    def _do_point_evaluation(self):
+        """do_point_evaluation (tp_01.cc:584-635): every time DoF at the points, interpolated in time at (r+1)^2
+        equidistant samples per time step."""
+        samples = (self.r + 1) * (self.r + 1)
+        TE = ft.get_time_evaluation_matrix(self.ttype, self.r, samples)
+        vals = self.point_evaluate([self.x.ptrs[b] for b in range(self.nb)])
+        cg = 1 if self.is_cgp else 0
+        lines = []
+        for it in range(self.nts):
+            pt = np.zeros((self.r + 1, len(self.real_points)))
+            if cg:
+                pt[0] = self._prev_pt
+            pt[cg:] = vals[it * self.nd:(it + 1) * self.nd]
+            res = TE @ pt
+            for row in range(samples):
+                t_ = self.time + self.tau * (it + row / max(samples - 1.0, 1.0))
+                self.functional_rows.append((t_,) + tuple(res[row]))
+                lines.append("%16s" % ("%.6e" % t_) + "".join(" " * 16 + "%.6e" % v for v in res[row]) + "\n")
+            lines.append("\n")
+            self._prev_pt = vals[(it + 1) * self.nd - 1]
+        if self.functional_file:
+            with open(self.functional_file, "a") as f:
+                f.writelines(lines)
 
     def _copy(self, dst_ptr, src_ptr):
         # device-to-device copy of one spatial vector on the library stream
@@ -289,6 +330,8 @@ class HeatWaveProblem:
         if evaluate_error and self.p["spaceTimeConvergenceTest"]:
             capi.check(L.stfem_evaluate_error(self.fmesh.h, self.k, 1 if self.is_cgp else 2, self.r, self.nts, self.x.ptrs,
                                               self.prev_x.ptrs[0], self.time, self.tau, self.freq, self.r + 1, capi._dptr(self.err)))
+        elif self._prev_pt is not None:
+            self._do_point_evaluation()
         self.time += self.nts * self.tau
         return it.value
 

@@ -91,3 +91,16 @@ def quadrature_rule(kind, n):
     x, w = np.zeros(n), np.zeros(n)
     capi.check(capi.lib().stfem_quadrature_rule({"gauss": 0, "lobatto": 1, "radau": 2}[kind], n, _p(x), _p(w)))
     return x, w
+
+
+def get_time_evaluation_matrix(ttype, r, samples_per_interval):
+    """get_time_evaluation_matrix(get_time_basis(type, r), samples) (fe_time.h:307-326, fe_time.cc:152-179): the Lagrange
+    basis on the GLL(r+1) (CGP) / right Radau(r+1) (DG) points of [0,1] at samples_per_interval equidistant times."""
+    nodes = quadrature_rule("lobatto" if ttype == CGP else "radau", r + 1)[0]
+    t = np.arange(samples_per_interval) / max(samples_per_interval - 1.0, 1.0)
+    M = np.ones((samples_per_interval, r + 1))
+    for j in range(r + 1):
+        for m in range(r + 1):
+            if m != j:
+                M[:, j] *= (t - nodes[m]) / (nodes[j] - nodes[m])
+    return M

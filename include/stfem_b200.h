@@ -247,6 +247,12 @@ int stfem_evaluate_error(stfem_mesh_t mesh, int degree, int time_type, int time_
                          const void *const *x, const void *prev_x, double time, double time_step, double frequency,
                          int n_space_quad, double *out3);
 
+/* Point-evaluation functionals (tests/tp_01.cc:455-481, 584-635: RemotePointEvaluation + FEPointEvaluation of every
+ * time DoF at fixed points): out[b * n_points + p] = u_b(points[p]) for the nb DOUBLE device vectors x[b] of FE_Q(degree)
+ * on `mesh`; points = n_points * dim doubles (host).  Points outside the mesh are an error. */
+int stfem_point_evaluate(stfem_mesh_t mesh, int degree, int n_points, const double *points, int nb, const void *const *x,
+                         double *out);
+
 /* ---- host-side time algebra (no GPU): reference include/fe_time.h, include/fe_time.cc.
  *      type: 1 = CGP, 2 = DG (enum TimeStepType, fe_time.h:18-23).  All matrices row-major doubles. ---- */
 int stfem_fe_time_n_blocks(int type, int r, int n_timesteps_at_once);

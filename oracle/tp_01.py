@@ -166,6 +166,50 @@ def interpolate(space, fun):
     return fun(dof_points(space))
 
 
+def locate_point(space, x):
+    """(cell, reference coordinates) of a real point on the MappingQ1 mesh: Newton inversion of the d-linear map on
+    every cell at once, first cell (lexicographic) that contains the point (what RemotePointEvaluation returns first,
+    tp_01.cc:461-462, 566-574)."""
+    d = space.dim
+    X = space.mesh.cell_vertices()                                   # [C, 2^d, d]
+    C = X.shape[0]
+    xi = np.full((C, d), 0.5)
+    for _ in range(30):
+        N = np.ones((C, 1 << d))
+        dN = np.ones((C, 1 << d, d))
+        for v in range(1 << d):
+            for a in range(d):
+                bit = (v >> a) & 1
+                na = xi[:, a] if bit else 1.0 - xi[:, a]
+                N[:, v] *= na
+                for b in range(d):
+                    dN[:, v, b] *= (1.0 if bit else -1.0) if a == b else na
+        f = np.einsum("cv,cva->ca", N, X)
+        J = np.einsum("cva,cvb->cab", X, dN)
+        xi = xi + np.linalg.solve(J, (x[None, :] - f)[..., None])[..., 0]
+    inside = np.all((xi >= -1e-10) & (xi <= 1 + 1e-10), axis=1)
+    c = int(np.argmax(inside))
+    assert inside[c], "point outside the mesh"
+    return c, xi[c]
+
+
+def point_evaluate(space, points, u):
+    """FEPointEvaluation::evaluate at real points (tp_01.cc:463-481): u_h(x_p) for u[nb, N] -> [nb, n_points]."""
+    d = space.dim
+    out = np.zeros((u.shape[0], len(points)))
+    for p, x in enumerate(np.asarray(points, float)):
+        c, xi = locate_point(space, x)
+        L = [Q.lagrange_eval(space.gll, np.array([xi[a]]))[:, 0] for a in range(d)]
+        w = np.einsum("y,x->yx", L[1], L[0]).reshape(-1) if d == 2 else np.einsum("z,y,x->zyx", L[2], L[1], L[0]).reshape(-1)
+        out[:, p] = u[:, space.cell_dofs[c]] @ w
+    return out
+
+
+def time_evaluation_matrix(ttype, r, samples):
+    """get_time_evaluation_matrix (fe_time.h:307-326) for get_time_basis(type, r) (fe_time.cc:162-179)."""
+    return Q.lagrange_eval(ft.time_nodes(ttype, r), np.arange(samples) / max(samples - 1.0, 1.0)).T.copy()
+
+
 class ErrorCalculator:
     """exact_solution.h:503-649, called with (type, fe_degree, fe_degree) (tp_01.cc:492-498):
     QGauss<dim>(fe_degree+1) per cell in space, QGauss<1>(fe_degree+1) in time."""
@@ -377,6 +421,13 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
             AixG = -AixG
         else:
             AixZ = -AixZ
+    # point evaluation functionals of the practical runs (tp_01.cc:455-459, 559-635)
+    real_points = [[0.75, 0.0]] if dim == 2 else [[0.75, 0.0, 0.0], [0.0, 0.0, 0.75], [0.75, 0.1, 0.75]]
+    functional_rows = []
+    if not p["spaceTimeConvergenceTest"]:
+        prev_pt = point_evaluate(space, real_points, x[-1:])[0]
+        samples = (fe_degree + 1) ** 2
+        TE = time_evaluation_matrix(ttype, fe_degree, samples)
     l2 = h1 = 0.0
     l8 = -1.0
     total_it = 0
@@ -427,10 +478,23 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
             l2 += e["L2"]
             h1 += e["H1"]
             l8 = max(l8, e["Linf"])
+        else:
+            vals = point_evaluate(space, real_points, x)
+            cg = 1 if is_cgp else 0
+            for it in range(nts):
+                pt = np.zeros((fe_degree + 1, len(real_points)))
+                if cg:
+                    pt[0] = prev_pt
+                pt[cg:] = vals[it * nt_dofs:(it + 1) * nt_dofs]
+                res = TE @ pt
+                for row in range(samples):
+                    functional_rows.append((time + tau * (it + row / max(samples - 1.0, 1.0)),) + tuple(res[row]))
+                prev_pt = vals[(it + 1) * nt_dofs - 1]
         time += nts * tau
         if max_steps is not None and n_solves >= max_steps:
             break
-    state = dict(x=x, v=v if wave else None, iterations_per_solve=its_per_solve) if return_state else {}
+    state = dict(x=x, v=v if wave else None, iterations_per_solve=its_per_solve,
+                 functional_rows=functional_rows) if return_state else {}
     return dict(state, cells=mesh.n_cells, s_dofs=space.n_dofs, t_dofs=nb, iterations=total_it, timesteps=n_solves,
                 linf=l8, l2=math.sqrt(l2), h1=math.sqrt(h1), tau=tau,
                 levels="".join(lv["mg_type_level"]) if lv else "", n_levels=(len(lv["mg_type_level"]) + 1) if lv else 0)

@@ -110,3 +110,27 @@ def test_driver_level_coefficient_selects_per_cell_or_per_q_path():
     # convergence tests carry no coefficient
     p2 = st.parse_parameters({}, 3)
     assert st.HeatWaveProblem._laplace_coefficient(types.SimpleNamespace(p=p2), 0, 2) == {}
+
+
+@pytest.mark.parametrize("dim,distort", [(2, 0.0), (2, 0.15), (3, 0.0), (3, 0.15)])
+def test_oracle_point_evaluation_reproduces_linear_functions(dim, distort):
+    """The oracle's FEPointEvaluation restatement (cell search + Newton inversion of the MappingQ1 map): a linear function
+    of x lies in the mapped FE_Q(k) space, so its point values are exact on perturbed meshes too."""
+    lo, up = [-1.0] * dim, [1.0] * dim
+    mesh = S.Mesh(dim, [5] * dim, 1, lo, up, distort=distort)
+    space = S.Space(mesh, 2)
+    coef = np.arange(1, dim + 1, dtype=float)
+    u = tp_01.interpolate(space, lambda pts: 0.3 + pts @ coef)[None, :]
+    pts = [[0.75, 0.0], [0.013, -0.48]] if dim == 2 else [[0.75, 0.0, 0.0], [0.0, 0.0, 0.75], [0.75, 0.1, 0.75], [0.31, -0.77, 0.05]]
+    got = tp_01.point_evaluate(space, pts, u)[0]
+    assert np.allclose(got, 0.3 + np.asarray(pts) @ coef, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("ttype,r", [("CGP", 1), ("CGP", 3), ("DG", 0), ("DG", 2)])
+def test_time_evaluation_matrix_matches_oracle(ttype, r):
+    from dealii_stfem_b200 import fe_time_host as fth
+    samples = (r + 1) ** 2 if r > 0 else 2
+    M = fth.get_time_evaluation_matrix(ttype, r, samples)
+    assert M.shape == (samples, r + 1)
+    assert np.allclose(M, tp_01.time_evaluation_matrix(ttype, r, samples), rtol=0, atol=1e-13)
+    assert np.allclose(M.sum(axis=1), 1.0)          # partition of unity

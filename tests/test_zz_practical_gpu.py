@@ -27,10 +27,16 @@ def _run_both(ctx, pj, dim, ref, k, vertices=None, steps=2):
     x = prob.x.download()
     v = prob.v.download() if prob.wave else None
     levels = "".join(prob.mg_type_level)
+    rows = np.array(prob.functional_rows)
     prob.close()
     o = tp_01.convergence_test(tp_01.parse_parameters(pj, dim), dim, ref, k, mg_dtype=np.float32, max_steps=steps,
                                return_state=True)
     assert levels == o["levels"]
+    # point-evaluation functionals (tp_01.cc:584-635): same sample times, values to solver accuracy
+    orows = np.array(o["functional_rows"])
+    assert rows.shape == orows.shape and rows.shape[0] == steps * p["nTimestepsAtOnce"] * (k + 1) ** 2
+    assert np.allclose(rows[:, 0], orows[:, 0], rtol=1e-14, atol=0)
+    assert np.abs(rows[:, 1:] - orows[:, 1:]).max() <= 1e-7 * max(np.abs(orows[:, 1:]).max(), 1e-300)
     return its, x, v, o
 
 
@@ -89,3 +95,31 @@ def test_tp01_front_end_prints_reference_tables(ctx):
     assert got[0] == ":: Number of active cells: 16" and got[2].startswith(":: Min Level 0  Max Level ")
     assert "Iteration count table" in got
     assert len(rows) == 1 and len(rows[0]) == 2
+
+
+@pytest.mark.parametrize("dim,distort,degree", [(3, 0.15, 3), (3, 0.0, 4), (2, 0.1, 2)])
+def test_point_evaluation_matches_oracle(ctx, dim, distort, degree):
+    """stfem_point_evaluate (cell search, Newton inversion of the MappingQ1 map, warp gather) against the oracle's
+    FEPointEvaluation restatement on random vectors."""
+    import ctypes as C
+
+    import dealii_stfem_b200 as st
+    lo, up = [-1.0] * dim, [1.0] * dim
+    mesh = S.Mesh(dim, [5] * dim, 1, lo, up, distort=distort)
+    space = S.Space(mesh, degree)
+    nb = 3
+    u = np.stack([np.random.RandomState(7 + b).uniform(-1, 1, space.n_dofs) for b in range(nb)])
+    pts = np.array([[0.75, 0.0], [0.013, -0.48], [-1.0, 1.0]] if dim == 2 else
+                   [[0.75, 0.0, 0.0], [0.0, 0.0, 0.75], [0.75, 0.1, 0.75], [0.31, -0.77, 0.05], [1.0, 1.0, 1.0]])
+    want = tp_01.point_evaluate(space, pts, u)
+    gm = st.Mesh(ctx, mesh.n, lower=lo, upper=up, vertices=None if distort == 0.0 else mesh.vertices.reshape(-1, dim))
+    dv = st.DeviceBlockVector(ctx, nb, space.n_dofs, st.F64).upload(u)
+    got = np.zeros((nb, len(pts)))
+    ptrs = (C.c_void_p * nb)(*[dv.ptrs[b] for b in range(nb)])
+    st.capi.check(st.capi.lib().stfem_point_evaluate(gm.h, degree, len(pts), st.capi._dptr(np.ascontiguousarray(pts)), nb, ptrs,
+                                                     st.capi._dptr(got)))
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    # a point outside the mesh is reported, not extrapolated
+    bad = np.ascontiguousarray([[2.0] * dim])
+    assert st.capi.lib().stfem_point_evaluate(gm.h, degree, 1, st.capi._dptr(bad), nb, ptrs, st.capi._dptr(got)) != 0
+    dv.free(); gm.close()
