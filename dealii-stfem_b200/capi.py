@@ -249,6 +249,10 @@ class Operator:
     def vmult_slice_add(self, dst, src0):
         check(lib().stfem_op_vmult_slice_add(self.h, dst.ptrs, src0.ptrs[0]))
 
+    def diagonal(self, dst):
+        """get_matrix_diagonal (operators.h:613-625) into a block vector of the operator's number type."""
+        check(lib().stfem_op_diagonal(self.h, dst.ptrs))
+
     def vmult_host(self, dst, src, transpose=False):
         """dst, src: numpy [nb, N] (C-contiguous rows; pinned or pageable)."""
         nb = self.nb_rows
@@ -273,7 +277,7 @@ class MgDesc(C.Structure):
                 ("smoother_types", C.POINTER(C.c_int)), ("time_type", C.c_int), ("n_timesteps_at_once", C.c_int),
                 ("poly_time_sequence", C.POINTER(C.c_int)), ("n_poly_time", C.c_int), ("smoothing_steps", C.c_int),
                 ("relaxation", C.c_double), ("smoothing_range", C.c_double), ("eig_n_iterations", C.c_int),
-                ("variable", C.c_int), ("restrict_is_transpose_prolongate", C.c_int)]
+                ("variable", C.c_int), ("restrict_is_transpose_prolongate", C.c_int), ("inner_preconditioner", C.c_int)]
 
 
 class Multigrid:
@@ -281,7 +285,8 @@ class Multigrid:
 
     def __init__(self, ctx, level_ops, mg_type_level, smoother_types, time_type, n_timesteps_at_once, poly_time_sequence,
                  smoothing_steps=1, relaxation=0.0, smoothing_range=1.0, eig_n_iterations=20, variable=True,
-                 restrict_is_transpose_prolongate=True):
+                 restrict_is_transpose_prolongate=True, inner_preconditioner="vanka"):
+        """inner_preconditioner: "vanka" (PreconditionVanka, the reference) or "jacobi" (point-Jacobi, diagonal inverse)."""
         self.ctx, self.ops = ctx, list(level_ops)
         nl = len(self.ops)
         d = MgDesc()
@@ -299,6 +304,7 @@ class Multigrid:
         d.smoothing_steps, d.relaxation, d.smoothing_range = smoothing_steps, relaxation, smoothing_range
         d.eig_n_iterations, d.variable = eig_n_iterations, int(variable)
         d.restrict_is_transpose_prolongate = int(restrict_is_transpose_prolongate)
+        d.inner_preconditioner = {"vanka": 0, "jacobi": 1}[inner_preconditioner]
         self.h = C.c_void_p()
         check(lib().stfem_mg_create(ctx.h, C.byref(d), C.byref(self.h)))
 

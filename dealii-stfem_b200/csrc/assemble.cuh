@@ -297,6 +297,79 @@ namespace stfem
       }
   }
 
+
+  // Diagonals of the spatial operators (MatrixFreeTools::compute_diagonal as used at include/operators.h:1092-1110):
+  //   dM_i = sum_cells sum_q phi_i(x_q)^2 JxW,   dK_i = sum_cells sum_q c(x_q) |J^-T grad phi_i(x_q)|^2 JxW
+  // One CTA per cell: the metric c J^-1 J^-T JxW (6 numbers) and JxW of every quadrature point go to shared memory once,
+  // then one thread per local node sums over the quadrature points.  Constrained rows stay 0.  Set-up work (called once
+  // per operator), not a hot kernel.  coeff_cell / coeff_q: optional Laplace coefficient (per cell / per cell and q-point).
+  static __global__ void k_diagonal(AsmGeom g, const double *__restrict__ coeff_cell, const double *__restrict__ coeff_q,
+                                    double *__restrict__ dK, double *__restrict__ dM)
+  {
+    const int dim = g.dim, n1 = g.n1, nq1 = g.nq1, k = n1 - 1;
+    const int nq = dim == 3 ? nq1 * nq1 * nq1 : nq1 * nq1;
+    const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    __shared__ double met[512 * 7]; // nq1 <= 8: [q][Gxx Gxy Gxz Gyy Gyz Gzz JxW]
+    for (long long cell = blockIdx.x; cell < g.n_cells; cell += gridDim.x)
+      {
+        const int c[3] = {(int)(cell % g.n[0]), (int)((cell / g.n[0]) % g.n[1]), dim == 3 ? (int)(cell / ((long long)g.n[0] * g.n[1])) : 0};
+        __syncthreads();
+        for (int q = threadIdx.x; q < nq; q += blockDim.x)
+          {
+            const int    qi[3] = {q % nq1, (q / nq1) % nq1, dim == 3 ? q / (nq1 * nq1) : 0};
+            const double xi[3] = {g.xq[qi[0]], g.xq[qi[1]], dim == 3 ? g.xq[qi[2]] : 0.0};
+            const double w = g.wq[qi[0]] * g.wq[qi[1]] * (dim == 3 ? g.wq[qi[2]] : 1.0);
+            double       x[3], J[3][3], inv[3][3];
+            map_q1(g, c, xi, x, J);
+            const double jxw = det_inv(dim, J, inv) * w;
+            double       cl  = coeff_cell ? coeff_cell[cell] : 1.0;
+            if (coeff_q) cl *= coeff_q[cell * nq + q];
+            double *m = met + q * 7;
+            int     o = 0;
+            for (int a = 0; a < 3; ++a)
+              for (int b = a; b < 3; ++b, ++o)
+                {
+                  double s = 0.0;
+                  if (a < dim && b < dim)
+                    for (int e = 0; e < dim; ++e) s += inv[a][e] * inv[b][e];
+                  m[o] = s * jxw * cl;
+                }
+            m[6] = jxw;
+          }
+        __syncthreads();
+        for (int l = threadIdx.x; l < nc; l += blockDim.x)
+          {
+            const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
+            const int gi[3] = {c[0] * k + li[0], c[1] * k + li[1], c[2] * k + li[2]};
+            if (asm_constrained(g, gi[0], gi[1], gi[2])) continue;
+            double sk = 0.0, sm = 0.0;
+            for (int q = 0; q < nq; ++q)
+              {
+                const int    qi[3] = {q % nq1, (q / nq1) % nq1, dim == 3 ? q / (nq1 * nq1) : 0};
+                const double sx = g.S[qi[0] * n1 + li[0]], sy = g.S[qi[1] * n1 + li[1]], sz = dim == 3 ? g.S[qi[2] * n1 + li[2]] : 1.0;
+                const double gx = g.D[qi[0] * n1 + li[0]] * sy * sz, gy = sx * g.D[qi[1] * n1 + li[1]] * sz,
+                             gz = dim == 3 ? sx * sy * g.D[qi[2] * n1 + li[2]] : 0.0;
+                const double *m = met + q * 7;
+                const double  v = sx * sy * sz;
+                sm += v * v * m[6];
+                sk += gx * (m[0] * gx + 2.0 * (m[1] * gy + m[2] * gz)) + gy * (m[3] * gy + 2.0 * m[4] * gz) + m[5] * gz * gz;
+              }
+            const long long dof = (long long)gi[0] + (long long)g.np[0] * (gi[1] + (long long)g.np[1] * gi[2]);
+            atomicAdd(dK + dof, sk);
+            atomicAdd(dM + dof, sm);
+          }
+      }
+  }
+
+  // out_i = a dK_i + b dM_i in the operator's number type
+  template <typename T>
+  static __global__ void k_diag_combine(long long n, double a, double b, const double *__restrict__ dK, const double *__restrict__ dM,
+                                        T *__restrict__ out)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      out[i] = (T)(a * dK[i] + b * dM[i]);
+  }
+
   inline void fill_asm_geom(AsmGeom &g, const stfem_mesh *m, int degree, int nq1)
   {
     g.dim = m->dim; g.n1 = degree + 1; g.nq1 = nq1; g.n_cells = m->n_cells; g.dirichlet = m->dirichlet;

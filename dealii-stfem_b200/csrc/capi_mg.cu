@@ -29,6 +29,8 @@ int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out)
   o.eig_n_iterations = desc->eig_n_iterations > 0 ? desc->eig_n_iterations : 20;
   o.variable         = desc->variable != 0;
   o.restrict_is_transpose_prolongate = desc->restrict_is_transpose_prolongate != 0;
+  STFEM_REQUIRE(desc->inner_preconditioner == 0 || desc->inner_preconditioner == 1, "stfem_mg_create: inner_preconditioner must be 0 or 1");
+  o.inner_preconditioner = desc->inner_preconditioner;
   STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
   auto mg         = std::make_unique<stfem_mg>();
   mg->number_type = ops[0]->number_type;

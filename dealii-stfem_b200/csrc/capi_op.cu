@@ -9,6 +9,7 @@
 #include "vec.cuh"
 #include "st_vmult_generic.cuh"
 #include "st_vmult_plane.cuh"
+#include "assemble.cuh"
 
 namespace stfem
 {
@@ -701,6 +702,48 @@ namespace stfem
 
 using namespace stfem;
 
+namespace stfem
+{
+  // diag K and diag M of the operator's spatial parts (double, N entries each, cudaMalloc'ed: the caller frees),
+  // constrained rows 0 (include/operators.h:1092-1110)
+  int op_spatial_diagonals(stfem_op *op, double **dK_out, double **dM_out)
+  {
+    stfem_mesh *m   = op->mesh;
+    stfem_ctx  *ctx = m->ctx;
+    STFEM_REQUIRE(!m->part.active, "diagonal: partitioned meshes are not supported yet");
+    STFEM_REQUIRE(op->degree >= 1 && op->degree <= 6, "diagonal: degree out of range");
+    AsmGeom g;
+    fill_asm_geom(g, m, op->degree, op->degree + 1);
+    const int nq = m->dim == 3 ? g.nq1 * g.nq1 * g.nq1 : g.nq1 * g.nq1;
+    double   *dK = nullptr, *dM = nullptr, *d_cc = nullptr, *d_cq = nullptr;
+    STFEM_CUDA_CHECK(cudaMalloc(&dK, sizeof(double) * op->N));
+    STFEM_CUDA_CHECK(cudaMalloc(&dM, sizeof(double) * op->N));
+    STFEM_CUDA_CHECK(cudaMemsetAsync(dK, 0, sizeof(double) * op->N, ctx->stream));
+    STFEM_CUDA_CHECK(cudaMemsetAsync(dM, 0, sizeof(double) * op->N, ctx->stream));
+    if (!op->h_coeff_cell.empty())
+      {
+        STFEM_CUDA_CHECK(cudaMalloc(&d_cc, sizeof(double) * m->n_cells));
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_cc, op->h_coeff_cell.data(), sizeof(double) * m->n_cells, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    if (!op->h_coeff_q.empty())
+      {
+        STFEM_CUDA_CHECK(cudaMalloc(&d_cq, sizeof(double) * m->n_cells * nq));
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_cq, op->h_coeff_q.data(), sizeof(double) * m->n_cells * nq, cudaMemcpyHostToDevice, ctx->stream));
+      }
+    const long long cap  = (long long)ctx->sm_count * 8;
+    const int       grid = (int)(m->n_cells < cap ? m->n_cells : cap);
+    k_diagonal<<<grid, 128, 0, ctx->stream>>>(g, d_cc, d_cq, dK, dM);
+    ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (d_cc) cudaFree(d_cc);
+    if (d_cq) cudaFree(d_cq);
+    *dK_out = dK;
+    *dM_out = dM;
+    return STFEM_OK;
+  }
+} // namespace stfem
+
 extern "C" {
 
 int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *out)
@@ -832,10 +875,28 @@ int stfem_op_vmult_slice_add(stfem_op_t op, void *const *dst, const void *src0)
   return op_apply(op, dst, src, 1, op->nb_rows, op->d_alpha, op->d_beta, false);
 }
 
-int stfem_op_diagonal(stfem_op_t, void *const *)
+int stfem_op_diagonal(stfem_op_t op, void *const *diag)
 {
-  set_error("stfem_op_diagonal: not implemented yet");
-  return STFEM_ERR_UNSUPPORTED;
+  STFEM_REQUIRE(op && diag, "stfem_op_diagonal: null argument");
+  STFEM_REQUIRE(op->nb_rows == op->nb_cols, "stfem_op_diagonal: operator not square in time");
+  stfem_ctx *ctx = op->mesh->ctx;
+  double    *dK = nullptr, *dM = nullptr;
+  STFEM_FORWARD(stfem::op_spatial_diagonals(op, &dK, &dM));
+  const int nb = op->nb_rows;
+  for (int b = 0; b < nb; ++b)
+    {
+      const double a = op->Alpha[(size_t)b * nb + b], be = op->Beta[(size_t)b * nb + b];
+      if (op->number_type == STFEM_F64)
+        k_diag_combine<double><<<grid_for(ctx, op->N, 256), 256, 0, ctx->stream>>>(op->N, a, be, dK, dM, (double *)diag[b]);
+      else
+        k_diag_combine<float><<<grid_for(ctx, op->N, 256), 256, 0, ctx->stream>>>(op->N, a, be, dK, dM, (float *)diag[b]);
+      ctx->launches++;
+    }
+  STFEM_CUDA_CHECK(cudaGetLastError());
+  STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dK);
+  cudaFree(dM);
+  return STFEM_OK;
 }
 
 int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const *src_host, int transpose)

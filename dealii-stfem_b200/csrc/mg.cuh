@@ -49,12 +49,32 @@ namespace stfem
       }
   }
 
+  // point-Jacobi inner preconditioner: inverse of diag_b = Alpha(b,b) diag K + Beta(b,b) diag M with the reference's
+  // rule for (near-)zero entries (include/operators.h:1105-1109: |d| > sqrt(eps) ? 1/d : 1), and its application
+  template <typename T>
+  __global__ void k_inv_diag(long long n, double a, double b, const double *__restrict__ dK, const double *__restrict__ dM, T *__restrict__ out)
+  {
+    const double tol = sizeof(T) == 8 ? 1.4901161193847656e-08 : 3.4526698300124393e-04; // sqrt(epsilon)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        const double d = a * dK[i] + b * dM[i];
+        out[i]         = (T)(fabs(d) > tol ? 1.0 / d : 1.0);
+      }
+  }
+  template <typename T>
+  __global__ void k_diag_apply_add(long long n, T scale, const T *__restrict__ inv_diag, const T *__restrict__ src, T *__restrict__ dst)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      dst[i] += scale * inv_diag[i] * src[i];
+  }
+
   template <typename T>
   struct MGLevel
   {
     stfem_op                 *op = nullptr;
     int                       smoother = 1; // 0 identity, 1 relaxation, 2 chebyshev
     std::unique_ptr<Vanka<T>> vanka;
+    BlockVec<T>               inv_diag; // point-Jacobi inner preconditioner (MGOptions::inner_preconditioner == 1)
     double                    omega = 1.0, theta = 1.0, delta = 0.0, lambda = 1.0;
     char                      ttype = 0; // transfer from level-1: 'h','p','k','t'
     SpaceTransfer<T>          st;
@@ -74,6 +94,7 @@ namespace stfem
     double relaxation = 0.0, smoothing_range = 1.0;
     int    eig_n_iterations = 20;
     bool   variable = true, restrict_is_transpose_prolongate = true;
+    int    inner_preconditioner = 0; // 0 PreconditionVanka (the reference, stmg.h:1055-1063), 1 point-Jacobi
   };
 
   struct MGBase
@@ -120,6 +141,12 @@ namespace stfem
     int vanka_add(int l, BlockVec<T> &dst, const BlockVec<T> &src, T scale)
     {
       MGLevel<T> &lv = L[l];
+      if (lv.inv_diag.d)
+        {
+          k_diag_apply_add<T><<<grid_for(ctx, dst.size(), 256), 256, 0, ctx->stream>>>(dst.size(), scale, lv.inv_diag.d, src.d, dst.d);
+          ctx->launches++;
+          return STFEM_OK;
+        }
       if (lv.op->mesh->part.active)
         {
           if (tmp_part.size() <= (size_t)l) tmp_part.resize(L.size());
@@ -389,7 +416,23 @@ namespace stfem
                         lv.op->nb_rows, lv_nts[l], lv_nd[l]);
           const int nb = lv.op->nb_rows;
           for (BlockVec<T> *v : {&lv.sol, &lv.defect, &lv.t, &lv.r, &lv.d, &lv.d2}) STFEM_FORWARD(v->alloc(ctx, nb, lv.op->N));
-          if (lv.smoother != 0)
+          if (lv.smoother != 0 && opt.inner_preconditioner == 1)
+            {
+              double *dK = nullptr, *dM = nullptr;
+              STFEM_FORWARD(op_spatial_diagonals(lv.op, &dK, &dM));
+              STFEM_FORWARD(lv.inv_diag.alloc(ctx, nb, lv.op->N));
+              for (int b = 0; b < nb; ++b)
+                {
+                  k_inv_diag<T><<<grid_for(ctx, lv.op->N, 256), 256, 0, ctx->stream>>>(lv.op->N, lv.op->Alpha[(size_t)b * nb + b],
+                                                                                       lv.op->Beta[(size_t)b * nb + b], dK, dM,
+                                                                                       lv.inv_diag.d + (size_t)b * lv.op->N);
+                  ctx->launches++;
+                }
+              STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+              cudaFree(dK);
+              cudaFree(dM);
+            }
+          else if (lv.smoother != 0)
             {
               lv.vanka = std::make_unique<Vanka<T>>();
               STFEM_FORWARD(lv.vanka->setup(lv.op));
@@ -551,7 +594,7 @@ namespace stfem
       switch (what)
         {
           case 0: // Vanka
-            STFEM_REQUIRE(lv.vanka, "level %d has no Vanka smoother", l);
+            STFEM_REQUIRE(lv.vanka || lv.inv_diag.d, "level %d has no inner preconditioner", l);
             STFEM_FORWARD(load(lv.defect, src));
             STFEM_FORWARD(lv.sol.zero());
             STFEM_FORWARD(vanka_add(l, lv.sol, lv.defect, (T)1));

@@ -36,4 +36,6 @@ namespace stfem
   // dst (+)= A src with explicit time matrices (device pointers in the operator's number type)
   int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                const void *beta, bool zero_dst);
+  // diag K, diag M (double, cudaMalloc'ed, caller frees), constrained rows 0; capi_op.cu
+  int op_spatial_diagonals(stfem_op *op, double **dK, double **dM);
 } // namespace stfem

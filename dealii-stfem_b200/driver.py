@@ -55,6 +55,7 @@ def default_parameters(dim=2):
         # accepted and ignored like in tests/tp_01.cc (unused there): relativeTolerance, timeRefineOffset, deltaTime
         "relativeTolerance": 1.0e-12, "timeRefineOffset": 1, "deltaTime": 0.0,
         "agglomerateBelow": 16,     # multi-GPU only (not a reference key): see HeatWaveProblem
+        "innerPreconditioner": "vanka",   # not a reference key: "jacobi" = point-Jacobi inside Relaxation / Chebyshev
     }
 
 
@@ -194,7 +195,8 @@ class HeatWaveProblem:
         self.mg = capi.Multigrid(ctx, self.level_ops, self.mg_type_level, self.ptypes, self.ttype, self.nts, self.poly_time,
                                  smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
                                  eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
-                                 restrict_is_transpose_prolongate=p["restrictIsTransposeProlongate"]) if p.get("useMg", True) else None
+                                 restrict_is_transpose_prolongate=p["restrictIsTransposeProlongate"],
+                                 inner_preconditioner=p.get("innerPreconditioner", "vanka")) if p.get("useMg", True) else None
         # ---- fine operators (tp_01.cc:121-168)
         fmesh = self.meshes[refinement]
         self.fmesh = fmesh

@@ -173,6 +173,9 @@ typedef struct stfem_mg_desc {
   int eig_n_iterations;          /* default 20 */
   int variable;                  /* MGSmootherPrecondition variable smoothing, default 1 */
   int restrict_is_transpose_prolongate; /* default 1 */
+  int inner_preconditioner;      /* 0 = PreconditionVanka (the reference, stmg.h:1055-1063); 1 = point-Jacobi: the inverse of
+                                    SystemMatrix::get_matrix_diagonal (operators.h:613-625) inside Relaxation / Chebyshev.
+                                    Not a reference configuration: the cheap smoother BASELINE.json's north_star names. */
 } stfem_mg_desc;
 
 int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out);

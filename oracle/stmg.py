@@ -135,6 +135,27 @@ class TimeTransfer:
 
 
 # ----------------------------------------------------------------------------- Vanka
+class PointJacobi:
+    """Point-Jacobi inner preconditioner (NOT a reference configuration; BASELINE.json's north_star names it as the cheap
+    smoother): the inverse of SystemMatrix::get_matrix_diagonal (operators.h:613-625), diag_b = Alpha(b,b) diag K +
+    Beta(b,b) diag M with the constrained rows of diag K, diag M zero, and the reference's rule for vanishing entries
+    (operators.h:1105-1109: |d| > sqrt(eps) ? 1/d : 1).  Same interface as PreconditionVanka (GMG(vanka=[...]))."""
+
+    def __init__(self, levelop, dtype):
+        free = ~levelop.space.constrained
+        dK = np.where(free, levelop.K_full.diagonal(), 0.0)
+        dM = np.where(free, levelop.M_full.diagonal(), 0.0)
+        nb = levelop.nb
+        d = np.stack([levelop.Alpha[b, b] * dK + levelop.Beta[b, b] * dM for b in range(nb)])
+        tol = np.sqrt(np.finfo(dtype).eps)
+        self.diag = d
+        self.inv = np.where(np.abs(d) > tol, 1.0 / np.where(d == 0, 1.0, d), 1.0).astype(dtype)
+        self.dtype = dtype
+
+    def vmult(self, src):
+        return (self.inv * src).astype(self.dtype)
+
+
 class PreconditionVanka:
     """stmg.h:745-872: per cell, B = Beta (x) M_c + Alpha (x) K_c from the ASSEMBLED matrices restricted to
     the cell's DoFs (rows scaled by the valence, compute_block_matrix.h:135-136), inverted."""

@@ -33,6 +33,7 @@ def default_parameters(dim=2):
         "endTime": 1.0, "smoother": "relaxation", "smoothingSteps": 1, "smoothingRange": 1.0,
         "relaxation": 0.0, "coarseGridSmootherType": "Smoother", "restrictIsTransposeProlongate": True,
         "variable": True, "smoothingEigCgNIterations": 20,
+        "innerPreconditioner": "vanka",   # not a reference key: "jacobi" = stmg.PointJacobi inside Relaxation / Chebyshev
         "sourcePoint": None,         # parameters.h:79: midpoint of the DEFAULT box (member initialiser order)
     }
 
@@ -395,8 +396,11 @@ def convergence_test(p, dim, refinement, fe_degree, mg_dtype=np.float32, use_mg=
     lv = None
     if use_mg:
         lv = build_levels(p, dim, refinement, fe_degree, tau, mg_dtype, coeff, mesh)
+        inner = None
+        if p["innerPreconditioner"] == "jacobi":
+            inner = [stmg.PointJacobi(o, mg_dtype) if t != 0 else None for o, t in zip(lv["ops"], lv["ptypes"])]
         gmg = stmg.GMG(ttype, lv["ops"], lv["spaces"], lv["mg_type_level"], lv["poly_time"], nts, lv["ptypes"],
-                       mg_dtype, smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"],
+                       mg_dtype, vanka=inner, smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"],
                        smoothing_range=p["smoothingRange"], eig_n_iterations=p["smoothingEigCgNIterations"],
                        variable=p["variable"], restrict_is_transpose_prolongate=p["restrictIsTransposeProlongate"])
     rhs_fun = (lambda pts, t: rhs_wave(pts, t, f)) if wave else (lambda pts, t: rhs_heat(pts, t, f))

@@ -123,3 +123,58 @@ def test_point_evaluation_matches_oracle(ctx, dim, distort, degree):
     bad = np.ascontiguousarray([[2.0] * dim])
     assert st.capi.lib().stfem_point_evaluate(gm.h, degree, 1, st.capi._dptr(bad), nb, ptrs, st.capi._dptr(got)) != 0
     dv.free(); gm.close()
+
+
+@pytest.mark.parametrize("dim,degree,distort,ttype,r,coef", [
+    (3, 4, 0.0, "CGP", 2, None), (3, 3, 0.15, "DG", 2, "q"), (3, 2, 0.0, "DG", 1, "cell"), (2, 2, 0.1, "DG", 1, None),
+    (2, 5, 0.0, "CGP", 3, None)])
+def test_matrix_diagonal_matches_oracle(ctx, dim, degree, distort, ttype, r, coef):
+    """SystemMatrix::get_matrix_diagonal (reference include/operators.h:613-625, 1092-1110): diag_b = Alpha(b,b) diag K +
+    Beta(b,b) diag M, constrained rows 0.  1e-12 in FP64, 1e-5 in FP32 (north_star tolerances of the operator)."""
+    import dealii_stfem_b200 as st
+    from dealii_stfem_b200 import fe_time_host as fth
+    lo, up = [-1.0] * dim, [1.0] * dim
+    sub = [5] * dim if coef else [3] * dim
+    mesh = S.Mesh(dim, sub, 1 if coef else 0, lo, up, distort=distort)
+    space = S.Space(mesh, degree)
+    A, B, _, _ = fth.get_fe_time_weights(ttype, r, 0.05, 1)
+    K, M = S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0)
+    kw = {}
+    if coef:
+        c = S.Coefficient(dim, sub, lo, up, distort_coeff=0.5)
+        K.evaluate_coefficient(c)
+        kw = {"laplace_coeff_q": K.laplace_coeff} if coef == "q" else {"laplace_coeff_cell": np.ascontiguousarray(K.laplace_coeff[:, 0])}
+    want = S.SystemMatrix(K, M, A, B).get_matrix_diagonal()
+    gm = st.Mesh(ctx, mesh.n, lower=lo, upper=up, vertices=None if distort == 0.0 else mesh.vertices.reshape(-1, dim))
+    for nt, tol in ((st.F64, 1e-12), (st.F32, 1e-5)):
+        op = st.Operator(gm, degree, A, B, number_type=nt, **kw)
+        d = op.new_vector()
+        op.diagonal(d)
+        got = d.download()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= tol * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
+        assert np.all(got[:, space.constrained] == 0)
+        d.free(); op.close()
+    gm.close()
+
+
+@pytest.mark.parametrize("name,dim,ref,over", [("tf03", 2, 3, {}), ("tf04", 2, 3, {"smoother": "chebyshev", "smoothingSteps": "3"}),
+                                               ("tf03", 3, 2, {})])
+def test_point_jacobi_smoother_matches_oracle(ctx, name, dim, ref, over):
+    """innerPreconditioner = jacobi (the cheap smoother north_star names; not a reference configuration): same space-time
+    errors as every other preconditioner, iteration counts within +-1 per solve of the oracle's run."""
+    import dealii_stfem_b200 as st
+    from golden_util import load
+    pj = dict(load("tp_01")["params"][name], innerPreconditioner="jacobi", **over)
+    p = st.parse_parameters(pj, dim)
+    prob = st.HeatWaveProblem(ctx, p, dim, ref, p["feDegree"])
+    its = [prob.step() for _ in range(2)]
+    row = prob.row()
+    infos = [prob.mg.level_info(l) for l in range(prob.mg.n_levels)]
+    prob.close()
+    assert all(i["patch_matrices"] == 0 for i in infos)             # no Vanka patches were built
+    o = tp_01.convergence_test(tp_01.parse_parameters(pj, dim), dim, ref, p["feDegree"], mg_dtype=np.float32, max_steps=2,
+                               return_state=True)
+    assert abs(row["l2"] - o["l2"]) <= 1e-9 * o["l2"]
+    for a, b in zip(its, o["iterations_per_solve"]):
+        assert abs(a - b) <= 1, (its, o["iterations_per_solve"])
