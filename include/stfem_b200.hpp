@@ -5,7 +5,7 @@
 //   stfem::BlockVector<Number>   ~ BlockVectorT<Number>                 (reference include/types.h:20-23)
 //   stfem::SystemMatrix<Number>  ~ SystemMatrix<dim,Number,...>         (include/operators.h:516-663)
 //        vmult(dst, src), Tvmult(dst, src), vmult_slice_add(dst, src), vmult_slice(dst, src),
-//        initialize_dof_vector(vec), m(), n()
+//        initialize_dof_vector(vec), m(), n(), get_matrix_diagonal()
 //   stfem::GMG                   ~ GMG<dim,Number,LevelMatrixType>      (include/stmg.h:1047-1344)  vmult(dst, src)
 //   stfem::SolverFGMRES          ~ dealii::SolverFGMRES + ReductionControl  (include/time_integrators.h:56-59)
 //        solve(matrix, x, rhs, preconditioner)
@@ -15,6 +15,7 @@
 #ifndef STFEM_B200_HPP
 #define STFEM_B200_HPP
 
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -144,6 +145,19 @@ namespace stfem
     std::vector<void *> ptrs_;
   };
 
+  // dealii::DiagonalMatrix<BlockVectorType> as returned by get_matrix_diagonal: access to the vector of entries
+  template <typename Number>
+  class DiagonalMatrix
+  {
+  public:
+    BlockVector<Number>       &get_vector() { return v_; }
+    const BlockVector<Number> &get_vector() const { return v_; }
+    long long                  m() const { return v_.size(); }
+
+  private:
+    BlockVector<Number> v_;
+  };
+
   // A = Alpha (x) K + Beta (x) M  with K, M the matrix-free Laplace / mass operators of FE_Q(degree)
   template <typename Number>
   class SystemMatrix
@@ -183,6 +197,14 @@ namespace stfem
     void initialize_dof_vector(BlockVectorType &vec, unsigned n_blocks) const { vec.reinit(mesh_.context(), n_blocks, m()); }
     long long  m() const { return stfem_op_n_dofs_per_block(h_); }
     long long  n() const { return m(); }
+    // diag_i = Alpha(i,i) diag K + Beta(i,i) diag M   (operators.h:613-625)
+    std::shared_ptr<DiagonalMatrix<Number>> get_matrix_diagonal() const
+    {
+      auto d = std::make_shared<DiagonalMatrix<Number>>();
+      initialize_dof_vector(d->get_vector());
+      check(stfem_op_diagonal(h_, d->get_vector().data()));
+      return d;
+    }
     stfem_op_t handle() const { return h_; }
 
   private:
@@ -199,6 +221,7 @@ namespace stfem
     double       relaxation                       = 0.0;
     bool         restrict_is_transpose_prolongate = true;
     bool         variable                         = true;
+    int          inner_preconditioner             = 0; // 0 PreconditionVanka (reference), 1 point-Jacobi (not a reference option)
   };
 
   // Space-time multigrid preconditioner; level matrices coarse -> fine, all of one precision
@@ -227,6 +250,7 @@ namespace stfem
       d.eig_n_iterations                 = (int)data.smoothing_eig_cg_n_iterations;
       d.variable                         = data.variable;
       d.restrict_is_transpose_prolongate = data.restrict_is_transpose_prolongate;
+      d.inner_preconditioner             = data.inner_preconditioner;
       check(stfem_mg_create(ctx.handle(), &d, &h_));
     }
     ~GMG() { stfem_mg_destroy(h_); }

@@ -73,6 +73,18 @@ int main(int argc, char **argv)
         }
       std::printf("N %lld nb %d iterations %u initial %.6e final %.6e rel_residual_inf %.3e launches %lld\n", N, nb, solver.last_step(),
                   solver.initial_value(), solver.last_value(), res / nrm, ctx.launch_count());
+      // get_matrix_diagonal (operators.h:613-625): checksum of the entries for the Python side of the test
+      {
+        auto                diag = A.get_matrix_diagonal();
+        std::vector<double> h((size_t)A.m());
+        double              sum = 0;
+        for (unsigned b = 0; b < diag->get_vector().n_blocks(); ++b)
+          {
+            diag->get_vector().copy_to_host(b, h.data());
+            for (double v : h) sum += v;
+          }
+        std::printf("diagonal_sum %.15e\n", sum);
+      }
       // error path: a non-square operator must be rejected by vmult like the reference's dimension Assert
       stfem::SystemMatrix<double> S(fine, degree, nb, 1, Gamma.data(), Zeta.data());
       bool                        threw = false;

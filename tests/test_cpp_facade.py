@@ -48,4 +48,8 @@ def test_facade_matches_oracle(tmp_path):
     y = np.fromfile(out, dtype=np.float64).reshape(nb, N)
     assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12
     assert 1 <= its <= 40 and res < 1e-9
+    md = re.search(r"diagonal_sum (\S+)", r.stdout)
+    assert md, r.stdout
+    dsum = sysm.get_matrix_diagonal().sum()
+    assert abs(float(md.group(1)) - dsum) <= 1e-11 * abs(dsum)
     assert "non-square vmult rejected: yes" in r.stdout
