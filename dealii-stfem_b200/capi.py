@@ -277,7 +277,8 @@ class MgDesc(C.Structure):
                 ("smoother_types", C.POINTER(C.c_int)), ("time_type", C.c_int), ("n_timesteps_at_once", C.c_int),
                 ("poly_time_sequence", C.POINTER(C.c_int)), ("n_poly_time", C.c_int), ("smoothing_steps", C.c_int),
                 ("relaxation", C.c_double), ("smoothing_range", C.c_double), ("eig_n_iterations", C.c_int),
-                ("variable", C.c_int), ("restrict_is_transpose_prolongate", C.c_int), ("inner_preconditioner", C.c_int)]
+                ("variable", C.c_int), ("restrict_is_transpose_prolongate", C.c_int), ("inner_preconditioner", C.c_int),
+                ("vanka_storage", C.c_int)]
 
 
 class Multigrid:
@@ -285,8 +286,9 @@ class Multigrid:
 
     def __init__(self, ctx, level_ops, mg_type_level, smoother_types, time_type, n_timesteps_at_once, poly_time_sequence,
                  smoothing_steps=1, relaxation=0.0, smoothing_range=1.0, eig_n_iterations=20, variable=True,
-                 restrict_is_transpose_prolongate=True, inner_preconditioner="vanka"):
-        """inner_preconditioner: "vanka" (PreconditionVanka, the reference) or "jacobi" (point-Jacobi, diagonal inverse)."""
+                 restrict_is_transpose_prolongate=True, inner_preconditioner="vanka", vanka_storage="level"):
+        """inner_preconditioner: "vanka" (PreconditionVanka, the reference) or "jacobi" (point-Jacobi, diagonal inverse).
+        vanka_storage: "level" (patch inverses in the level precision) or "half" (FP16, dense patches only)."""
         self.ctx, self.ops = ctx, list(level_ops)
         nl = len(self.ops)
         d = MgDesc()
@@ -305,6 +307,7 @@ class Multigrid:
         d.eig_n_iterations, d.variable = eig_n_iterations, int(variable)
         d.restrict_is_transpose_prolongate = int(restrict_is_transpose_prolongate)
         d.inner_preconditioner = {"vanka": 0, "jacobi": 1}[inner_preconditioner]
+        d.vanka_storage = {"level": 0, "half": 1}[vanka_storage]
         self.h = C.c_void_p()
         check(lib().stfem_mg_create(ctx.h, C.byref(d), C.byref(self.h)))
 

@@ -31,6 +31,8 @@ int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out)
   o.restrict_is_transpose_prolongate = desc->restrict_is_transpose_prolongate != 0;
   STFEM_REQUIRE(desc->inner_preconditioner == 0 || desc->inner_preconditioner == 1, "stfem_mg_create: inner_preconditioner must be 0 or 1");
   o.inner_preconditioner = desc->inner_preconditioner;
+  STFEM_REQUIRE(desc->vanka_storage == 0 || desc->vanka_storage == 1, "stfem_mg_create: vanka_storage must be 0 or 1");
+  o.vanka_storage = desc->vanka_storage;
   STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
   auto mg         = std::make_unique<stfem_mg>();
   mg->number_type = ops[0]->number_type;

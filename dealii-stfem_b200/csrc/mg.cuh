@@ -95,6 +95,7 @@ namespace stfem
     int    eig_n_iterations = 20;
     bool   variable = true, restrict_is_transpose_prolongate = true;
     int    inner_preconditioner = 0; // 0 PreconditionVanka (the reference, stmg.h:1055-1063), 1 point-Jacobi
+    int    vanka_storage = 0;        // 0 level precision (the reference: float), 1 FP16 (dense patch inverses only)
   };
 
   struct MGBase
@@ -435,7 +436,7 @@ namespace stfem
           else if (lv.smoother != 0)
             {
               lv.vanka = std::make_unique<Vanka<T>>();
-              STFEM_FORWARD(lv.vanka->setup(lv.op));
+              STFEM_FORWARD(lv.vanka->setup(lv.op, opt.vanka_storage == 1));
             }
           if (l > 0)
             {

@@ -8,6 +8,8 @@
 // (nb*n_c)^2 inverses come from a batched Gauss-Jordan kernel in double precision, and on Cartesian meshes
 // with constant coefficients only the <= 3^dim distinct patches are stored (the reference stores one per cell).
 #pragma once
+#include <cuda_fp16.h>
+#include <cstdlib>
 #include "op.hpp"
 #include "vanka_fd.cuh"
 #include "vec.cuh"
@@ -297,11 +299,120 @@ namespace stfem
       }
   }
 
+  // ---- FP16 storage of the dense patch inverses (opt-in: stfem_mg_desc::vanka_storage = 1 or STFEM_VANKA_HALF=1).  k_vanka_apply streams (nb n_c)^2 numbers per cell and application — it is bound by HBM on
+  //      the inverses — so halving their size is the lever.  Every matrix is normalised by its largest
+  //      entry (patch inverses reach 1/(h^d tau), far outside the FP16 range) and stored [column][ld] with ld even, so that
+  //      a thread owns two rows and reads them as one __half2; products are accumulated in FP32.  Entry-wise relative error
+  //      2^-11: the smoother changes in the fourth digit, FGMRES iteration counts stay within +-1 (tests).
+  template <typename T>
+  __global__ void k_vanka_to_half(int nrow, int ld, const T *__restrict__ invT, __half *__restrict__ invH, float *__restrict__ mscale)
+  {
+    const T     *A = invT + (size_t)blockIdx.x * nrow * nrow;
+    __half      *H = invH + (size_t)blockIdx.x * nrow * ld;
+    __shared__ float red[32];
+    float        m = 0.f;
+    for (int i = threadIdx.x; i < nrow * nrow; i += blockDim.x) m = fmaxf(m, fabsf((float)A[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32)
+      {
+        float v = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (threadIdx.x == 0) red[0] = v;
+      }
+    __syncthreads();
+    m               = red[0];
+    const float inv = m > 0.f ? 1.f / m : 0.f;
+    for (int i = threadIdx.x; i < nrow * ld; i += blockDim.x)
+      {
+        const int cc = i / ld, r = i - cc * ld;
+        H[i]         = __float2half_rn(r < nrow ? (float)A[(size_t)cc * nrow + r] * inv : 0.f);
+      }
+    if (threadIdx.x == 0) mscale[blockIdx.x] = m;
+  }
+
+  // dst += scale * R_c^T B_c^-1 R_c src with the FP16 inverses: one CTA per cell, one thread per PAIR of patch rows
+  template <typename T>
+  __global__ void k_vanka_apply_half(VankaApplyArgs a, int ld, const __half *__restrict__ invH, const float *__restrict__ mscale,
+                                     const T *__restrict__ src, T *__restrict__ dst, T scale)
+  {
+    extern __shared__ __align__(16) unsigned char vk_smem[];
+    float    *x  = reinterpret_cast<float *>(vk_smem);
+    const int n1 = a.n1, k = n1 - 1, dim = a.dim;
+    const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+    const int nrow = a.nb * nc, ld2 = ld >> 1;
+    for (long long cell = blockIdx.x; cell < a.n_cells; cell += gridDim.x)
+      {
+        const int c[3] = {(int)(cell % a.n[0]), (int)((cell / a.n[0]) % a.n[1]), dim == 3 ? (int)(cell / ((long long)a.n[0] * a.n[1])) : 0};
+        long long mat  = cell;
+        if (a.dedup)
+          {
+            int t = 0, mul = 1;
+            for (int d = 0; d < dim; ++d)
+              {
+                const int cls = a.n[d] == 1 ? 0 : (c[d] == 0 ? 0 : (c[d] == a.n[d] - 1 ? 2 : 1));
+                t += cls * mul;
+                mul *= 3;
+              }
+            mat = a.type_to_mat[t];
+          }
+        const __half2 *Bm = reinterpret_cast<const __half2 *>(invH + (size_t)mat * nrow * ld);
+        const float    ms = mscale[mat] * (float)scale;
+        __syncthreads();
+        for (int r = threadIdx.x; r < nrow; r += blockDim.x)
+          {
+            const int b = r / nc, l = r % nc;
+            const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
+            const long long gi = (long long)(c[0] * k + li[0]) + (long long)a.np[0] * ((c[1] * k + li[1]) + (long long)a.np[1] * (c[2] * k + li[2]));
+            x[r] = (float)src[(size_t)b * a.N + gi];
+          }
+        __syncthreads();
+        for (int t = threadIdx.x; 2 * t < nrow; t += blockDim.x)
+          {
+            float          s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const __half2 *col = Bm + t;
+            int            cc  = 0;
+#pragma unroll 4
+            for (; cc + 1 < nrow; cc += 2)
+              {
+                const float2 f0 = __half22float2(col[(size_t)cc * ld2]);
+                const float2 f1 = __half22float2(col[(size_t)(cc + 1) * ld2]);
+                const float  x0 = x[cc], x1 = x[cc + 1];
+                s0 += f0.x * x0;
+                s1 += f0.y * x0;
+                s2 += f1.x * x1;
+                s3 += f1.y * x1;
+              }
+            if (cc < nrow)
+              {
+                const float2 f0 = __half22float2(col[(size_t)cc * ld2]);
+                s0 += f0.x * x[cc];
+                s1 += f0.y * x[cc];
+              }
+            const float v[2] = {(s0 + s2) * ms, (s1 + s3) * ms};
+            for (int e = 0; e < 2; ++e)
+              {
+                const int r = 2 * t + e;
+                if (r >= nrow) break;
+                const int b = r / nc, l = r % nc;
+                const int li[3] = {l % n1, (l / n1) % n1, dim == 3 ? l / (n1 * n1) : 0};
+                const long long gi = (long long)(c[0] * k + li[0]) + (long long)a.np[0] * ((c[1] * k + li[1]) + (long long)a.np[1] * (c[2] * k + li[2]));
+                atomicAdd(dst + (size_t)b * a.N + gi, (T)v[e]);
+              }
+          }
+      }
+  }
+
+
   template <typename T>
   struct Vanka
   {
     stfem_op      *op = nullptr;
     T             *d_invT = nullptr;
+    __half        *d_invH = nullptr;  // FP16 storage of the inverses (normalised per matrix), [mat][column][ld]
+    float         *d_mscale = nullptr;
+    int            ld_half = 0;
     long long      n_mat = 0;
     int            nrow = 0;
     VankaApplyArgs args;
@@ -314,10 +425,12 @@ namespace stfem
     ~Vanka()
     {
       if (d_invT) cudaFree(d_invT);
+      if (d_invH) cudaFree(d_invH);
+      if (d_mscale) cudaFree(d_mscale);
       if (d_modes) cudaFree(d_modes);
     }
 
-    int setup(stfem_op *op_);
+    int setup(stfem_op *op_, bool half_storage = false);
     int setup_fd();
     template <int N1, int NB>
     int launch_fd(const T *src, T *dst, T scale);
@@ -327,9 +440,18 @@ namespace stfem
     {
       stfem_ctx *ctx = op->mesh->ctx;
       if (fd) return apply_fd(src.d, dst.d, scale);
-      const int threads = nrow < 64 ? 64 : (nrow > 256 ? 256 : ((nrow + 31) / 32) * 32);
       const long long cap = (long long)ctx->sm_count * 16;
       const int grid = (int)(args.n_cells < cap ? args.n_cells : cap);
+      if (d_invH)
+        {
+          const int pairs = (nrow + 1) / 2;
+          const int th    = pairs < 32 ? 32 : (pairs > 256 ? 256 : ((pairs + 31) / 32) * 32);
+          k_vanka_apply_half<T><<<grid, th, sizeof(float) * nrow, ctx->stream>>>(args, ld_half, d_invH, d_mscale, src.d, dst.d, scale);
+          ctx->launches++;
+          STFEM_CUDA_CHECK(cudaGetLastError());
+          return STFEM_OK;
+        }
+      const int threads = nrow < 64 ? 64 : (nrow > 256 ? 256 : ((nrow + 31) / 32) * 32);
       k_vanka_apply<T><<<grid, threads, sizeof(T) * nrow, ctx->stream>>>(args, d_invT, src.d, dst.d, scale);
       ctx->launches++;
       STFEM_CUDA_CHECK(cudaGetLastError());
@@ -346,7 +468,7 @@ namespace stfem
   int metric_double(stfem_op *op, double **out); // capi_op.cu: double metric incl. per-q coefficient (caller frees)
 
   template <typename T>
-  int Vanka<T>::setup(stfem_op *op_)
+  int Vanka<T>::setup(stfem_op *op_, bool half_storage)
   {
     op = op_;
     stfem_mesh *m   = op->mesh;
@@ -453,6 +575,20 @@ namespace stfem
     STFEM_REQUIRE(info == 0, "Vanka: singular patch matrix (patch %d)", info - 1);
     args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
     for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }
+    static const bool env_half = std::getenv("STFEM_VANKA_HALF") != nullptr && std::getenv("STFEM_VANKA_HALF")[0] == '1';
+    if (half_storage || env_half)
+      {
+        ld_half = (nrow + 1) & ~1;
+        STFEM_CUDA_CHECK(cudaMalloc(&d_invH, sizeof(__half) * (size_t)n_mat * nrow * ld_half));
+        STFEM_CUDA_CHECK(cudaMalloc(&d_mscale, sizeof(float) * (size_t)n_mat));
+        k_vanka_to_half<T><<<(unsigned)n_mat, 256, 0, ctx->stream>>>(nrow, ld_half, d_invT, d_invH, d_mscale);
+        ctx->launches++;
+        STFEM_CUDA_CHECK(cudaGetLastError());
+        STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_invT);
+        d_invT = nullptr;
+        bytes  = sizeof(__half) * (size_t)n_mat * nrow * ld_half + sizeof(float) * (size_t)n_mat;
+      }
     return STFEM_OK;
   }
 

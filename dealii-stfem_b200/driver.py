@@ -56,6 +56,7 @@ def default_parameters(dim=2):
         "relativeTolerance": 1.0e-12, "timeRefineOffset": 1, "deltaTime": 0.0,
         "agglomerateBelow": 16,     # multi-GPU only (not a reference key): see HeatWaveProblem
         "innerPreconditioner": "vanka",   # not a reference key: "jacobi" = point-Jacobi inside Relaxation / Chebyshev
+        "vankaStorage": "level",          # not a reference key: "half" = FP16 storage of the dense patch inverses
     }
 
 
@@ -196,7 +197,8 @@ class HeatWaveProblem:
                                  smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
                                  eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
                                  restrict_is_transpose_prolongate=p["restrictIsTransposeProlongate"],
-                                 inner_preconditioner=p.get("innerPreconditioner", "vanka")) if p.get("useMg", True) else None
+                                 inner_preconditioner=p.get("innerPreconditioner", "vanka"),
+                                 vanka_storage=p.get("vankaStorage", "level")) if p.get("useMg", True) else None
         # ---- fine operators (tp_01.cc:121-168)
         fmesh = self.meshes[refinement]
         self.fmesh = fmesh

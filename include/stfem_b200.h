@@ -176,6 +176,9 @@ typedef struct stfem_mg_desc {
   int inner_preconditioner;      /* 0 = PreconditionVanka (the reference, stmg.h:1055-1063); 1 = point-Jacobi: the inverse of
                                     SystemMatrix::get_matrix_diagonal (operators.h:613-625) inside Relaxation / Chebyshev.
                                     Not a reference configuration: the cheap smoother BASELINE.json's north_star names. */
+  int vanka_storage;             /* 0 = patch inverses in the level precision (the reference: float, stmg.h:901);
+                                    1 = FP16, normalised per patch, FP32 accumulation: half the HBM traffic of the dense
+                                    PreconditionVanka::vmult (stmg.h:832-872).  Levels in Kronecker form are unaffected. */
 } stfem_mg_desc;
 
 int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out);

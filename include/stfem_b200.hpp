@@ -222,6 +222,7 @@ namespace stfem
     bool         restrict_is_transpose_prolongate = true;
     bool         variable                         = true;
     int          inner_preconditioner             = 0; // 0 PreconditionVanka (reference), 1 point-Jacobi (not a reference option)
+    int          vanka_storage                    = 0; // 0 level precision (reference), 1 FP16 patch inverses
   };
 
   // Space-time multigrid preconditioner; level matrices coarse -> fine, all of one precision
@@ -251,6 +252,7 @@ namespace stfem
       d.variable                         = data.variable;
       d.restrict_is_transpose_prolongate = data.restrict_is_transpose_prolongate;
       d.inner_preconditioner             = data.inner_preconditioner;
+      d.vanka_storage                    = data.vanka_storage;
       check(stfem_mg_create(ctx.handle(), &d, &h_));
     }
     ~GMG() { stfem_mg_destroy(h_); }

@@ -137,5 +137,24 @@ if get("facade") is not None:
     check("facade diagonal_sum", bool(md) and abs(float(md.group(1)) - dsum) <= 1e-11 * abs(dsum), md.group(1) if md else txt[-300:])
     check("facade rest", "non-square vmult rejected: yes" in txt)
 
+d = get("half") if os.path.exists(os.path.join(OUT, "shot_half.npz")) else None
+if d is not None:
+    o = tp_01.convergence_test(tp_01.parse_parameters(dict(PRACTICAL, problemType="heat"), 3), 3, 1, 1, mg_dtype=np.float32,
+                               max_steps=2, return_state=True)
+    scale = np.abs(o["x"]).max()
+    e = np.abs(d["half_vanka"].astype(np.float64) - d["level_vanka"]).max() / np.abs(d["level_vanka"]).max()
+    check("half: one Vanka application vs float storage", e <= 2e-3, "%.2e" % e)
+    check("half: patch bytes halved", np.all(d["half_bytes"] <= 0.51 * d["level_bytes"] + 1e3), "%s %s" % (d["half_bytes"], d["level_bytes"]))
+    check("half: iterations vs float storage", all(abs(a - b) <= 1 for a, b in zip(d["half_its"], d["level_its"])),
+          "%s vs %s (oracle %s)" % (list(d["half_its"]), list(d["level_its"]), o["iterations_per_solve"]))
+    e = np.abs(d["half_x"] - o["x"]).max() / scale
+    check("half: solution vs oracle", e <= 1e-8, "%.2e" % e)
+d = np.load(os.path.join(OUT, "shot_c4time.npz")) if os.path.exists(os.path.join(OUT, "shot_c4time.npz")) else None
+if d is not None:
+    for storage in ("level", "half"):
+        setup_s, ms, bytes_, s0, s1, i0, i1, ndof = d[storage]
+        print("c4 %-5s: Vanka apply %.3f ms, %.1f MB of inverses -> %.0f GB/s; steps %.1f / %.1f ms, iterations %d / %d, %.3e st-DoF/s"
+              % (storage, ms, bytes_ / 1e6, bytes_ / ms / 1e6, s0, s1, i0, i1, ndof / (s1 * 1e-3)))
+
 print("FAILED: %s" % FAILED if FAILED else "all checks passed")
 sys.exit(1 if FAILED else 0)

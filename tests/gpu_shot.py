@@ -186,5 +186,86 @@ if want("facade"):
         assert r.returncode == 0, r.stdout + r.stderr
         return {"ok": np.array(1)}
 
+if want("half"):
+    @section("half")
+    def _():
+        # FP16 storage of the dense patch inverses against the level-precision storage: one Vanka application on the
+        # finest level (random input) and the first two solves of practical01 (3D heat)
+        out = {}
+        for storage in ("level", "half"):
+            pj = dict(PRACTICAL, problemType="heat", vankaStorage=storage)
+            p = st.parse_parameters(pj, 3)
+            prob = st.HeatWaveProblem(ctx, p, 3, 1, 1)
+            lop = prob.level_ops[-1]
+            xin = np.stack([np.random.RandomState(11 + b).uniform(-1, 1, lop.n) for b in range(lop.nb_rows)]).astype(np.float32)
+            dx, dy = lop.new_vector().upload(xin), lop.new_vector()
+            prob.mg.level_apply(prob.mg.n_levels - 1, 0, dy, dx)
+            out[storage + "_vanka"] = dy.download()
+            out[storage + "_bytes"] = np.array([prob.mg.level_info(l)["patch_bytes"] for l in range(prob.mg.n_levels)])
+            dx.free(); dy.free()
+            out[storage + "_its"] = np.array([prob.step() for _ in range(2)])
+            out[storage + "_x"] = prob.x.download()
+            prob.close()
+            log("half section:", storage, out[storage + "_its"])
+        return out
+
+if want("c4time"):
+    @section("c4time")
+    def _():
+        # BASELINE configs[3], practical set-up (scripts/solve_c4.py), refinement 3: time of one dense Vanka application on
+        # the finest level (CUDA events on the library stream, 20 launches) and of the first two time steps
+        out = {}
+        ref, k, r = 3, 3, 2
+
+        def vertices(n_cells):
+            n = [c + 1 for c in n_cells]
+            g = [np.linspace(-1.0, 1.0, m) for m in n]
+            V = np.stack(np.meshgrid(g[2], g[1], g[0], indexing="ij")[::-1], axis=-1)
+            d = np.random.RandomState(1).uniform(-1, 1, V.shape) * 0.15 * (2.0 / n_cells[0])
+            d[0] = d[-1] = 0
+            d[:, 0] = d[:, -1] = 0
+            d[:, :, 0] = d[:, :, -1] = 0
+            return V + d
+
+        V = vertices([5 << ref] * 3).reshape(-1, 3)
+        src_pt = [float(c) for c in V[np.argmin(np.sum(V * V, axis=1))]]
+        for storage in ("level", "half"):
+            pj = {"timeType": "DG", "problemType": "heat", "feDegree": r, "refinement": ref, "subdivisions": "5,5,5",
+                  "hyperRectLowerLeft": "-1,-1,-1", "hyperRectUpperRight": "1,1,1", "mgTimeBeforeSpace": "true",
+                  "spaceTimeConvergenceTest": "false", "distortGrid": 0.15, "distortCoeff": "0.6", "extrapolate": "false",
+                  "vankaStorage": storage}
+            p = st.parse_parameters(pj, 3)
+            p["sourcePoint"] = src_pt
+            t = time.time()
+            prob = st.HeatWaveProblem(ctx, p, 3, ref, r, space_degree=k, vertices_fn=vertices)
+            ctx.synchronize()
+            setup_s = time.time() - t
+            l = prob.mg.n_levels - 1
+            lop = prob.level_ops[-1]
+            xin = np.stack([np.random.RandomState(11 + b).uniform(-1, 1, lop.n) for b in range(lop.nb_rows)]).astype(np.float32)
+            dx, dy = lop.new_vector().upload(xin), lop.new_vector()
+            for _ in range(3):
+                prob.mg.level_apply(l, 0, dy, dx)
+            ctx.synchronize()
+            ctx.timer_start()
+            for _ in range(20):
+                prob.mg.level_apply(l, 0, dy, dx)
+            ms = ctx.timer_stop() / 20.0
+            dx.free(); dy.free()
+            steps = []
+            its = []
+            for _ in range(2):
+                ctx.synchronize()
+                t = time.perf_counter()
+                its.append(prob.step(evaluate_error=False))
+                ctx.synchronize()
+                steps.append((time.perf_counter() - t) * 1e3)
+            bytes_ = prob.mg.level_info(l)["patch_bytes"]
+            out[storage] = np.array([setup_s, ms, bytes_, steps[0], steps[1], its[0], its[1], prob.n * prob.nb])
+            log("c4time %s: setup %.2fs, level_apply(Vanka) %.3f ms for %.1f MB of inverses (%.0f GB/s incl. 2 vector copies + memset), "
+                "steps %.1f / %.1f ms, iterations %s" % (storage, setup_s, ms, bytes_ / 1e6, bytes_ / ms / 1e6, steps[0], steps[1], its))
+            prob.close()
+        return out
+
 ctx.close()
 log("done")

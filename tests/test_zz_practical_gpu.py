@@ -178,3 +178,31 @@ def test_point_jacobi_smoother_matches_oracle(ctx, name, dim, ref, over):
     assert abs(row["l2"] - o["l2"]) <= 1e-9 * o["l2"]
     for a, b in zip(its, o["iterations_per_solve"]):
         assert abs(a - b) <= 1, (its, o["iterations_per_solve"])
+
+
+def test_half_precision_patch_inverses(ctx):
+    """stfem_mg_desc::vanka_storage = 1 (driver key vankaStorage = half): the dense patch inverses in FP16, normalised per
+    patch, FP32 accumulation.  One Vanka application agrees with the float storage to 2e-3, the storage halves, the solve
+    needs the same number of FGMRES iterations (+-1) and converges to the oracle's solution."""
+    import dealii_stfem_b200 as st
+    res = {}
+    for storage in ("level", "half"):
+        pj = dict(PRACTICAL, problemType="heat", vankaStorage=storage)
+        prob = st.HeatWaveProblem(ctx, st.parse_parameters(pj, 3), 3, 1, 1)
+        lop = prob.level_ops[-1]
+        xin = np.stack([np.random.RandomState(11 + b).uniform(-1, 1, lop.n) for b in range(lop.nb_rows)]).astype(np.float32)
+        dx, dy = lop.new_vector().upload(xin), lop.new_vector()
+        prob.mg.level_apply(prob.mg.n_levels - 1, 0, dy, dx)
+        vk = dy.download().astype(np.float64)
+        nbytes = np.array([prob.mg.level_info(l)["patch_bytes"] for l in range(prob.mg.n_levels)])
+        dx.free(); dy.free()
+        its = [prob.step() for _ in range(2)]
+        res[storage] = (vk, nbytes, its, prob.x.download())
+        prob.close()
+    assert np.abs(res["half"][0] - res["level"][0]).max() <= 2e-3 * np.abs(res["level"][0]).max()
+    assert np.all(res["half"][1] <= 0.51 * res["level"][1] + 1e3) and np.all(res["half"][1] > 0)
+    for a, b in zip(res["half"][2], res["level"][2]):
+        assert abs(a - b) <= 1, (res["half"][2], res["level"][2])
+    o = tp_01.convergence_test(tp_01.parse_parameters(dict(PRACTICAL, problemType="heat"), 3), 3, 1, 1, mg_dtype=np.float32,
+                               max_steps=2, return_state=True)
+    assert np.abs(res["half"][3] - o["x"]).max() <= 1e-8 * np.abs(o["x"]).max()
