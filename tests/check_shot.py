@@ -144,7 +144,7 @@ if d is not None:
     scale = np.abs(o["x"]).max()
     e = np.abs(d["half_vanka"].astype(np.float64) - d["level_vanka"]).max() / np.abs(d["level_vanka"]).max()
     check("half: one Vanka application vs float storage", e <= 2e-3, "%.2e" % e)
-    check("half: patch bytes halved", np.all(d["half_bytes"] <= 0.51 * d["level_bytes"] + 1e3), "%s %s" % (d["half_bytes"], d["level_bytes"]))
+    check("half: patch bytes halved", np.all(d["half_bytes"] <= 0.55 * d["level_bytes"]), "%s %s" % (d["half_bytes"], d["level_bytes"]))
     check("half: iterations vs float storage", all(abs(a - b) <= 1 for a, b in zip(d["half_its"], d["level_its"])),
           "%s vs %s (oracle %s)" % (list(d["half_its"]), list(d["level_its"]), o["iterations_per_solve"]))
     e = np.abs(d["half_x"] - o["x"]).max() / scale

@@ -200,7 +200,8 @@ def test_half_precision_patch_inverses(ctx):
         res[storage] = (vk, nbytes, its, prob.x.download())
         prob.close()
     assert np.abs(res["half"][0] - res["level"][0]).max() <= 2e-3 * np.abs(res["level"][0]).max()
-    assert np.all(res["half"][1] <= 0.51 * res["level"][1] + 1e3) and np.all(res["half"][1] > 0)
+    # odd patch sizes are padded to even, plus one scale factor per patch
+    assert np.all(res["half"][1] <= 0.55 * res["level"][1]) and np.all(res["half"][1] > 0)
     for a, b in zip(res["half"][2], res["level"][2]):
         assert abs(a - b) <= 1, (res["half"][2], res["level"][2])
     o = tp_01.convergence_test(tp_01.parse_parameters(dict(PRACTICAL, problemType="heat"), 3), 3, 1, 1, mg_dtype=np.float32,
