@@ -134,3 +134,30 @@ def test_time_evaluation_matrix_matches_oracle(ttype, r):
     assert M.shape == (samples, r + 1)
     assert np.allclose(M, tp_01.time_evaluation_matrix(ttype, r, samples), rtol=0, atol=1e-13)
     assert np.allclose(M.sum(axis=1), 1.0)          # partition of unity
+
+
+@pytest.mark.parametrize("grid", [[2, 1, 1], [2, 2, 1], [2, 2, 2]])
+def test_coefficient_and_initial_value_on_partition_bricks(grid):
+    """Multi-GPU runs (one brick of the box partition per rank, stfem_partition_brick): evaluating the coefficient table and
+    the cut-off initial value on a rank's brick (local box, GLOBAL coefficient grid / source point) gives exactly the
+    slice of the global arrays that the brick covers — what HeatWaveProblem does for partition != None."""
+    from dealii_stfem_b200 import dist
+    dim, degree, sub, ref, dc = 3, 2, [5, 5, 5], 1, 0.6
+    lo, up = [-1.0] * 3, [1.0] * 3
+    n = [s << ref for s in sub]
+    nq = (degree + 1) ** 3
+    glob = ph.coefficient_at_qpoints(n, lo, up, degree, sub, lo, up, dc).reshape(n[2], n[1], n[0], nq)
+    center = [0.0, 0.0, 0.0]
+    u0 = ph.cutoff_cinfty_interpolate(n, lo, up, degree, center, radius=0.3).reshape([degree * m + 1 for m in n][::-1])
+    covered = np.zeros(n[::-1], bool)
+    for rank in range(int(np.prod(grid))):
+        coords = dist.coords_of(rank, grid)
+        n_loc, off, llo, lup, _ = dist.partition_brick(n, lo, up, grid, coords)
+        loc = ph.coefficient_at_qpoints(n_loc, llo, lup, degree, sub, lo, up, dc).reshape(n_loc[2], n_loc[1], n_loc[0], nq)
+        sl = tuple(slice(off[a], off[a] + n_loc[a]) for a in (2, 1, 0))
+        assert np.array_equal(loc, glob[sl])
+        covered[sl] = True
+        u_loc = ph.cutoff_cinfty_interpolate(n_loc, llo, lup, degree, center, radius=0.3).reshape([degree * m + 1 for m in n_loc][::-1])
+        sln = tuple(slice(degree * off[a], degree * (off[a] + n_loc[a]) + 1) for a in (2, 1, 0))
+        assert np.allclose(u_loc, u0[sln], rtol=1e-12, atol=1e-14)          # brick coordinates are lower + h*(c + xi)
+    assert covered.all()
