@@ -13,6 +13,9 @@ Prints ONE JSON line (rank 0).  `value` = space-time DoFs/s with inputs resident
 the library's stream, max over ranks); `e2e` = the same metric through the C-ABI entry point with
 pinned HOST buffers (H2D + kernel + D2H inside the timed region); `roofline`, `cpu_baseline`,
 `clocks`, `gpu_launches` as the contract asks.  torch is used for torch.distributed plumbing only.
+Extra objects on the same line (N=1): `perturbed_mesh` (general-geometry kernel), `solve` (STMG-FGMRES time steps of
+configs[1]) and `practical_c4` (configs[3]: heterogeneous coefficient, perturbed mesh, dense cell-patch smoother, with the
+patch inverses in float and in FP16).
 """
 import argparse
 import json
@@ -197,6 +200,65 @@ def solve_leg(st, ctx, refinement, n_steps=3, grid=None, coords=None, reduce_max
     return out
 
 
+def practical_leg(st, ctx, refinement=3, n_steps=2):
+    """BASELINE configs[3] in the reference's practical set-up (tests/json/practical01.json + run_practical.sh): 3D heat,
+    Q3 x DG(2), box [-1,1]^3 with 5 subdivisions, perturbed mesh (0.15), Coefficient<dim> table (distortCoeff 0.6) on K on
+    every level, cut-off initial value, zero source; relaxation smoother around the DENSE cell-patch Vanka (one inverse
+    per cell).  Reported for the patch inverses in the level precision (float, what the reference stores) and in FP16."""
+    k, r = 3, 2
+
+    def vertices(n_cells):
+        n = [c + 1 for c in n_cells]
+        g = [np.linspace(-1.0, 1.0, m) for m in n]
+        V = np.stack(np.meshgrid(g[2], g[1], g[0], indexing="ij")[::-1], axis=-1)
+        d = np.random.RandomState(1).uniform(-1, 1, V.shape) * 0.15 * (2.0 / n_cells[0])
+        d[0] = d[-1] = 0
+        d[:, 0] = d[:, -1] = 0
+        d[:, :, 0] = d[:, :, -1] = 0
+        return V + d
+
+    V = vertices([5 << refinement] * 3).reshape(-1, 3)
+    source = [float(c) for c in V[np.argmin(np.sum(V * V, axis=1))]]     # the displaced vertex next to the origin
+    out = {"metric": "space-time DoFs/s, STMG-FGMRES solve of configs[3] (3D heat, Q3 x DG(2), perturbed mesh, heterogeneous "
+                     "coefficient, dense cell-patch smoother)", "unit": UNIT}
+    for storage in ("level", "half"):
+        pj = {"timeType": "DG", "problemType": "heat", "feDegree": r, "refinement": refinement, "subdivisions": "5,5,5",
+              "hyperRectLowerLeft": "-1,-1,-1", "hyperRectUpperRight": "1,1,1", "mgTimeBeforeSpace": "true",
+              "spaceTimeConvergenceTest": "false", "distortGrid": 0.15, "distortCoeff": "0.6", "extrapolate": "false",
+              "vankaStorage": storage}
+        p = st.parse_parameters(pj, 3)
+        p["sourcePoint"] = source
+        t0 = time.perf_counter()
+        prob = st.HeatWaveProblem(ctx, p, 3, refinement, r, space_degree=k, vertices_fn=vertices)
+        ctx.synchronize()
+        setup_s = time.perf_counter() - t0
+        level = prob.mg.n_levels - 1
+        lop = prob.level_ops[-1]
+        dx, dy = lop.new_vector(), lop.new_vector()
+        dx.upload(np.sin(0.1 * np.arange(lop.n)[None, :] + np.arange(lop.nb_rows)[:, None]).astype(np.float32))
+        for _ in range(3):
+            prob.mg.level_apply(level, 0, dy, dx)
+        ctx.timer_start()
+        for _ in range(10):
+            prob.mg.level_apply(level, 0, dy, dx)
+        vanka_ms = ctx.timer_stop() / 10.0
+        dx.free(); dy.free()
+        its = [prob.step(evaluate_error=False)]        # warm-up step
+        ctx.synchronize()
+        ctx.timer_start()
+        for _ in range(n_steps):
+            its.append(prob.step(evaluate_error=False))
+        ms = ctx.timer_stop() / n_steps
+        patch_bytes = prob.mg.level_info(level)["patch_bytes"]
+        dofs = prob.n * prob.nb
+        out[storage] = {"value": dofs / (ms * 1e-3), "ms_per_solve": ms, "fgmres_iterations_per_solve": its[1:], "st_dofs": dofs,
+                        "cells": int(np.prod(prob.n_cells)), "levels": "".join(prob.mg_type_level), "setup_s": setup_s,
+                        "vanka_apply_ms": vanka_ms, "patch_inverse_bytes": patch_bytes,
+                        "vanka_apply_GBs": patch_bytes / (vanka_ms * 1e-3) / 1e9}
+        prob.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +270,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the STMG-FGMRES solve leg")
     ap.add_argument("--no-perturbed", action="store_true", help="skip the perturbed-mesh operator leg")
+    ap.add_argument("--no-practical", action="store_true", help="skip the configs[3] (practical set-up, dense Vanka) leg")
     ap.add_argument("--solve-refinement", type=int, default=5, help="solve leg: subdivisions 3, this many refinements (5 = 96^3 cells)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -362,6 +425,11 @@ def main():
             return float(tt.item())
 
         line["solve"] = solve_leg(st, ctx, args.solve_refinement, grid=grid, coords=coords, reduce_max=reduce_max)
+    if world == 1 and not args.no_practical and not args.no_solve:
+        try:
+            line["practical_c4"] = practical_leg(st, ctx)
+        except Exception as e:                      # an extra leg must never cost the headline line
+            line["practical_c4"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, ms, threads, ndofs = cpu_reference_run(CPU_SAMPLE_CELLS, 3, 1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
