@@ -763,6 +763,11 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
   op->number_type = desc->number_type;
   op->nb_rows     = desc->nb_rows;
   op->nb_cols     = desc->nb_cols;
+  // 31-34 are timing-only ablation builds of the Cartesian kernel (parts of the algorithm removed: WRONG results).
+  // They stay out of reach of normal callers: an explicit opt-in through the environment is required.
+  STFEM_REQUIRE(desc->kernel_variant < 31 || desc->kernel_variant > 34 || std::getenv("STFEM_ALLOW_ABLATION") != nullptr,
+                "stfem_op_create: kernel_variant %d is a timing-only ablation build (wrong results); set STFEM_ALLOW_ABLATION=1 to use it",
+                desc->kernel_variant);
   op->variant     = desc->kernel_variant;
   op->shape       = std::make_unique<ShapeHost>(desc->degree);
   op->N           = 1;

@@ -97,7 +97,7 @@ typedef struct stfem_op_desc {
                                        1 generic q-point kernel; 2 (level operators) dense Vanka patches instead of the
                                        Kronecker form; 11-19, 26-28 launch-bound configurations of the Cartesian kernel;
                                        17 largest-CTA rule; 18, 20-25 software-pipelined persistent kernel; 31-34 ablation
-                                       experiments (WRONG results, timing only); 40-42 cp.async.bulk + mbarrier gather;
+                                       experiments (WRONG results, timing only; rejected unless STFEM_ALLOW_ABLATION is set); 40-42 cp.async.bulk + mbarrier gather;
                                        51 two 8-byte exchange fields instead of 16-byte pairs */
 } stfem_op_desc;
 

@@ -5,6 +5,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("STFEM_ALLOW_ABLATION", "1")     # this tuning tool may time the ablation builds (variants 31-34)
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dealii_stfem_b200 as st  # noqa: E402
 from dealii_stfem_b200 import fe_time_host as ft  # noqa: E402
