@@ -109,6 +109,12 @@ def level_time_weights(ttype, tau, nts, mg_type_level, poly_time, wave):
     return out
 
 
+def format_functional_row(t, values):
+    """One line of the functional file (tp_01.cc:620-630): `setw(16) << scientific << t`, then for every point
+    `setw(16) << scientific << " " << value` — the width applies to the blank, so a value follows 16 blanks."""
+    return "%16s" % ("%.6e" % t) + "".join(" " * 16 + "%.6e" % v for v in values) + "\n"
+
+
 class HeatWaveProblem:
     """One (refinement, degree) run of the reference's convergence_test lambda."""
 
@@ -306,7 +312,7 @@ class HeatWaveProblem:
             for row in range(samples):
                 t_ = self.time + self.tau * (it + row / max(samples - 1.0, 1.0))
                 self.functional_rows.append((t_,) + tuple(res[row]))
-                lines.append("%16s" % ("%.6e" % t_) + "".join(" " * 16 + "%.6e" % v for v in res[row]) + "\n")
+                lines.append(format_functional_row(t_, res[row]))
             lines.append("\n")
             self._prev_pt = vals[(it + 1) * self.nd - 1]
         if self.functional_file:

@@ -143,6 +143,8 @@ def run(params_json, dim, out=sys.stdout, precondition_float=True, ctx=None, max
         rows = []
         for rf in refinements:
             prob = HeatWaveProblem(ctx, p, dim, rf, k, mg_number_type=capi.F32 if precondition_float else capi.F64)
+            if not p["spaceTimeConvergenceTest"]:
+                prob.functional_file = p["functionalFile"]          # appended to like tp_01.cc:620
             row = prob.run(max_steps=max_steps)
             prob.close()
             out.write(run_header(row))

@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""Run the CPU oracle on ALL 96 rows of the reference's tests/tp_01.output (8 parameter files x 3 degrees x 4
+refinements) and report, per row, the three space-time errors against the stored 6-digit values.  The CPU test suite
+only runs the cheap rows (tests/test_oracle_tp01_golden.py); this script is the full sweep (about an hour on 8 cores),
+its log is committed as profiles/r01_oracle_tp01_all_rows.txt.
+
+    python tests/golden/check_all_tp01_rows.py [n_processes] > profiles/r01_oracle_tp01_all_rows.txt
+"""
+import multiprocessing as mp
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run(job):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+
+    from golden_util import load
+    from oracle import tp_01
+    name, di, ref = job
+    G = load("tp_01")
+    p = tp_01.parse_parameters(G["params"][name], 2)
+    gold = G["tables"][name][di]["runs"][ref - p["refinement"]]
+    t0 = time.time()
+    try:
+        r = tp_01.convergence_test(p, 2, ref, p["feDegree"] + di, mg_dtype=np.float32)
+    except Exception as e:                                   # noqa: BLE001
+        return name, di, ref, None, gold, repr(e)[:200], time.time() - t0
+    return name, di, ref, r, gold, "", time.time() - t0
+
+
+def main():
+    nproc = int(sys.argv[1]) if len(sys.argv) > 1 else max(1, (os.cpu_count() or 2) - 2)
+    names = ["tf01", "tf02", "tf03", "tf04", "tf05", "tf06", "tf07", "tf08"]
+    jobs = [(n, d, r) for r in (2, 3, 4, 5) for d in (0, 1, 2) for n in names]       # cheap rows first
+    bad = 0
+    print("# config degree_index refinement | s_dofs t_dofs | L2 (oracle, stored) | max rel. deviation of Linf, L2, H1 | "
+          "iterations (oracle, stored) | seconds", flush=True)
+    with mp.Pool(nproc) as pool:
+        for name, di, ref, r, gold, err, dt in pool.imap_unordered(run, jobs):
+            if r is None:
+                bad += 1
+                print("%s %d %d FAILED %s" % (name, di, ref, err), flush=True)
+                continue
+            dev = max(abs(r[k] - gold[k]) / abs(gold[k]) for k in ("linf", "l2", "h1"))
+            ok = dev <= 6e-6 and r["s_dofs"] == gold["s_dofs"] and r["t_dofs"] == gold["t_dofs"] and r["timesteps"] == gold["timesteps"]
+            bad += 0 if ok else 1
+            print("%s %d %d | %6d %2d | %.5e %.5e | %.1e %s | %4d %4d | %.0f" % (name, di, ref, r["s_dofs"], r["t_dofs"], r["l2"], gold["l2"],
+                                                                                dev, "ok" if ok else "MISMATCH", r["iterations"], gold["iterations"], dt),
+                  flush=True)
+    print("# rows: %d, not reproduced to the 6 printed digits: %d" % (len(jobs), bad), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,3 +56,10 @@ def test_parameter_file_keys():
     assert p["spaceTimeConvergenceTest"] is False and p["functionalFile"] == "practical_01.txt"
     p = st.parse_parameters({"sourcePoint": "0.0,0.0,0.0", "timeType": "DG", "feDegree": "0"}, 3)
     assert p["sourcePoint"] == [0.0, 0.0, 0.0] and p["feDegreeMin"] == 0
+
+
+def test_functional_file_line_format():
+    """tp_01.cc:620-630: time in a 16-wide scientific field, every value after a 16-wide blank field."""
+    from dealii_stfem_b200.driver import format_functional_row
+    ln = format_functional_row(0.0625, [2.229576e-02, -3.5])
+    assert ln == "    6.250000e-02                2.229576e-02                -3.500000e+00\n"
