@@ -80,6 +80,7 @@ SYMBOLS = {
     "stfem_mg_sequence": (C.c_int, [C.c_int] * 5 + [C.c_char] + [C.c_int] * 4 + [C.c_char_p, C.c_int]),
     "stfem_precondition_stmg_types": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "stfem_quadrature_rule": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
+    "stfem_cart_fd_modes": (C.c_int, [C.c_int, _dp, _dp]),
     "stfem_coefficient_distortion": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_double, _dp]),
     "stfem_coefficient_at_qpoints": (C.c_int, [C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, C.c_int, C.POINTER(C.c_int), _dp, _dp,
                                                C.c_double, _dp, _dp]),

@@ -9,6 +9,7 @@
 #include "vec.cuh"
 #include "st_vmult_generic.cuh"
 #include "st_vmult_plane.cuh"
+#include "st_vmult_cart_fd.cuh"
 #include "assemble.cuh"
 
 namespace stfem
@@ -483,12 +484,109 @@ namespace stfem
     return STFEM_OK;
   }
 
+  // EXPERIMENTAL (kernel_variant 60): fast-diagonalisation form of the Cartesian operator, st_vmult_cart_fd.cuh.
+  // Whole-mesh launches with square time matrices only; everything else keeps the default kernel.
+  static void cart_fd_reference_matrices(const ShapeHost &sh, int n1, std::vector<double> &V, std::vector<double> &lam)
+  {
+    std::vector<double> Mh((size_t)n1 * n1), Kh((size_t)n1 * n1);
+    for (int i = 0; i < n1; ++i)
+      for (int j = 0; j < n1; ++j)
+        {
+          long double mm = 0, kk = 0;
+          for (int q = 0; q < n1; ++q)
+            {
+              mm += (long double)sh.wq[q] * sh.S[q * n1 + i] * sh.S[q * n1 + j];
+              kk += (long double)sh.wq[q] * sh.D[q * n1 + i] * sh.D[q * n1 + j];
+            }
+          Mh[i * n1 + j] = (double)mm;
+          Kh[i * n1 + j] = (double)kk;
+        }
+    V.assign((size_t)n1 * n1, 0.0);
+    lam.assign(n1, 0.0);
+    cartfd_host::pencil_modes(Mh.data(), Kh.data(), n1, V.data(), lam.data());
+  }
+
+  template <int N1, int NB, typename T>
+  static int launch_cart_fd(stfem_op *op, void *const *dst, const void *const *src, const void *alpha, const void *beta)
+  {
+    stfem_mesh *m = op->mesh;
+    if (op->fd_V.empty()) cart_fd_reference_matrices(*op->shape, N1, op->fd_V, op->fd_lam);
+    CartFdArgs<T, N1> a;
+    double            h[3], vol = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        h[d] = (m->upper[d] - m->lower[d]) / m->n[d];
+        vol *= h[d];
+        a.n[d]  = m->n[d];
+        a.np[d] = op->np[d];
+      }
+    for (int q = 0; q < N1; ++q)
+      for (int i = 0; i < N1; ++i)
+        {
+          const double v    = op->fd_V[(size_t)q * N1 + i];
+          a.V[q * N1 + i]   = (T)v;
+          a.Vt[i * N1 + q]  = (T)v;
+          a.Vtx[i * N1 + q] = (T)(v * vol);
+        }
+    for (int d = 0; d < 3; ++d)
+      for (int q = 0; q < N1; ++q) a.lam[d][q] = (T)(op->fd_lam[q] / (h[d] * h[d]));
+    a.n_cells = m->n_cells;
+    if (a.n_cells <= 0) return STFEM_OK;
+    STFEM_REQUIRE(a.n_cells < (1ll << 31), "st_vmult: more than 2^31 cells per GPU are not supported");
+    a.dirichlet = m->dirichlet;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
+      {
+        a.src[b] = b < NB ? (const T *)src[b] : nullptr;
+        a.dst[b] = b < NB ? (T *)dst[b] : nullptr;
+      }
+    a.alpha      = (const T *)alpha;
+    a.beta       = (const T *)beta;
+    a.coeff_cell = (const T *)op->d_coeff;
+    const int tpc = NB * N1;
+    int       best = 1;
+    double    best_score = -1;
+    for (int c = 1; c * tpc <= 256; ++c)
+      {
+        const int    thr = c * tpc;
+        const double eff = (double)thr / (((thr + 31) / 32) * 32);
+        const double score = eff >= 0.9 ? 2.0 - 1e-4 * thr : eff; // smallest CTA with well-filled warps (see launch_cart)
+        if (score > best_score + 1e-9) { best_score = score; best = c; }
+      }
+    a.cells_per_cta = best;
+    const size_t smem = (size_t)best * NB * ExchLayout<N1>::CBS * sizeof(T);
+    auto         kern = k_st_vmult_cart_fd<N1, NB, T>;
+    if (smem > 48 * 1024) STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t    stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
+    const long long grid   = (a.n_cells + best - 1) / best;
+    kern<<<(unsigned)grid, best * tpc, smem, stream>>>(a);
+    m->ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
+  // STFEM_ERR_UNSUPPORTED = this (degree, blocks) pair is not instantiated: the caller falls back to the default kernel
+  template <typename T>
+  static int launch_cart_fd_any(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta)
+  {
+    const int n1 = op->degree + 1;
+#define STFEM_CFD_CASE(N1_, NB_) \
+  if (n1 == N1_ && nb == NB_) return launch_cart_fd<N1_, NB_, T>(op, dst, src, alpha, beta);
+    STFEM_CFD_CASE(3, 2) STFEM_CFD_CASE(3, 3) STFEM_CFD_CASE(4, 2) STFEM_CFD_CASE(4, 3) STFEM_CFD_CASE(5, 2) STFEM_CFD_CASE(5, 3)
+#undef STFEM_CFD_CASE
+    return STFEM_ERR_UNSUPPORTED;
+  }
+
   template <int DIM, typename T>
   static int dispatch_degree(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst,
                              const void *alpha, const void *beta)
   {
     if (DIM == 3 && op->variant != 1 && op->mesh->cartesian && !op->d_metric)
       {
+        if (op->variant == 60 && nb_src == nb_dst && !op->box_lo && op->n_xbox == 0)
+          {
+            const int rc = launch_cart_fd_any<T>(op, dst, src, nb_dst, alpha, beta);
+            if (rc != STFEM_ERR_UNSUPPORTED) return rc;
+          }
         const int nbd = nb_dst;
         switch (op->degree)
           {
@@ -995,5 +1093,19 @@ int stfem_op_set_timing(stfem_op_t op, int enable)
 }
 
 float stfem_op_last_kernel_ms(stfem_op_t op) { return op ? op->last_ms : -1.f; }
+
+/* kernel_variant 60 (experimental fast-diagonalisation form of the Cartesian operator): the modes of the reference-cell
+ * pencil (Kh, Mh) of FE_Q(degree) with QGauss(degree+1).  Host only.  V: (degree+1)^2 row-major, lam: degree+1. */
+int stfem_cart_fd_modes(int degree, double *V, double *lam)
+{
+  STFEM_REQUIRE(degree >= 1 && degree <= 6 && V && lam, "stfem_cart_fd_modes: bad arguments");
+  const int           n1 = degree + 1;
+  ShapeHost           sh(degree);
+  std::vector<double> v, l;
+  cart_fd_reference_matrices(sh, n1, v, l);
+  std::copy(v.begin(), v.end(), V);
+  std::copy(l.begin(), l.end(), lam);
+  return STFEM_OK;
+}
 
 } // extern "C"

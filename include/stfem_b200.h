@@ -98,7 +98,9 @@ typedef struct stfem_op_desc {
                                        Kronecker form; 11-19, 26-28 launch-bound configurations of the Cartesian kernel;
                                        17 largest-CTA rule; 18, 20-25 software-pipelined persistent kernel; 31-34 ablation
                                        experiments (WRONG results, timing only; rejected unless STFEM_ALLOW_ABLATION is set); 40-42 cp.async.bulk + mbarrier gather;
-                                       51 two 8-byte exchange fields instead of 16-byte pairs */
+                                       51 two 8-byte exchange fields instead of 16-byte pairs; 60 EXPERIMENTAL
+                                       fast-diagonalisation form (st_vmult_cart_fd.cuh; written after the last GPU call of
+                                       round 1, its parity test has not run yet) */
 } stfem_op_desc;
 
 int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *out);
@@ -114,6 +116,11 @@ int stfem_op_vmult(stfem_op_t op, void *const *dst, const void *const *src, int 
 int stfem_op_vmult_slice_add(stfem_op_t op, void *const *dst, const void *src0);
 /* get_matrix_diagonal (operators.h:613-625): diag_i = Alpha(i,i) diag K + Beta(i,i) diag M */
 int stfem_op_diagonal(stfem_op_t op, void *const *diag);
+
+/* kernel_variant 60 — EXPERIMENTAL, not verified on a GPU in round 1: the Cartesian operator in fast-diagonalisation form
+ * (csrc/st_vmult_cart_fd.cuh).  This host-only helper returns the modes it is built on: V (n1 x n1, row-major) and lam (n1)
+ * with  Mh = V^T V,  Kh = V^T diag(lam) V  for the 1D reference matrices of FE_Q(degree) / QGauss(degree+1). */
+int stfem_cart_fd_modes(int degree, double *V, double *lam);
 
 /* Same call with HOST buffers (nb arrays of N numbers of the operator's number type):
  * copies src to the device, applies, copies dst back — the end-to-end path bench.py times. */
