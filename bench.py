@@ -171,7 +171,8 @@ def solve_leg(st, ctx, refinement, n_steps=3, grid=None, coords=None, reduce_max
     pj = {"timeType": TTYPE, "problemType": "heat", "feDegree": TDEG, "refinement": refinement,
           "subdivisions": ",".join(str(3 * g) for g in grid), "hyperRectUpperRight": ",".join(str(float(g)) for g in grid),
           "mgTimeBeforeSpace": "true", "smoother": "relaxation", "spaceTimeConvergenceTest": "true",
-          "agglomerateBelow": os.environ.get("STFEM_AGGLO", "16")}
+          "agglomerateBelow": os.environ.get("STFEM_AGGLO", "16"),
+          "levelKernelVariant": os.environ.get("STFEM_LEVEL_VARIANT", "0")}
     p = st.parse_parameters(pj, 3)
     t0 = time.perf_counter()
     prob = st.HeatWaveProblem(ctx, p, 3, refinement, TDEG, space_degree=DEGREE,

@@ -57,6 +57,7 @@ def default_parameters(dim=2):
         "agglomerateBelow": 16,     # multi-GPU only (not a reference key): see HeatWaveProblem
         "innerPreconditioner": "vanka",   # not a reference key: "jacobi" = point-Jacobi inside Relaxation / Chebyshev
         "vankaStorage": "level",          # not a reference key: "half" = FP16 storage of the dense patch inverses
+        "levelKernelVariant": 0,          # not a reference key: stfem_op_desc::kernel_variant of the multigrid level operators
     }
 
 
@@ -198,6 +199,7 @@ class HeatWaveProblem:
         self.mesh_desc = mesh_desc
         self._coeff_cache = {}
         self.level_ops = [capi.Operator(self.meshes[level_ref[l]], level_degree[l], fetw[l][0], fetw[l][1], number_type=mg_number_type,
+                                        variant=int(p.get("levelKernelVariant", 0)),
                                         **self._laplace_coefficient(level_ref[l], level_degree[l])) for l in range(nl)]
         self.mg = capi.Multigrid(ctx, self.level_ops, self.mg_type_level, self.ptypes, self.ttype, self.nts, self.poly_time,
                                  smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
