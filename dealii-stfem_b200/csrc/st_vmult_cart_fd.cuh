@@ -16,11 +16,13 @@
 // Constrained (Dirichlet) nodes are read as 0 and never written (FEEvaluation::read_dof_values /
 // distribute_local_to_global with zero-boundary AffineConstraints, operators.h:1119-1128).
 #pragma once
-#include <cuda_runtime.h>
-
 #include <cmath>
 
+#ifndef STFEM_CART_FD_STANDALONE // tests/cpp/cart_fd_host_emulation.cpp compiles this header as plain host C++ with shims
+#include <cuda_runtime.h>
+
 #include "st_vmult_cart.cuh"
+#endif
 
 namespace stfem
 {

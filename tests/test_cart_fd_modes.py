@@ -66,3 +66,69 @@ def test_fast_diagonalisation_form_equals_the_operator(degree, ttype, r, coef):
         loc = vol * np.einsum("az,by,cx,rabc->rzyx", V, V, V, m2).reshape(nb, -1)
         np.add.at(out, (slice(None), dofs), np.where(free[dofs], loc, 0.0))
     assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+# ---- the kernel source itself, compiled for the host (tests/cpp/cart_fd_host_emulation.cpp: one std::thread per CUDA
+# thread, std::barrier for __syncthreads, a global array for the shared memory) and run on small meshes: checks the thread
+# mapping, the shared-memory layout, the ragged last CTA and the Dirichlet masking of k_st_vmult_cart_fd against the oracle.
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emulator(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("cartfd") / "cart_fd_emul")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-o", exe,
+                        os.path.join(ROOT, "tests", "cpp", "cart_fd_host_emulation.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_emulator_uses_the_exchange_layout_of_the_cuda_header():
+    """The harness restates ExchLayout<3..5>; the constants must be the ones of st_vmult_cart.cuh."""
+    cu = open(os.path.join(ROOT, "dealii-stfem_b200", "csrc", "st_vmult_cart.cuh")).read()
+    em = open(os.path.join(ROOT, "tests", "cpp", "cart_fd_host_emulation.cpp")).read()
+    pat = r"struct ExchLayout<(\d)> \{ static constexpr int LS = (\d+), CBS = (\d+);"
+    ref = {m[0]: m[1:] for m in re.findall(pat, cu)}
+    got = {m[0]: m[1:] for m in re.findall(pat, em)}
+    assert got and all(ref[k] == v for k, v in got.items())
+
+
+@pytest.mark.parametrize("degree,ttype,r,cells,upper,mask,coef", [
+    (4, "CGP", 2, [3, 2, 2], [1.2, 0.8, 1.0], 0x3f, False),     # configs[1] family: 3 cells per CTA, 4 CTAs
+    (4, "DG", 2, [4, 1, 2], [1.0, 1.0, 1.0], 0x00, True),       # nb = 3, no constraints, ragged last CTA
+    (3, "DG", 1, [3, 3, 2], [1.0, 1.5, 0.5], 0x15, True),       # Dirichlet on the lower faces only
+    (2, "CGP", 2, [2, 3, 2], [1.0, 2.0, 0.7], 0x2a, False),     # upper faces
+    (3, "DG", 2, [2, 2, 2], [1.0, 1.0, 1.0], 0x3f, False),
+])
+def test_emulated_kernel_matches_oracle(emulator, tmp_path, degree, ttype, r, cells, upper, mask, coef):
+    mesh = S.Mesh(3, cells, 0, [0.0, 0.0, 0.0], upper)
+    space = S.Space(mesh, degree, dirichlet_faces=mask)
+    A, B, _, _ = fth.get_fe_time_weights(ttype, r, 0.05, 1)
+    nb = A.shape[0]
+    K, M = S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0)
+    cc = np.ones(mesh.n_cells)
+    if coef:
+        cc = 1.0 + (np.arange(mesh.n_cells) % 4) * 0.75
+        K.laplace_coeff = np.repeat(cc[:, None], (degree + 1) ** 3, axis=1)
+    src = np.stack([np.random.RandomState(42 + b).uniform(-1, 1, space.n_dofs) for b in range(nb)])
+    ref = S.SystemMatrix(K, M, A, B).vmult(src)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([A.reshape(-1), B.reshape(-1), cc, src.reshape(-1)]).astype(np.float64).tofile(fin)
+    h = [upper[d] / cells[d] for d in range(3)]
+    cmd = [emulator, str(degree), str(nb)] + [str(c) for c in cells] + ["%.17g" % v for v in h] + [hex(mask), fin, fout]
+    run = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    out = np.fromfile(fout, dtype=np.float64).reshape(nb, space.n_dofs)
+    assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max(), np.abs(out - ref).max() / np.abs(ref).max()
+    assert np.all(out[:, space.constrained] == 0)
+    # transpose: the caller hands the kernel Alpha^T, Beta^T (capi_op.cu, d_alphaT / d_betaT)
+    np.concatenate([A.T.reshape(-1), B.T.reshape(-1), cc, src.reshape(-1)]).astype(np.float64).tofile(fin)
+    run = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0
+    out_t = np.fromfile(fout, dtype=np.float64).reshape(nb, space.n_dofs)
+    ref_t = S.SystemMatrix(K, M, A, B).Tvmult(src)
+    assert np.abs(out_t - ref_t).max() <= 1e-13 * np.abs(ref_t).max()
