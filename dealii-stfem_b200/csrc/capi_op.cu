@@ -545,7 +545,7 @@ namespace stfem
     const int tpc = NB * N1;
     int       best = 1;
     double    best_score = -1;
-    for (int c = 1; c * tpc <= 256; ++c)
+    for (int c = 1; c * tpc <= 128; ++c)
       {
         const int    thr = c * tpc;
         const double eff = (double)thr / (((thr + 31) / 32) * 32);

@@ -56,8 +56,10 @@ namespace stfem
       }
   }
 
+  // launch bounds (128, 3) = a budget of 170 registers: Q4, nb = 2 in FP64 needs 136 without spills (128 with 16 bytes of
+  // spills under (256, 2)); the launcher picks one-warp CTAs (3 cells x 2 blocks x 5 planes), about 15 resident per SM
   template <int N1, int NB, typename T>
-  __global__ void __launch_bounds__(256, 2) k_st_vmult_cart_fd(const __grid_constant__ CartFdArgs<T, N1> a)
+  __global__ void __launch_bounds__(128, 3) k_st_vmult_cart_fd(const __grid_constant__ CartFdArgs<T, N1> a)
   {
     using L           = ExchLayout<N1>;
     constexpr int K   = N1 - 1;

@@ -106,7 +106,7 @@ static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &
   const int tpc = NB * N1;
   int       best = 1;
   double    best_score = -1;
-  for (int c = 1; c * tpc <= 256; ++c)
+  for (int c = 1; c * tpc <= 128; ++c)
     {
       const int    thr = c * tpc;
       const double eff = (double)thr / (((thr + 31) / 32) * 32);
