@@ -218,7 +218,10 @@ def golden_tp_01_text():
             cur = []
         i += 1
     assert len(blocks) == 8, len(blocks)
-    return dict(zip(names, blocks))
+    # three blocks with three different column-width patterns are enough to pin the table writer (the numbers of all
+    # eight are in tp_01.json); the fixture stays a small excerpt of the reference's output file
+    keep = ("tf03", "tf05", "tf06")
+    return {n: b for n, b in zip(names, blocks) if n in keep}
 
 
 def golden_transfer_01():
