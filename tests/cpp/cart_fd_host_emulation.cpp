@@ -4,13 +4,14 @@
 // its thread mapping, shared-memory layout and Dirichlet masking can be checked against the oracle without a GPU
 // (tests/test_cart_fd_modes.py).  Not a performance tool and not part of the product.
 //
-//   cart_fd_host_emulation <degree> <nb> <nx> <ny> <nz> <hx> <hy> <hz> <dirichlet mask> <in.bin> <out.bin>
+//   cart_fd_host_emulation <degree> <nb> <nx> <ny> <nz> <hx> <hy> <hz> <dirichlet mask> <in.bin> <out.bin> [f32]
 // in.bin : Alpha[nb*nb], Beta[nb*nb], coeff[n_cells], src[nb][N]   (doubles);   out.bin: dst[nb][N]
 #include <barrier>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -52,7 +53,7 @@ namespace stfem
 
 using namespace stfem;
 
-template <int N1, int NB>
+template <int N1, int NB, typename T>
 static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &in, std::vector<double> &out)
 {
   const int       degree = N1 - 1;
@@ -67,7 +68,7 @@ static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &
         }
   cartfd_host::pencil_modes(Mh.data(), Kh.data(), N1, V.data(), lam.data());
   // the argument block exactly as launch_cart_fd (csrc/capi_op.cu) fills it
-  CartFdArgs<double, N1> a;
+  CartFdArgs<T, N1> a;
   const double           vol = h[0] * h[1] * h[2];
   long long              N = 1;
   for (int d = 0; d < 3; ++d)
@@ -79,12 +80,12 @@ static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &
   for (int q = 0; q < N1; ++q)
     for (int i = 0; i < N1; ++i)
       {
-        a.V[q * N1 + i]   = V[q * N1 + i];
-        a.Vt[i * N1 + q]  = V[q * N1 + i];
-        a.Vtx[i * N1 + q] = V[q * N1 + i] * vol;
+        a.V[q * N1 + i]   = (T)V[q * N1 + i];
+        a.Vt[i * N1 + q]  = (T)V[q * N1 + i];
+        a.Vtx[i * N1 + q] = (T)(V[q * N1 + i] * vol);
       }
   for (int d = 0; d < 3; ++d)
-    for (int q = 0; q < N1; ++q) a.lam[d][q] = lam[q] / (h[d] * h[d]);
+    for (int q = 0; q < N1; ++q) a.lam[d][q] = (T)(lam[q] / (h[d] * h[d]));
   a.n_cells   = (long long)n[0] * n[1] * n[2];
   a.dirichlet = mask;
   const size_t need = 2 * NB * NB + a.n_cells + (size_t)NB * N;
@@ -93,12 +94,13 @@ static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &
       std::fprintf(stderr, "input has %zu doubles, expected %zu\n", in.size(), need);
       return 2;
     }
-  const double *alpha = in.data(), *beta = alpha + NB * NB, *coeff = beta + NB * NB, *src = coeff + a.n_cells;
-  out.assign((size_t)NB * N, 0.0);
+  // the operator's number type: everything the kernel touches is converted like the library does at op_create / upload
+  std::vector<T> tin(in.begin(), in.end()), tout((size_t)NB * N, T(0));
+  const T       *alpha = tin.data(), *beta = alpha + NB * NB, *coeff = beta + NB * NB, *src = coeff + a.n_cells;
   for (int b = 0; b < STFEM_MAX_BLOCKS; ++b)
     {
       a.src[b] = b < NB ? src + (size_t)b * N : nullptr;
-      a.dst[b] = b < NB ? out.data() + (size_t)b * N : nullptr;
+      a.dst[b] = b < NB ? tout.data() + (size_t)b * N : nullptr;
     }
   a.alpha      = alpha;
   a.beta       = beta;
@@ -116,7 +118,7 @@ static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &
   a.cells_per_cta     = best;
   const int       threads = best * tpc;
   const long long grid    = (a.n_cells + best - 1) / best;
-  if ((size_t)best * NB * ExchLayout<N1>::CBS * sizeof(double) > sizeof(smem_raw)) return 3;
+  if ((size_t)best * NB * ExchLayout<N1>::CBS * sizeof(T) > sizeof(smem_raw)) return 3;
   std::printf("N1 %d NB %d cells %lld: %d cells per CTA, %d threads, grid %lld\n", N1, NB, a.n_cells, best, threads, grid);
   for (long long blk = 0; blk < grid; ++blk)
     {
@@ -127,16 +129,18 @@ static int run(int n[3], double h[3], unsigned mask, const std::vector<double> &
         pool.emplace_back([&a, t, blk]() {
           threadIdx.x = (unsigned)t;
           blockIdx.x  = (unsigned)blk;
-          k_st_vmult_cart_fd<N1, NB, double>(a);
+          k_st_vmult_cart_fd<N1, NB, T>(a);
         });
       for (auto &th : pool) th.join();
     }
+  out.assign(tout.begin(), tout.end());
   return 0;
 }
 
 int main(int argc, char **argv)
 {
-  if (argc != 12) return 1;
+  if (argc != 12 && argc != 13) return 1;
+  const bool f32 = argc == 13 && std::string(argv[12]) == "f32";
   const int degree = std::atoi(argv[1]), nb = std::atoi(argv[2]);
   int       n[3] = {std::atoi(argv[3]), std::atoi(argv[4]), std::atoi(argv[5])};
   double    h[3] = {std::atof(argv[6]), std::atof(argv[7]), std::atof(argv[8])};
@@ -154,7 +158,7 @@ int main(int argc, char **argv)
   }
   int rc = 4;
 #define CASE(K_, NB_) \
-  if (degree == K_ && nb == NB_) rc = run<K_ + 1, NB_>(n, h, mask, in, out);
+  if (degree == K_ && nb == NB_) rc = f32 ? run<K_ + 1, NB_, float>(n, h, mask, in, out) : run<K_ + 1, NB_, double>(n, h, mask, in, out);
   CASE(2, 2) CASE(2, 3) CASE(3, 2) CASE(3, 3) CASE(4, 2) CASE(4, 3)
 #undef CASE
   if (rc != 0) return rc;
