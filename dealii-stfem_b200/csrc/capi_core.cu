@@ -1,4 +1,8 @@
 // C ABI: context, device memory helpers, mesh.
+#include <chrono>
+#include <cstdlib>
+#include <thread>
+
 #include "common.hpp"
 
 namespace stfem
@@ -12,6 +16,46 @@ namespace stfem
     va_end(ap);
   }
   const char *get_error() { return g_err; }
+
+  // Fail-fast synchronisation.  On a multi-GPU context a stream can wait for ever on a collective / send-receive pair the
+  // peer ranks never enter (mismatched call sequences): instead of spinning until some watchdog kills the job minutes later,
+  // the wait is bounded (STFEM_SYNC_TIMEOUT_S, default 60 s) and the call returns STFEM_ERR_CUDA with a message naming it.
+  int stream_sync_checked(stfem_ctx *ctx, const char *what, cudaStream_t stream)
+  {
+    if (!stream) stream = ctx->stream;
+    if (ctx->n_ranks <= 1 || !ctx->nccl_comm)
+      {
+        STFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return STFEM_OK;
+      }
+    static const double limit = [] {
+      const char *e = std::getenv("STFEM_SYNC_TIMEOUT_S");
+      const double v = e ? std::atof(e) : 60.0;
+      return v > 0 ? v : 60.0;
+    }();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0;; ++spin)
+      {
+        const cudaError_t q = cudaStreamQuery(stream);
+        if (q == cudaSuccess) return STFEM_OK;
+        if (q != cudaErrorNotReady)
+          {
+            set_error("%s: stream failed: %s", what, cudaGetErrorString(q));
+            return STFEM_ERR_CUDA;
+          }
+        if ((spin & 1023u) == 1023u)
+          {
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (dt > limit)
+              {
+                set_error("%s: rank %d of %d waited %.0f s for its stream - a collective or halo exchange the other ranks did not enter "
+                          "(mismatched call sequence across ranks?)", what, ctx->rank, ctx->n_ranks, dt);
+                return STFEM_ERR_CUDA;
+              }
+            if (dt > 0.002) std::this_thread::yield();
+          }
+      }
+  }
 } // namespace stfem
 
 extern "C" {
@@ -61,8 +105,7 @@ int stfem_ctx_destroy(stfem_ctx_t ctx)
 int stfem_ctx_synchronize(stfem_ctx_t ctx)
 {
   STFEM_REQUIRE(ctx, "null context");
-  STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  return STFEM_OK;
+  return stfem::stream_sync_checked(ctx, "stfem_ctx_synchronize", nullptr);
 }
 
 int stfem_ctx_timer_start(stfem_ctx_t ctx)
@@ -76,6 +119,7 @@ int stfem_ctx_timer_stop(stfem_ctx_t ctx, float *ms)
 {
   STFEM_REQUIRE(ctx && ms, "null argument");
   STFEM_CUDA_CHECK(cudaEventRecord(ctx->tm1, ctx->stream));
+  STFEM_FORWARD(stfem::stream_sync_checked(ctx, "stfem_ctx_timer_stop", nullptr));
   STFEM_CUDA_CHECK(cudaEventSynchronize(ctx->tm1));
   STFEM_CUDA_CHECK(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
   return STFEM_OK;

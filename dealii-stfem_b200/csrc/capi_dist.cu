@@ -181,6 +181,34 @@ int stfem_ctx_comm_destroy(stfem_ctx_t ctx)
   return STFEM_OK;
 }
 
+// host values reduced over the ranks of the context's communicator (in place); op 0 = sum, 1 = max, 2 = min.
+// A context without a communicator (single GPU) returns the values unchanged.
+int stfem_ctx_allreduce(stfem_ctx_t ctx, double *values, int n, int op)
+{
+  STFEM_REQUIRE(ctx && values && n >= 0 && n <= 256 && op >= 0 && op <= 2, "stfem_ctx_allreduce: bad arguments");
+  if (!ctx->nccl_comm || ctx->n_ranks <= 1 || n == 0) return STFEM_OK;
+  NcclApi *api = nccl_api();
+  STFEM_REQUIRE(api, "stfem_ctx_allreduce: NCCL unavailable");
+  STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
+  double *d = nullptr;
+  STFEM_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * n));
+  STFEM_CUDA_CHECK(cudaMemcpyAsync(d, values, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  static const int red[3] = {0, 2, 3}; // ncclSum, ncclMax, ncclMin
+  int rc = api->AllReduce(d, d, (size_t)n, NcclApi::kDouble, red[op], (nccl_comm_t)ctx->nccl_comm, ctx->stream);
+  if (rc == 0)
+    {
+      STFEM_CUDA_CHECK(cudaMemcpyAsync(values, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      STFEM_FORWARD(stream_sync_checked(ctx, "stfem_ctx_allreduce"));
+    }
+  cudaFree(d);
+  if (rc != 0)
+    {
+      set_error("stfem_ctx_allreduce: ncclAllReduce failed: %s", api->GetErrorString(rc));
+      return STFEM_ERR_CUDA;
+    }
+  return STFEM_OK;
+}
+
 int stfem_ctx_rank(stfem_ctx_t ctx) { return ctx ? ctx->rank : 0; }
 int stfem_ctx_n_ranks(stfem_ctx_t ctx) { return ctx ? ctx->n_ranks : 1; }
 

@@ -600,7 +600,7 @@ namespace stfem
               if (op->variant == 12) return launch_cart<4, T, 256, 1>(op, dst, src, nb_src, nb_dst, alpha, beta);
               return launch_cart<4, T, 128, 3>(op, dst, src, nb_src, nb_dst, alpha, beta);
             case 4:
-              if (op->variant >= 40 && op->variant <= 42 && !op->box_lo)
+              if (op->variant >= 40 && op->variant <= 42 && !op->box_lo && op->n_xbox == 0) // whole-mesh launches only
                 {
                   if (nbd * 5 * 12 <= 128 && op->mesh->n[0] % 12 == 0)
                     {
@@ -691,9 +691,17 @@ namespace stfem
           }
         target = op->d_part_scratch.data();
       }
-    if (zero_dst || via_scratch)
+    const PartitionInfo &part = op->mesh->part;
+    static const bool no_overlap = std::getenv("STFEM_NO_OVERLAP") != nullptr;
+    const int *mn = op->mesh->n;
+    const bool overlap = part.active && uses_cart(op) && !no_overlap && mn[0] >= 8 && mn[1] >= 8 && mn[2] >= 8;
+    // the brick kernel writes every DoF exactly once: no zero fill, accumulation (if any) happens in its store
+    const bool brick = !overlap && brick_eligible(op, nb_src, nb_dst, alpha, beta);
+    if ((zero_dst || via_scratch) && !brick)
       for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(target[b], 0, bytes, ctx->stream));
     auto dispatch = [&]() -> int {
+      if (brick)
+        return brick_launch(op, target, src, nb_dst, alpha, beta, !(zero_dst || via_scratch), false);
       if (op->mesh->dim == 2)
         return op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
                                               dispatch_degree<2, float>(op, target, src, nb_src, nb_dst, alpha, beta);
@@ -705,13 +713,10 @@ namespace stfem
         return halo_compress_add<double>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim, stream);
       return halo_compress_add<float>(ctx, op->mesh->part, op->halo, target, nb_dst, op->np, op->mesh->dim, stream);
     };
-    const PartitionInfo &part = op->mesh->part;
     // multi-GPU: interface DoFs hold partial sums -> add over the ranks sharing them (cell_loop's compress(add)).
     // Large Cartesian bricks: the shell of cells touching a rank interface runs first, the exchange then overlaps
     // the interior cells on a second stream.
-    static const bool no_overlap = std::getenv("STFEM_NO_OVERLAP") != nullptr;
-    const int *mn = op->mesh->n;
-    if (part.active && uses_cart(op) && !no_overlap && mn[0] >= 8 && mn[1] >= 8 && mn[2] >= 8)
+    if (overlap)
       {
         STFEM_FORWARD(ctx_ensure_aux(ctx));
         int ilo[3], ihi[3];
@@ -887,6 +892,10 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
   std::vector<double> AN(op->Alpha), BN(op->Beta);
   for (auto &v : AN) v = -v;
   for (auto &v : BN) v = -v;
+  op->AlphaT = AT;
+  op->BetaT = BT;
+  op->AlphaNeg = AN;
+  op->BetaNeg = BN;
   const bool f64 = desc->number_type == STFEM_F64;
   if (f64)
     {
@@ -1034,8 +1043,7 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
       STFEM_FORWARD(stfem_op_vmult(op, d.data(), s.data(), transpose));
       for (int b = 0; b < nb; ++b)
         STFEM_CUDA_CHECK(cudaMemcpyAsync(dst_host[b], d[b], bytes, cudaMemcpyDeviceToHost, ctx->stream));
-      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-      return STFEM_OK;
+      return stream_sync_checked(ctx, "stfem_op_vmult_host");
     }
   // Pipelined over z slabs of cells: upload of slab s+1 (copy engine 1), cell kernel of slab s, download of the
   // node planes slab s has completed (copy engine 2) run concurrently; PCIe is used in both directions at once.
@@ -1054,7 +1062,15 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
   STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
   STFEM_CUDA_CHECK(cudaStreamWaitEvent(up, ctx->ev_fork, 0));
   STFEM_CUDA_CHECK(cudaStreamWaitEvent(down, ctx->ev_fork, 0));
-  for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(d[b], 0, bytes, ctx->stream));
+  // brick kernel: every slab writes its node planes once (the first plane of a slab adds to the partial sum the slab below
+  // left there), so dst needs no zero fill
+  int  lo0[3] = {0, 0, 0}, nn0[3] = {mn[0], mn[1], 1};
+  op->box_lo = lo0;
+  op->box_n  = nn0;
+  const bool brick = brick_eligible(op, nb, nb, alpha, beta);
+  op->box_lo = op->box_n = nullptr;
+  if (!brick)
+    for (int b = 0; b < nb; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(d[b], 0, bytes, ctx->stream));
   for (int sl = 0; sl < n_slabs; ++sl)
     {
       const int z0 = (int)((long long)mn[2] * sl / n_slabs), z1 = (int)((long long)mn[2] * (sl + 1) / n_slabs);
@@ -1068,7 +1084,8 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
       int lo[3] = {0, 0, z0}, nn[3] = {mn[0], mn[1], z1 - z0};
       op->box_lo = lo;
       op->box_n  = nn;
-      int rc = op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, d.data(), s.data(), nb, nb, alpha, beta) :
+      int rc = brick ? brick_launch(op, d.data(), s.data(), nb, alpha, beta, false, sl > 0) :
+               op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, d.data(), s.data(), nb, nb, alpha, beta) :
                                               dispatch_degree<3, float>(op, d.data(), s.data(), nb, nb, alpha, beta);
       op->box_lo = op->box_n = nullptr;
       if (rc != STFEM_OK) return rc;
@@ -1081,8 +1098,7 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
     }
   STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_join, down));
   STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-  STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  return STFEM_OK;
+  return stream_sync_checked(ctx, "stfem_op_vmult_host");
 }
 
 int stfem_op_set_timing(stfem_op_t op, int enable)

@@ -68,6 +68,12 @@ struct stfem_ctx
 
 namespace stfem
 {
+  // cudaStreamSynchronize(stream ? stream : ctx->stream), bounded in time on multi-GPU contexts (capi_core.cu)
+  int stream_sync_checked(stfem_ctx *ctx, const char *what, cudaStream_t stream = nullptr);
+} // namespace stfem
+
+namespace stfem
+{
   struct PartitionInfo
   {
     bool active = false;

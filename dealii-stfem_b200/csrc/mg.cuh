@@ -556,8 +556,12 @@ namespace stfem
           STFEM_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
           const int rc = v_step(top);
           const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-          if (rc != STFEM_OK) return rc;
-          STFEM_CUDA_CHECK(ce);
+          if (rc != STFEM_OK || ce != cudaSuccess)
+            {
+              if (graph) cudaGraphDestroy(graph);
+              if (rc != STFEM_OK) return rc;
+              STFEM_CUDA_CHECK(ce);
+            }
           graph_launches = ctx->launches - l0;
           ctx->launches  = l0;
           STFEM_CUDA_CHECK(cudaGraphInstantiate(&graph_exec, graph, 0));
@@ -701,14 +705,15 @@ namespace stfem
           if (first)
             {
               res.initial_residual = beta;
-              res.final_residual   = beta;
               tol                  = std::max(abstol, reduce * beta);
               first                = false;
-              if (beta <= tol)
-                {
-                  res.converged = true;
-                  break;
-                }
+            }
+          // also after a restart: the recomputed residual may already meet the tolerance (or be exactly 0)
+          res.final_residual = beta;
+          if (beta <= tol)
+            {
+              res.converged = true;
+              break;
             }
           v_scale(V[0], 1.0 / beta);
           std::fill(H.begin(), H.end(), 0.0);
@@ -788,7 +793,7 @@ namespace stfem
         }
       for (int k = 0; k < nb; ++k)
         STFEM_CUDA_CHECK(cudaMemcpyAsync(x_blocks[k], x.d + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      STFEM_FORWARD(stream_sync_checked(ctx, "fgmres"));
       if (!res.converged)
         {
           set_error("fgmres: no convergence after %d iterations (residual %.3e, tolerance %.3e)", res.iterations, res.final_residual, tol);

@@ -12,6 +12,7 @@ struct stfem_op
   long long   N = 0; // spatial dofs per block
   std::unique_ptr<stfem::ShapeHost> shape;
   std::vector<double> Alpha, Beta; // host copies, row-major nb_rows x nb_cols
+  std::vector<double> AlphaT, BetaT, AlphaNeg, BetaNeg; // host copies of the transposed / negated device matrices below
   void *d_alpha = nullptr, *d_beta = nullptr, *d_alphaT = nullptr, *d_betaT = nullptr;
   void *d_alpha_neg = nullptr, *d_beta_neg = nullptr; // -Alpha, -Beta: residual r = b - A x in one cell loop
   void *d_metric = nullptr; // general geometry: per cell, per q-point metric (+JxW)
@@ -37,6 +38,11 @@ namespace stfem
   // dst (+)= A src with explicit time matrices (device pointers in the operator's number type)
   int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                const void *beta, bool zero_dst);
+  // brick kernel (brick.cu): can this application run through it / run it.  The launch honours op->box_lo / box_n in z
+  // (cell layers) and op->launch_stream; first_plane_acc: the first node plane of the z range is accumulated
+  bool brick_eligible(const stfem_op *op, int nb_src, int nb_dst, const void *alpha, const void *beta);
+  int  brick_launch(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, bool accumulate,
+                    bool first_plane_acc);
   // diag K, diag M (double, cudaMalloc'ed, caller frees), constrained rows 0; capi_op.cu
   int op_spatial_diagonals(stfem_op *op, double **dK, double **dM);
 } // namespace stfem

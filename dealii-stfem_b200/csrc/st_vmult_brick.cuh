@@ -1,0 +1,683 @@
+// st_vmult, BRICK variant (3D, Cartesian mesh, constant coefficient): the fused space-time operator
+//     dst_j (+)= sum_s  Alpha(j,s) K src_s + Beta(j,s) M src_s
+// (reference: SystemMatrix::vmult over MatrixFreeOperator cell loops, include/operators.h:536-559, 1112-1173)
+// organised so that every DoF is READ ONCE FROM HBM AND WRITTEN ONCE, without atomics and without zeroing dst:
+//
+//  * On a Cartesian mesh with constant coefficient the assembled operator factorises over the directions,
+//        M = Mz (x) My (x) Mx,    K = Mz (x) My (x) Kx + Mz (x) Ky (x) Mx + Kz (x) My (x) Mx,
+//    with the ASSEMBLED 1D matrices (block-banded: one (k+1)^2 block per cell, overlapping in the shared vertex).
+//    Homogeneous Dirichlet constraints are separable too (read constrained nodes as 0, write 0 to constrained rows).
+//  * One CTA owns a tile of CX x CY cells in x-y and marches through z plane by plane ("2.5D blocking"):
+//      load   TMA box load (cp.async.bulk.tensor, mbarrier completion) of the (K(CX+1)+1) x (K(CY+1)+1) node tile of every
+//             source block of plane z into a ring of shared-memory stages, two to three planes ahead;
+//      X      per tile row and cell (one lane each): a_s = Mx u_s, b_s = Kx u_s by the even-odd decomposition of the
+//             (k+1)^2 cell matrices, temporal contraction  P_j = sum_s Beta(j,s) a_s + Alpha(j,s) b_s,
+//             Q_j = sum_s Alpha(j,s) a_s;  the partial sum of the vertex shared with the left cell comes by warp shuffle;
+//      Y+Z    one lane per x node, one warp per (cell row, dst block):  c = My P + Ky Q,  d = My Q  on its K (+1) nodes,
+//             then  out(z') += Mz(z',z) c + Kz(z',z) d  into register accumulators of the K+1 planes of the current cell
+//             layer; when a layer is complete its K planes are written with plain coalesced stores.
+//    The only redundancy is the halo cell on the low side of the tile in x and y (re-read through L2, its X-phase rows
+//    recomputed) and one warm-up cell layer per z chunk.
+//  * Row pitches of the block vectors ((k n + 1) numbers) are not multiples of 16 bytes; the tensor maps therefore view a
+//    block as 16/gcd(16, pitch) interleaved row classes (2 for FP64, 4 for FP32 when the pitch is odd), each with a 16-byte
+//    aligned base and a row stride that is a multiple of 16 bytes.  A box must also START on a 16-byte boundary of global
+//    memory (measured: cp.async.bulk.tensor raises an illegal-instruction error otherwise), so every class' box starts at the
+//    boundary at or below the first node of the tile row and the X phase skips the 0..3 lead-in elements.  Out-of-range box
+//    elements are zero-filled by TMA.
+#pragma once
+#ifndef STFEM_HOST_EMULATION
+#include <cuda.h>
+#include <cuda_runtime.h>
+#endif
+
+#include <type_traits>
+
+#include "../../include/stfem_b200.h"
+
+namespace stfem
+{
+  // what the host needs to encode one tensor map (and what the host emulation of the kernel reads instead of it)
+  struct BrickMapDesc
+  {
+    const void        *base;    // 16-byte aligned
+    unsigned long long dim0, dim1;    // elements, rows
+    unsigned long long stride1; // bytes
+    int                box0, box1;
+  };
+
+  template <int N1> struct BrickTile;
+  template <> struct BrickTile<3> { static constexpr int CX = 15, CY = 6; };
+  template <> struct BrickTile<4> { static constexpr int CX = 9, CY = 5; };
+  template <> struct BrickTile<5> { static constexpr int CX = 7, CY = 4; };
+
+  template <typename T, int N1, int NB, int CX_, int CY_>
+  struct BrickCfg
+  {
+    static constexpr int K = N1 - 1, CX = CX_, CY = CY_;
+    static constexpr int TX = K * CX, TY = K * CY;           // owned nodes of a tile (+ the last plane of the mesh)
+    static constexpr int WX = TX + K + 1, WY = TY + K + 1;   // input nodes: one halo cell on the low side
+    static constexpr int EPV = 16 / (int)sizeof(T);
+    // box width: a multiple of 16 bytes that also covers the lead-in elements of a box whose start has to be moved down to
+    // a 16-byte boundary of global memory (TMA rejects - illegal instruction - boxes that start anywhere else)
+    static constexpr int WXP = ((WX + EPV - 1 + EPV - 1) / EPV) * EPV;
+    static constexpr int MAXCLS = EPV;                       // row classes: 1, 2 (,4 for FP32)
+    static constexpr int CXL = CX + 1;                       // cells per tile row incl. the halo cell
+    static constexpr int RPW = 32 / CXL;                     // tile rows per warp in the X phase
+    static constexpr int XW = (WY + RPW - 1) / RPW;          // warps with X work
+    static constexpr int YW = CY * NB;                       // warps of the Y+Z phase: one per (cell row, dst block)
+    static constexpr int NWARPS = XW > YW ? XW : YW;
+    static constexpr int NTHREADS = 32 * NWARPS;
+    static constexpr int STAGES = 3;
+    static constexpr int PXP = ((TX + 1 + EPV - 1) / EPV) * EPV + ((((TX + 1 + EPV - 1) / EPV) & 1) ? 0 : EPV); // odd number of 16-byte words
+    static constexpr int PQ_FIELD = WY * PXP;                // one field of one dst block
+    static constexpr int PQ_BUF = 2 * NB * PQ_FIELD;
+    static_assert(CXL <= 32 && TX + 1 <= 32, "tile does not fit the lane mappings");
+    static_assert(RPW >= 1, "tile row does not fit a warp");
+    // bytes of one (source block, row class) sub-tile for n_cls classes, padded to 128 bytes
+    __host__ __device__ static constexpr int sub_bytes(int n_cls) { return ((((WY + n_cls - 1) / n_cls) * WXP * (int)sizeof(T)) + 127) / 128 * 128; }
+    __host__ __device__ static constexpr int stage_bytes(int n_cls) { return NB * n_cls * sub_bytes(n_cls); }
+    __host__ __device__ static constexpr int smem_bytes(int n_cls) { return 128 + STAGES * stage_bytes(n_cls) + 2 * PQ_BUF * (int)sizeof(T); }
+  };
+
+  template <typename T, int N1, int NB>
+  struct BrickArgs
+  {
+    static constexpr int NE = N1 - N1 / 2, NO = N1 / 2;
+#ifndef STFEM_HOST_EMULATION
+    alignas(64) CUtensorMap maps[NB][4];
+#endif
+    BrickMapDesc desc[NB][4]; // the same in plain form (host emulation, non-TMA load path)
+    int          shift[NB][4]; // elements between the aligned base of a class and its first row
+    int          n_cls;
+    // x: even/odd parts of vol*Mh and vol*Kh/hx^2; y, z: full matrices Mh, Kh/hy^2, Kh/hz^2 (row = output node)
+    T Mxe[NE * NE], Mxo[NO * NO + 1], Kxe[NE * NE], Kxo[NO * NO + 1];
+    T M[N1 * N1], Ky[N1 * N1], Kz[N1 * N1];
+    T alpha[NB * NB], beta[NB * NB]; // row-major [dst j][src s]
+    int n[3], np[3];
+    int zlo, zhi;        // cell layers [zlo, zhi) of this launch
+    int layers_per_chunk, n_chunks, tiles_x, tiles_y;
+    int mode;            // 0: dst = A src, 1: dst += A src
+    int first_plane_acc; // plane K*zlo is accumulated even in mode 0 (z-slab pipeline: it holds the partial sum of the slab below)
+    int use_tma;
+    unsigned dirichlet;
+    const T *src[NB];
+    T       *dst[NB];
+  };
+
+
+  // ------------------------------------------------------------------------------------------------ host helpers (plain C++)
+  inline int brick_gcd(long long a, long long b) { return b == 0 ? (int)a : brick_gcd(b, a % b); }
+
+  // the row classes of one block vector: class c = rows r = c (mod n_cls), each a 2D tensor with an aligned base
+  template <typename T>
+  inline void brick_describe_block(const void *base, int np0, long long n_rows, int n_cls, int box0, int box1, BrickMapDesc *desc, int *shift)
+  {
+    for (int c = 0; c < n_cls; ++c)
+      {
+        const unsigned long long first = (unsigned long long)base + (unsigned long long)c * np0 * sizeof(T);
+        desc[c].base    = (const void *)(first & ~15ull);
+        shift[c]        = (int)((first & 15ull) / sizeof(T));
+        desc[c].dim0    = (unsigned long long)np0 + shift[c];
+        desc[c].dim1    = (unsigned long long)((n_rows - c + n_cls - 1) / n_cls);
+        desc[c].stride1 = (unsigned long long)n_cls * np0 * sizeof(T);
+        desc[c].box0    = box0;
+        desc[c].box1    = box1;
+      }
+  }
+
+  // even / odd parts of a centrosymmetric n1 x n1 matrix (row-major, row = output): see brick_eo_apply2
+  template <typename T>
+  inline void brick_even_odd(const long double *A, int n1, T *Ae, T *Ao)
+  {
+    const int K = n1 - 1, NO = n1 / 2, NE = n1 - NO;
+    for (int i = 0; i < NE; ++i)
+      for (int k = 0; k < NE; ++k) Ae[i * NE + k] = (T)((k < NO) ? 0.5L * (A[i * n1 + k] + A[i * n1 + K - k]) : A[i * n1 + k]);
+    for (int i = 0; i < NO; ++i)
+      for (int k = 0; k < NO; ++k) Ao[i * NO + k] = (T)(0.5L * (A[i * n1 + k] - A[i * n1 + K - k]));
+  }
+
+  // number of z chunks: minimise  waves x (layers per chunk + warm-up layer)  for `slots` resident CTAs
+  inline int brick_choose_chunks(long long tiles, int layers, long long slots)
+  {
+    int    best = 1;
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= layers && nc <= 64; ++nc)
+      {
+        const int       lpc   = (layers + nc - 1) / nc;
+        const int       real  = (layers + lpc - 1) / lpc;
+        const long long ctas  = tiles * real;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double    cost  = (double)waves * (lpc + (real > 1 ? 1.0 : 0.0) + 0.75); // 0.75: pipeline fill of a CTA
+        if (cost < best_cost - 1e-9)
+          {
+            best_cost = cost;
+            best      = real;
+          }
+      }
+    return best;
+  }
+
+  // everything of the argument block except the tensor maps.  S, D, wq: shape values / derivatives [q][i] and weights of
+  // QGauss(k+1) for the GLL-nodal FE_Q(k) basis on [0,1]; h: cell sizes; n_chunks <= 0: choose for `slots` resident CTAs
+  template <typename T, int N1, int NB, int CX, int CY>
+  inline void brick_fill_args(BrickArgs<T, N1, NB> &a, const double *S, const double *D, const double *wq, const double h[3], const int n[3],
+                              unsigned dirichlet, const double *Alpha, const double *Beta, const void *const *src, void *const *dst, int zlo,
+                              int zhi, bool accumulate, bool first_plane_acc, int n_chunks, long long slots)
+  {
+    using C = BrickCfg<T, N1, NB, CX, CY>;
+    constexpr int K = N1 - 1;
+    const double  vol = h[0] * h[1] * h[2];
+    for (int d = 0; d < 3; ++d)
+      {
+        a.n[d]  = n[d];
+        a.np[d] = K * n[d] + 1;
+      }
+    long double Mh[N1 * N1], Kh[N1 * N1], Mx[N1 * N1], Kx[N1 * N1];
+    for (int i = 0; i < N1; ++i)
+      for (int j = 0; j < N1; ++j)
+        {
+          long double mm = 0, kk = 0;
+          for (int q = 0; q < N1; ++q)
+            {
+              mm += (long double)wq[q] * S[q * N1 + i] * S[q * N1 + j];
+              kk += (long double)wq[q] * D[q * N1 + i] * D[q * N1 + j];
+            }
+          Mh[i * N1 + j] = mm;
+          Kh[i * N1 + j] = kk;
+        }
+    // enforce the exact symmetries the even-odd form relies on (they hold up to rounding of the quadrature sums)
+    for (int i = 0; i < N1; ++i)
+      for (int j = 0; j < N1; ++j)
+        {
+          const long double ms = 0.25L * (Mh[i * N1 + j] + Mh[j * N1 + i] + Mh[(K - i) * N1 + K - j] + Mh[(K - j) * N1 + K - i]);
+          const long double ks = 0.25L * (Kh[i * N1 + j] + Kh[j * N1 + i] + Kh[(K - i) * N1 + K - j] + Kh[(K - j) * N1 + K - i]);
+          Mx[i * N1 + j]   = ms * vol;
+          Kx[i * N1 + j]   = ks * vol / (h[0] * h[0]);
+          a.M[i * N1 + j]  = (T)ms;
+          a.Ky[i * N1 + j] = (T)(ks / (h[1] * h[1]));
+          a.Kz[i * N1 + j] = (T)(ks / (h[2] * h[2]));
+        }
+    brick_even_odd<T>(Mx, N1, a.Mxe, a.Mxo);
+    brick_even_odd<T>(Kx, N1, a.Kxe, a.Kxo);
+    for (int i = 0; i < NB * NB; ++i)
+      {
+        a.alpha[i] = (T)Alpha[i];
+        a.beta[i]  = (T)Beta[i];
+      }
+    a.zlo             = zlo;
+    a.zhi             = zhi;
+    a.mode            = accumulate ? 1 : 0;
+    a.first_plane_acc = first_plane_acc ? 1 : 0;
+    a.dirichlet       = dirichlet;
+    a.tiles_x         = (n[0] + CX - 1) / CX;
+    a.tiles_y         = (n[1] + CY - 1) / CY;
+    const int layers  = zhi - zlo;
+    if (n_chunks <= 0) n_chunks = brick_choose_chunks((long long)a.tiles_x * a.tiles_y, layers, slots);
+    if (n_chunks > layers) n_chunks = layers;
+    a.layers_per_chunk = (layers + n_chunks - 1) / n_chunks;
+    a.n_chunks         = (layers + a.layers_per_chunk - 1) / a.layers_per_chunk;
+    const long long pitch = (long long)a.np[0] * sizeof(T);
+    a.n_cls               = 16 / brick_gcd(16, pitch % 16 == 0 ? 16 : pitch % 16);
+    const int       HB     = (C::WY + a.n_cls - 1) / a.n_cls;
+    const long long n_rows = (long long)a.np[1] * a.np[2];
+    a.use_tma              = 0;
+    for (int b = 0; b < NB; ++b)
+      {
+        a.src[b] = (const T *)src[b];
+        a.dst[b] = (T *)dst[b];
+        brick_describe_block<T>(src[b], a.np[0], n_rows, a.n_cls, C::WXP, HB, a.desc[b], a.shift[b]);
+      }
+  }
+
+  // ------------------------------------------------------------------------------------------------ async-copy primitives
+#ifndef STFEM_HOST_EMULATION
+  namespace brick_hw
+  {
+    __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+    __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    }
+    __device__ __forceinline__ void fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+    {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    }
+    // bounded wait: a lost transaction must end in a trap, not in a hung GPU
+    __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+    {
+      unsigned ok = 0;
+      for (unsigned spin = 0; !ok; ++spin)
+        {
+          asm volatile("{\n"
+                       ".reg .pred p;\n"
+                       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                       "selp.u32 %0, 1, 0, p;\n"
+                       "}"
+                       : "=r"(ok)
+                       : "r"(smem_addr(bar)), "r"(parity)
+                       : "memory");
+          if (!ok && spin > (1u << 22)) __trap();
+        }
+    }
+    __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar)
+    {
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_addr(dst)),
+                   "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+                   : "memory");
+    }
+  } // namespace brick_hw
+#endif
+
+  // plain (synchronous) version of one box load: element (i0, i1) of the box = tensor element (c0 + i0, c1 + i1), 0 outside
+  template <typename T>
+  __device__ __forceinline__ void brick_box_load_plain(T *dst, const BrickMapDesc &d, int c0, int c1, int tid, int nthreads)
+  {
+    const int total = d.box0 * d.box1;
+    for (int e = tid; e < total; e += nthreads)
+      {
+        const int       i0 = e % d.box0, i1 = e / d.box0;
+        const long long g0 = (long long)c0 + i0, g1 = (long long)c1 + i1;
+        T               v  = T(0);
+        if (g0 >= 0 && g0 < (long long)d.dim0 && g1 >= 0 && g1 < (long long)d.dim1)
+          v = *reinterpret_cast<const T *>(reinterpret_cast<const char *>(d.base) + (size_t)g1 * d.stride1 + (size_t)g0 * sizeof(T));
+        dst[e] = v;
+      }
+  }
+
+  // y = A u for a centrosymmetric (k+1)^2 matrix pair given by their even / odd parts, both applied to the same u
+  template <typename T, int N1>
+  __device__ __forceinline__ void brick_eo_apply2(const T (&u)[N1], const T *__restrict__ Ae, const T *__restrict__ Ao, const T *__restrict__ Be,
+                                                  const T *__restrict__ Bo, T (&ya)[N1], T (&yb)[N1])
+  {
+    constexpr int K = N1 - 1, NO = N1 / 2, NE = N1 - NO;
+    T             e[NE], o[NO > 0 ? NO : 1];
+#pragma unroll
+    for (int k = 0; k < NO; ++k)
+      {
+        e[k] = u[k] + u[K - k];
+        o[k] = u[k] - u[K - k];
+      }
+    if (N1 & 1) e[NE - 1] = u[NO];
+#pragma unroll
+    for (int i = 0; i < NE; ++i)
+      {
+        T ea = T(0), eb = T(0);
+#pragma unroll
+        for (int k = 0; k < NE; ++k)
+          {
+            ea += Ae[i * NE + k] * e[k];
+            eb += Be[i * NE + k] * e[k];
+          }
+        if (i < NO)
+          {
+            T oa = T(0), ob = T(0);
+#pragma unroll
+            for (int k = 0; k < NO; ++k)
+              {
+                oa += Ao[i * NO + k] * o[k];
+                ob += Bo[i * NO + k] * o[k];
+              }
+            ya[i]     = ea + oa;
+            ya[K - i] = ea - oa;
+            yb[i]     = eb + ob;
+            yb[K - i] = eb - ob;
+          }
+        else
+          {
+            ya[i] = ea;
+            yb[i] = eb;
+          }
+      }
+  }
+
+  // lane <-> (tile row within the warp, cell) of the X phase.  For 8 cells per row the two low bits of the cell index are
+  // swapped so that the 8 lanes of a quarter warp read (16-byte accesses) / write conflict-free.
+  template <int CXL, int RPW>
+  __device__ __forceinline__ int brick_cell_of(int cb)
+  {
+    if (CXL == 8) return (cb & 4) | ((cb & 1) << 1) | ((cb >> 1) & 1);
+    return cb;
+  }
+
+  template <typename T, int N1, int NB, int CX, int CY, int MINB>
+  __global__ void __launch_bounds__((BrickCfg<T, N1, NB, CX, CY>::NTHREADS), MINB)
+    st_vmult_brick_kernel(const __grid_constant__ BrickArgs<T, N1, NB> a)
+  {
+    using C = BrickCfg<T, N1, NB, CX, CY>;
+    constexpr int K = C::K, TX = C::TX, TY = C::TY, WY = C::WY, WXP = C::WXP, PXP = C::PXP, S = C::STAGES;
+    constexpr int CXL = C::CXL, RPW = C::RPW;
+    extern __shared__ __align__(128) unsigned char brick_smem[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(brick_smem);
+    const int           n_cls = a.n_cls;
+    const int           HB = (WY + n_cls - 1) / n_cls;      // box rows per class
+    const int           sub_elems = C::sub_bytes(n_cls) / (int)sizeof(T);
+    const int           stage_elems = NB * n_cls * sub_elems;
+    T                  *tiles = reinterpret_cast<T *>(brick_smem + 128);
+    T                  *pq    = tiles + (size_t)S * stage_elems;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- this CTA's tile and z chunk
+    int       bid   = blockIdx.x;
+    const int tix   = bid % a.tiles_x;
+    bid /= a.tiles_x;
+    const int tiy   = bid % a.tiles_y;
+    const int chunk = bid / a.tiles_y;
+    const int cx0 = tix * CX, cy0 = tiy * CY; // first owned cell
+    const int x0 = cx0 * K, y0 = cy0 * K;     // first owned node
+    const int cz0 = a.zlo + chunk * a.layers_per_chunk;
+    const int cz1 = min(a.zhi, cz0 + a.layers_per_chunk);
+    if (cz0 >= cz1) return;
+    const int start = cz0 > a.zlo ? cz0 - 1 : cz0; // warm-up layer: recomputes the partial sum carried into plane K*cz0
+    const int nq    = K * (cz1 - start) + 1;       // node planes this CTA walks through
+    const int np0 = a.np[0], np1 = a.np[1], np2 = a.np[2];
+    const unsigned dm = a.dirichlet;
+
+    // ---- plane loads
+    auto issue = [&](int qq) {
+      const int  stage = qq % S;
+      const long long r0 = (long long)(K * start + qq) * np1 + (y0 - K); // first tensor row of the tile (may be negative)
+      T         *st = tiles + (size_t)stage * stage_elems;
+#ifndef STFEM_HOST_EMULATION
+      if (a.use_tma)
+        {
+          if (tid == 0)
+            {
+              brick_hw::mbar_expect_tx(&bars[stage], (unsigned)(NB * n_cls * HB * WXP * (int)sizeof(T)));
+              for (int s = 0; s < NB; ++s)
+                for (int c = 0; c < n_cls; ++c)
+                  {
+                    const long long rc = r0 + (((long long)c - r0) & (n_cls - 1)); // first row >= r0 of class c
+                    const int       mc = (int)((rc - c) / n_cls);
+                    brick_hw::tma_load_2d(st + (size_t)(s * n_cls + c) * sub_elems, &a.maps[s][c], (x0 - K + a.shift[s][c]) & ~(C::EPV - 1), mc,
+                                          &bars[stage]);
+                  }
+            }
+          return;
+        }
+#endif
+      for (int s = 0; s < NB; ++s)
+        for (int c = 0; c < n_cls; ++c)
+          {
+            const long long rc = r0 + (((long long)c - r0) & (n_cls - 1));
+            const int       mc = (int)((rc - c) / n_cls);
+            brick_box_load_plain<T>(st + (size_t)(s * n_cls + c) * sub_elems, a.desc[s][c], (x0 - K + a.shift[s][c]) & ~(C::EPV - 1), mc, tid,
+                                    C::NTHREADS);
+          }
+    };
+
+#ifndef STFEM_HOST_EMULATION
+    if (a.use_tma)
+      {
+        if (tid == 0)
+          {
+            for (int s = 0; s < S; ++s) brick_hw::mbar_init(&bars[s], 1);
+            brick_hw::fence_init();
+          }
+        __syncthreads();
+        for (int qq = 0; qq < S && qq < nq; ++qq) issue(qq);
+      }
+#endif
+
+    // ---- Y+Z phase identity of this thread: lane = x node of the tile, warp = (cell row yc, dst block j)
+    const int  yc = warp % CY, jz = warp / CY;
+    const bool yz_warp = warp < C::YW;
+    const int  xo = lane <= TX ? lane : TX;
+    const int  xg = x0 + xo;
+    const bool last_tile_y = cy0 + CY >= a.n[1];
+    const bool extra       = last_tile_y && yc == CY - 1; // also owns the node row K*CY of the tile (last plane of the mesh)
+    const bool has_below   = cy0 + yc >= 1;               // the cell below this chunk's first node row exists
+    const bool has_above   = cy0 + yc < a.n[1];
+    const bool x_store     = lane <= TX && xg < np0 && (lane < TX || xg == np0 - 1);
+    const bool x_con       = ((dm & 1u) && xg == 0) || ((dm & 2u) && xg == np0 - 1);
+    T          acc[N1][N1]; // [node of the chunk][plane of the current cell layer]
+#pragma unroll
+    for (int nn = 0; nn < N1; ++nn)
+#pragma unroll
+      for (int i = 0; i < N1; ++i) acc[nn][i] = T(0);
+
+    // write plane z (local plane index i of the accumulators) of the chunk's nodes
+    auto store_plane = [&](int z, auto itag) {
+      constexpr int i = decltype(itag)::value;
+      const bool    z_con = ((dm & 16u) && z == 0) || ((dm & 32u) && z == np2 - 1);
+      const bool    add   = a.mode == 1 || (a.first_plane_acc && z == K * a.zlo);
+#pragma unroll
+      for (int nn = 0; nn < N1; ++nn)
+        {
+          if (nn == K && !extra) continue;
+          const int yg = y0 + K * yc + nn;
+          if (!x_store || yg >= np1 || (nn == K && yg != np1 - 1)) continue;
+          const bool con = x_con || z_con || ((dm & 4u) && yg == 0) || ((dm & 8u) && yg == np1 - 1);
+          T         *p   = a.dst[jz] + ((long long)xg + (long long)np0 * ((long long)yg + (long long)np1 * z));
+          if (add)
+            {
+              if (!con) *p += acc[nn][i];
+            }
+          else
+            *p = con ? T(0) : acc[nn][i];
+        }
+    };
+
+    // ---- march through the planes
+    for (int q = 0; q < nq; ++q)
+      {
+        const int  zp    = K * start + q; // node plane
+        const int  m     = q % K;         // its local index in the current cell layer (0: also node K of the layer below)
+        const int  layer = start + q / K;
+        const int  stage = q % S;
+        const bool plane_con = ((dm & 16u) && zp == 0) || ((dm & 32u) && zp == np2 - 1);
+        T         *st  = tiles + (size_t)stage * stage_elems;
+        T         *pqb = pq + (size_t)(q & 1) * C::PQ_BUF;
+#ifndef STFEM_HOST_EMULATION
+        if (a.use_tma)
+          brick_hw::mbar_wait(&bars[stage], (unsigned)((q / S) & 1));
+        else
+#endif
+          {
+            issue(q);
+            __syncthreads();
+          }
+
+        // ================= X phase
+        if (warp < C::XW)
+          {
+            const bool lane_ok = lane < RPW * CXL;
+            const int  r  = lane_ok ? lane % RPW : 0;
+            const int  cb = lane_ok ? lane / RPW : 0;
+            const int  ci = brick_cell_of<CXL, RPW>(cb); // 0 = halo cell on the low side
+            const int  yl = warp * RPW + r;
+            const bool row_in = lane_ok && yl < WY;
+            const int  yg  = y0 - K + yl;
+            const int  cxg = cx0 - 1 + ci;
+            const bool valid = row_in && !plane_con && yg >= 0 && yg < np1 && !((dm & 4u) && yg == 0) && !((dm & 8u) && yg == np1 - 1) &&
+                               cxg >= 0 && cxg < a.n[0];
+            T P[NB][N1], Q[NB][N1];
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+#pragma unroll
+              for (int i = 0; i < N1; ++i) P[j][i] = Q[j][i] = T(0);
+            if (valid)
+              {
+                // tile row yl sits in class c at index idx of that class' box
+                const long long r0  = (long long)zp * np1 + (y0 - K);
+                const int       c   = (int)((r0 + yl) & (n_cls - 1));
+                const long long rc  = r0 + (((long long)c - r0) & (n_cls - 1));
+                const int       idx = (int)((r0 + yl - rc) / n_cls);
+#pragma unroll
+                for (int s = 0; s < NB; ++s)
+                  {
+                    // the box of this class starts at the 16-byte boundary at or below the first node of the tile row
+                    const int lead = (x0 - K + a.shift[s][c]) & (C::EPV - 1);
+                    const T  *row  = st + (size_t)(s * n_cls + c) * sub_elems + (size_t)idx * WXP + lead + K * ci;
+                    T        u[N1], av[N1], bv[N1];
+#pragma unroll
+                    for (int i = 0; i < N1; ++i) u[i] = row[i];
+                    if ((dm & 1u) && cxg == 0) u[0] = T(0);
+                    if ((dm & 2u) && cxg == a.n[0] - 1) u[K] = T(0);
+                    brick_eo_apply2<T, N1>(u, a.Mxe, a.Mxo, a.Kxe, a.Kxo, av, bv);
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                      {
+                        const T be = a.beta[j * NB + s], al = a.alpha[j * NB + s];
+#pragma unroll
+                        for (int i = 0; i < N1; ++i)
+                          {
+                            P[j][i] += be * av[i];
+                            P[j][i] += al * bv[i];
+                            Q[j][i] += al * av[i];
+                          }
+                      }
+                  }
+              }
+            // the vertex shared with the left cell: add that cell's partial sum (all lanes take part in the shuffles)
+            int src_lane = lane;
+            if (lane_ok && ci >= 1)
+              {
+                int cbl = 0;
+#pragma unroll
+                for (int t = 0; t < CXL; ++t)
+                  if (brick_cell_of<CXL, RPW>(t) == ci - 1) cbl = t;
+                src_lane = r + RPW * cbl;
+              }
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              {
+                const T pk = __shfl_sync(0xffffffffu, P[j][K], src_lane);
+                const T qk = __shfl_sync(0xffffffffu, Q[j][K], src_lane);
+                if (lane_ok && ci >= 1)
+                  {
+                    P[j][0] += pk;
+                    Q[j][0] += qk;
+                  }
+              }
+            if (row_in && ci >= 1)
+              {
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                  {
+                    T *pp = pqb + (size_t)(0 * NB + j) * C::PQ_FIELD + (size_t)yl * PXP + K * (ci - 1);
+                    T *qp = pqb + (size_t)(1 * NB + j) * C::PQ_FIELD + (size_t)yl * PXP + K * (ci - 1);
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      {
+                        pp[i] = P[j][i];
+                        qp[i] = Q[j][i];
+                      }
+                    if (ci == CX)
+                      {
+                        pp[K] = P[j][K];
+                        qp[K] = Q[j][K];
+                      }
+                  }
+              }
+          }
+        __syncthreads(); // P, Q of this plane complete; stage `stage` consumed by everybody
+#ifndef STFEM_HOST_EMULATION
+        if (a.use_tma && q + S < nq) issue(q + S);
+#endif
+
+        // ================= Y + Z phase
+        if (yz_warp)
+          {
+            const T *pp = pqb + (size_t)(0 * NB + jz) * C::PQ_FIELD + (size_t)(K * yc) * PXP + xo;
+            const T *qp = pqb + (size_t)(1 * NB + jz) * C::PQ_FIELD + (size_t)(K * yc) * PXP + xo;
+            T        p[2 * K + 1], qv[2 * K + 1];
+#pragma unroll
+            for (int t = 0; t < 2 * K + 1; ++t)
+              {
+                p[t]  = pp[t * PXP];
+                qv[t] = qp[t * PXP];
+              }
+            T c[N1], d[N1];
+            // node 0 of the chunk: vertex row shared by the cell below (its node K) and the cell above (its node 0)
+            {
+              T cb_ = T(0), db_ = T(0), ca_ = T(0), da_ = T(0);
+#pragma unroll
+              for (int t = 0; t < N1; ++t)
+                {
+                  cb_ += a.M[K * N1 + t] * p[t];
+                  cb_ += a.Ky[K * N1 + t] * qv[t];
+                  db_ += a.M[K * N1 + t] * qv[t];
+                  ca_ += a.M[t] * p[K + t];
+                  ca_ += a.Ky[t] * qv[K + t];
+                  da_ += a.M[t] * qv[K + t];
+                }
+              c[0] = (has_below ? cb_ : T(0)) + (has_above ? ca_ : T(0));
+              d[0] = (has_below ? db_ : T(0)) + (has_above ? da_ : T(0));
+            }
+#pragma unroll
+            for (int nn = 1; nn < N1; ++nn)
+              {
+                if (nn == K && !extra)
+                  {
+                    c[nn] = d[nn] = T(0);
+                    continue;
+                  }
+                T cc = T(0), dd = T(0);
+#pragma unroll
+                for (int t = 0; t < N1; ++t)
+                  {
+                    cc += a.M[nn * N1 + t] * p[K + t];
+                    cc += a.Ky[nn * N1 + t] * qv[K + t];
+                    dd += a.M[nn * N1 + t] * qv[K + t];
+                  }
+                c[nn] = cc;
+                d[nn] = dd;
+              }
+            auto zacc = [&](auto mtag) {
+              constexpr int mm = decltype(mtag)::value;
+#pragma unroll
+              for (int nn = 0; nn < N1; ++nn)
+                {
+                  if (nn == K && !extra) continue;
+#pragma unroll
+                  for (int i = 0; i < N1; ++i)
+                    {
+                      acc[nn][i] += a.M[i * N1 + mm] * c[nn];
+                      acc[nn][i] += a.Kz[i * N1 + mm] * d[nn];
+                    }
+                }
+            };
+            if (m == 0)
+              {
+                if (q > 0)
+                  {
+                    zacc(std::integral_constant<int, K>()); // closes cell layer `layer - 1`
+                    if (layer - 1 >= cz0)
+                      {
+                        const int zb = K * (layer - 1);
+                        if (K > 0) store_plane(zb + 0, std::integral_constant<int, 0>());
+                        if (K > 1) store_plane(zb + 1, std::integral_constant<int, (K > 1 ? 1 : 0)>());
+                        if (K > 2) store_plane(zb + 2, std::integral_constant<int, (K > 2 ? 2 : 0)>());
+                        if (K > 3) store_plane(zb + 3, std::integral_constant<int, (K > 3 ? 3 : 0)>());
+                        if (K > 4) store_plane(zb + 4, std::integral_constant<int, (K > 4 ? 4 : 0)>());
+                        if (K > 5) store_plane(zb + 5, std::integral_constant<int, (K > 5 ? 5 : 0)>());
+                      }
+#pragma unroll
+                    for (int nn = 0; nn < N1; ++nn)
+                      {
+                        acc[nn][0] = acc[nn][K];
+#pragma unroll
+                        for (int i = 1; i < N1; ++i) acc[nn][i] = T(0);
+                      }
+                  }
+                if (q < nq - 1) zacc(std::integral_constant<int, 0>());
+              }
+            else
+              {
+                switch (m)
+                  {
+                    case 1: zacc(std::integral_constant<int, (K > 1 ? 1 : 0)>()); break;
+                    case 2: zacc(std::integral_constant<int, (K > 2 ? 2 : 0)>()); break;
+                    case 3: zacc(std::integral_constant<int, (K > 3 ? 3 : 0)>()); break;
+                    case 4: zacc(std::integral_constant<int, (K > 4 ? 4 : 0)>()); break;
+                    default: zacc(std::integral_constant<int, (K > 5 ? 5 : 0)>()); break;
+                  }
+              }
+          }
+      }
+    // the top plane of the launch range: complete if it is the top of the mesh, else the partial sum of the cells below
+    if (yz_warp && cz1 == a.zhi) store_plane(K * cz1, std::integral_constant<int, 0>());
+  }
+} // namespace stfem

@@ -318,7 +318,7 @@ namespace stfem
         STFEM_NCCL_CHECK(api->AllReduce(sc.d, sc.d, (size_t)m, NcclApi::kDouble, NcclApi::kSum, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
       }
     STFEM_CUDA_CHECK(cudaMemcpyAsync(sc.h, sc.d, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    STFEM_FORWARD(stream_sync_checked(ctx, "multi_dot"));
     for (int k = 0; k < m; ++k) out[k] = sc.h[k];
     return STFEM_OK;
   }
@@ -379,7 +379,7 @@ namespace stfem
         STFEM_NCCL_CHECK(api->AllReduce(sc.d, sc.d, 1, NcclApi::kDouble, NcclApi::kSum, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
       }
     STFEM_CUDA_CHECK(cudaMemcpyAsync(sc.h, sc.d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    STFEM_FORWARD(stream_sync_checked(ctx, "multi_axpy_norm"));
     *nrm2 = sc.h[0];
     return STFEM_OK;
   }

@@ -355,8 +355,17 @@ class HeatWaveProblem:
         return self.row()
 
     def row(self):
-        return dict(cells=int(np.prod(self.n_cells)), s_dofs=int(self.n), t_dofs=self.nb, iterations=self.total_iterations,
-                    timesteps=self.n_solves, linf=float(self.err[1]), l2=math.sqrt(self.err[0]), h1=math.sqrt(self.err[2]),
+        """One line of the convergence table (tests/tp_01.cc:703-715).  Partitioned runs: the error integrals of the local
+        cells are summed (L2, H1) / maximised (Linf) over the ranks and the DoF count is the global one, as the reference
+        does with Utilities::MPI::sum / max (include/exact_solution.h:612-631)."""
+        err, s_dofs = self.err, int(self.n)
+        if self.partition is not None:
+            from . import dist
+            sums = dist.allreduce(self.ctx, [self.err[0], self.err[2]], "sum")
+            err = np.array([sums[0], dist.allreduce(self.ctx, [self.err[1]], "max")[0], sums[1]])
+            s_dofs = int(np.prod([self.k * n + 1 for n in self.n_cells]))
+        return dict(cells=int(np.prod(self.n_cells)), s_dofs=s_dofs, t_dofs=self.nb, iterations=self.total_iterations,
+                    timesteps=self.n_solves, linf=float(err[1]), l2=math.sqrt(err[0]), h1=math.sqrt(err[2]),
                     levels="".join(self.mg_type_level), tau=self.tau)
 
     def close(self):

@@ -143,6 +143,10 @@ int stfem_comm_unique_id(char *id128);
 int stfem_ctx_comm_init(stfem_ctx_t ctx, int rank, int n_ranks, const char *id128);
 int stfem_ctx_comm_destroy(stfem_ctx_t ctx);
 int stfem_ctx_rank(stfem_ctx_t ctx);
+/* host values reduced in place over the ranks of the context's communicator (the MPI_Allreduce / Utilities::MPI::sum|max
+ * of the reference's drivers, e.g. the error norms of tests/tp_01.cc:409-432); op: 0 sum, 1 max, 2 min; n <= 256.
+ * Without a communicator the values are returned unchanged. */
+int stfem_ctx_allreduce(stfem_ctx_t ctx, double *values, int n, int op);
 int stfem_ctx_n_ranks(stfem_ctx_t ctx);
 /* brick of process `coords` (x fastest rank order) in `proc_grid`: local cells, global cell offset,
  * local bounding box, Dirichlet mask restricted to physical boundary faces.  Pure host logic. */

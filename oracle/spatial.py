@@ -93,35 +93,49 @@ class Space:
         self.xq, self.wq = Q.gauss(self.n1)                       # QGauss(k+1), tp_01.cc:78
         self.S = Q.lagrange_eval(self.gll, self.xq).T.copy()      # S[q,i] = phi_i(x_q)
         self.D = Q.lagrange_deriv(self.gll, self.xq).T.copy()     # D[q,i] = phi_i'(x_q)
-        d = self.dim
-        idx = np.arange(self.n_dofs).reshape(self.np[::-1])
-        mask = np.zeros(self.np[::-1], bool)
-        for ax in range(d):
-            coord = d - 1 - ax                                  # array axis ax <-> coordinate direction
-            sl = [slice(None)] * d
-            if (dirichlet_faces >> (2 * coord)) & 1:
-                sl[ax] = 0
-                mask[tuple(sl)] = True
-            if (dirichlet_faces >> (2 * coord + 1)) & 1:
-                sl[ax] = -1
-                mask[tuple(sl)] = True
-        self.constrained = mask.reshape(-1)
-        # cell_dofs[c, local] lexicographic in both
-        k = degree
-        loc = np.arange(self.n1)
-        if d == 2:
-            cy, cx = np.meshgrid(np.arange(mesh.n[1]), np.arange(mesh.n[0]), indexing="ij")
-            iy = (k * cy.reshape(-1))[:, None, None] + loc[None, :, None]
-            ix = (k * cx.reshape(-1))[:, None, None] + loc[None, None, :]
-            self.cell_dofs = (ix + self.np[0] * iy).reshape(mesh.n_cells, -1)
-        else:
-            cz, cy, cx = np.meshgrid(np.arange(mesh.n[2]), np.arange(mesh.n[1]), np.arange(mesh.n[0]),
-                                     indexing="ij")
-            iz = (k * cz.reshape(-1))[:, None, None, None] + loc[None, :, None, None]
-            iy = (k * cy.reshape(-1))[:, None, None, None] + loc[None, None, :, None]
-            ix = (k * cx.reshape(-1))[:, None, None, None] + loc[None, None, None, :]
-            self.cell_dofs = (ix + self.np[0] * (iy + self.np[1] * iz)).reshape(mesh.n_cells, -1)
+        self._dirichlet_faces = dirichlet_faces
+        self._constrained = None
+        self._cell_dofs = None
         self._geom = None
+
+    # the index tables are built on first use: the CPU baseline of bench.py runs 96^3-cell bricks through
+    # oracle/cpu_ref.cpp, which needs neither of them
+    @property
+    def constrained(self):
+        if self._constrained is None:
+            d = self.dim
+            mask = np.zeros(self.np[::-1], bool)
+            for ax in range(d):
+                coord = d - 1 - ax                                  # array axis ax <-> coordinate direction
+                sl = [slice(None)] * d
+                if (self._dirichlet_faces >> (2 * coord)) & 1:
+                    sl[ax] = 0
+                    mask[tuple(sl)] = True
+                if (self._dirichlet_faces >> (2 * coord + 1)) & 1:
+                    sl[ax] = -1
+                    mask[tuple(sl)] = True
+            self._constrained = mask.reshape(-1)
+        return self._constrained
+
+    @property
+    def cell_dofs(self):
+        """cell_dofs[c, local], lexicographic in both"""
+        if self._cell_dofs is None:
+            mesh, d, k = self.mesh, self.dim, self.k
+            loc = np.arange(self.n1)
+            if d == 2:
+                cy, cx = np.meshgrid(np.arange(mesh.n[1]), np.arange(mesh.n[0]), indexing="ij")
+                iy = (k * cy.reshape(-1))[:, None, None] + loc[None, :, None]
+                ix = (k * cx.reshape(-1))[:, None, None] + loc[None, None, :]
+                self._cell_dofs = (ix + self.np[0] * iy).reshape(mesh.n_cells, -1)
+            else:
+                cz, cy, cx = np.meshgrid(np.arange(mesh.n[2]), np.arange(mesh.n[1]), np.arange(mesh.n[0]),
+                                         indexing="ij")
+                iz = (k * cz.reshape(-1))[:, None, None, None] + loc[None, :, None, None]
+                iy = (k * cy.reshape(-1))[:, None, None, None] + loc[None, None, :, None]
+                ix = (k * cx.reshape(-1))[:, None, None, None] + loc[None, None, None, :]
+                self._cell_dofs = (ix + self.np[0] * (iy + self.np[1] * iz)).reshape(mesh.n_cells, -1)
+        return self._cell_dofs
 
     # ---- geometry (MappingQ1, SURVEY App. A.2)
     def geometry(self):

@@ -1,0 +1,143 @@
+"""GPU parity of the brick kernel (csrc/st_vmult_brick.cuh: TMA box loads, 2.5D blocking, owner-writes stores) through the
+C ABI.  Small meshes against the oracle's unfused SystemMatrix::vmult (include/operators.h:536-559), all load paths and
+chunkings; larger meshes (several tiles, several waves of CTAs) against the per-cell kernel of round 1 and through
+size-independent properties.  Tolerances: relative 1e-12 in FP64, 1e-5 in FP32 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from oracle import fe_time as ft
+from oracle import spatial as S
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-12, 1: 1e-5}
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _rand(nb, n, seed=42):
+    return np.stack([np.random.RandomState(seed + b).uniform(-1, 1, n) for b in range(nb)])
+
+
+CASES = [
+    # k, cells, upper, ttype, r, nts, dirichlet mask
+    (4, [8, 5, 3], [1.0, 1.0, 0.5], "CGP", 2, 1, 0x3f),     # configs[1] family: 2 x 2 tiles of 7 x 4 cells, ragged
+    (4, [3, 2, 5], [1.2, 0.8, 1.0], "DG", 1, 1, 0x00),      # no constraints: last node planes stored
+    (4, [9, 9, 2], [1.0, 1.0, 1.0], "DG", 2, 1, 0x15),      # nb = 3, lower faces only
+    (4, [7, 4, 4], [1.0, 1.0, 1.0], "DG", 0, 1, 0x2a),      # nb = 1, exactly one tile, upper faces
+    (3, [10, 6, 3], [1.0, 1.5, 0.5], "CGP", 2, 1, 0x3f),    # configs[2] family (Q3 x cG(2))
+    (3, [4, 11, 2], [1.0, 1.0, 1.0], "DG", 2, 1, 0x00),
+    (2, [16, 7, 3], [1.0, 2.0, 0.7], "DG", 1, 1, 0x3f),     # configs[0] family in 3D (Q2 x DG(1))
+    (2, [5, 5, 5], [1.0, 1.0, 1.0], "CGP", 2, 1, 0x0c),
+]
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("variant", [72, 70, 82, 71])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "k%d_%s_%s%d_m%x" % (c[0], "x".join(map(str, c[1])), c[3], c[4], c[6]))
+def test_brick_kernel_matches_oracle(ctx, case, variant, number_type):
+    """72: TMA loads; 70: plain loads; 82: three z chunks (warm-up layers); 71: one CTA per SM (Q4, two blocks only)."""
+    import dealii_stfem_b200 as st
+    k, cells, upper, ttype, r, nts, mask = case
+    mesh = S.Mesh(3, cells, 0, lower=[0, 0, 0], upper=upper)
+    space = S.Space(mesh, k, dirichlet_faces=mask)
+    A, B = ft.get_fe_time_weights(ttype, r, 0.05, nts)[:2]
+    nb = A.shape[0]
+    if variant == 71 and not (k == 4 and nb == 2):
+        pytest.skip("variant 71 is instantiated for Q4 with two blocks only")
+    dt = np.float64 if number_type == 0 else np.float32
+    sysm = S.SystemMatrix(S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0), A, B)
+    src = _rand(nb, space.n_dofs).astype(dt)
+    gm = st.Mesh(ctx, cells, lower=[0, 0, 0], upper=upper, dirichlet_faces=mask)
+    op = st.Operator(gm, k, A, B, number_type=number_type, variant=variant)
+    d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+    d_dst.upload(np.full((nb, space.n_dofs), 7.5, dt))          # every entry must be overwritten (no zero fill, no atomics)
+    l0 = ctx.launches
+    op.vmult(d_dst, d_src)
+    assert ctx.launches - l0 == 1                                # one kernel, no memset kernel, no fallback
+    out = d_dst.download()
+    assert _rel(out, sysm.vmult(src.astype(np.float64))) < TOL[number_type]
+    assert np.all(out[:, space.constrained] == 0)
+    op.Tvmult(d_dst, d_src)
+    assert _rel(d_dst.download(), sysm.Tvmult(src.astype(np.float64))) < TOL[number_type]
+    d_src.free(); d_dst.free(); op.close(); gm.close()
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("k,cells,ttype,r", [(4, [30, 21, 17], "CGP", 2), (3, [37, 20, 9], "DG", 2), (2, [40, 40, 12], "DG", 1)])
+def test_brick_kernel_matches_per_cell_kernel_on_larger_meshes(ctx, k, cells, ttype, r, number_type):
+    """Many tiles and z chunks chosen by the launcher: the brick kernel (default) against the per-cell kernel (variant 3)."""
+    import dealii_stfem_b200 as st
+    A, B = ft.get_fe_time_weights(ttype, r, 0.02, 1)[:2]
+    nb = A.shape[0]
+    gm = st.Mesh(ctx, cells, lower=[0, 0, 0], upper=[1.0, 0.7, 0.6])
+    ops = [st.Operator(gm, k, A, B, number_type=number_type, variant=v) for v in (0, 3)]
+    n = ops[0].n
+    dt = np.float64 if number_type == 0 else np.float32
+    x = _rand(nb, n, 3).astype(dt)
+    dx, dy = ops[0].new_vector().upload(x), ops[0].new_vector()
+    res = []
+    for op in ops:
+        op.vmult(dy, dx)
+        res.append(dy.download().astype(np.float64))
+    assert _rel(res[0], res[1]) < TOL[number_type]
+    res = []
+    for op in ops:
+        op.Tvmult(dy, dx)
+        res.append(dy.download().astype(np.float64))
+    assert _rel(res[0], res[1]) < TOL[number_type]
+    dx.free(); dy.free()
+    for op in ops:
+        op.close()
+    gm.close()
+
+
+def test_brick_kernel_host_buffer_entry_point(ctx):
+    """stfem_op_vmult_host pipelines z slabs of cells: every slab is one brick launch whose first node plane accumulates."""
+    import dealii_stfem_b200 as st
+    A, B = ft.get_fe_time_weights("CGP", 2, 0.02, 1)[:2]
+    gm = st.Mesh(ctx, [20, 12, 37])
+    op = st.Operator(gm, 4, A, B)
+    x = _rand(2, op.n, 11)
+    dx, dy = op.new_vector().upload(x), op.new_vector()
+    op.vmult(dy, dx)
+    ref = dy.download()
+    hy = np.full_like(x, -1.0)
+    op.vmult_host(hy, x)
+    assert _rel(hy, ref) < 1e-14
+    op.vmult_host(hy, x, transpose=True)
+    op.Tvmult(dy, dx)
+    assert _rel(hy, dy.download()) < 1e-14
+    dx.free(); dy.free(); op.close(); gm.close()
+
+
+def test_brick_kernel_properties_at_full_size(ctx):
+    """configs[1] at full size (96^3 cells, 1.14e8 space-time DoFs): linearity, adjointness of vmult / Tvmult, zero rows on
+    the Dirichlet boundary, and agreement with the per-cell kernel."""
+    import dealii_stfem_b200 as st
+    A, B = ft.get_fe_time_weights("CGP", 2, 2.0 ** -6, 1)[:2]
+    gm = st.Mesh(ctx, [96, 96, 96])
+    op, old = st.Operator(gm, 4, A, B), st.Operator(gm, 4, A, B, variant=3)
+    n, nb = op.n, 2
+    x, y = _rand(nb, n, 1), _rand(nb, n, 5)
+    dx, dy, dz, dr = (op.new_vector() for _ in range(4))
+    dx.upload(x); dy.upload(y); dz.upload(2.0 * x - 3.0 * y)
+    op.vmult(dr, dx); Ax = dr.download()
+    old.vmult(dr, dx)
+    assert _rel(Ax, dr.download()) < 1e-12
+    op.vmult(dr, dy); Ay = dr.download()
+    op.vmult(dr, dz); Az = dr.download()
+    assert _rel(Az, 2.0 * Ax - 3.0 * Ay) < 1e-12
+    op.Tvmult(dr, dy); ATy = dr.download()
+    lhs, rhs = np.vdot(Ax, y), np.vdot(x, ATy)
+    assert abs(lhs - rhs) <= 1e-11 * np.linalg.norm(Ax) * np.linalg.norm(y)
+    np3 = 4 * 96 + 1
+    Ax3 = Ax.reshape(nb, np3, np3, np3)
+    for sl in ((slice(None), 0), (slice(None), -1), (slice(None), slice(None), 0), (slice(None), slice(None), -1),
+               (slice(None), slice(None), slice(None), 0), (slice(None), slice(None), slice(None), -1)):
+        assert np.all(Ax3[sl] == 0)
+    for v in (dx, dy, dz, dr):
+        v.free()
+    op.close(); old.close(); gm.close()
