@@ -17,7 +17,8 @@
 //             then  out(z') += Mz(z',z) c + Kz(z',z) d  into register accumulators of the K+1 planes of the current cell
 //             layer; when a layer is complete its K planes are written with plain coalesced stores.
 //    The only redundancy is the halo cell on the low side of the tile in x and y (re-read through L2, its X-phase rows
-//    recomputed) and one warm-up cell layer per z chunk.
+//    recomputed).  The z range of a launch is cut into chunks (one CTA each) to fill the GPU evenly; the node plane between
+//    two chunks receives one partial sum from either side by atomic adds (two addends: order-independent result).
 //  * Row pitches of the block vectors ((k n + 1) numbers) are not multiples of 16 bytes; the tensor maps therefore view a
 //    block as 16/gcd(16, pitch) interleaved row classes (2 for FP64, 4 for FP32 when the pitch is odd), each with a 16-byte
 //    aligned base and a row stride that is a multiple of 16 bytes.  A box must also START on a 16-byte boundary of global
@@ -88,7 +89,9 @@ namespace stfem
 #endif
     BrickMapDesc desc[NB][4]; // the same in plain form (host emulation, non-TMA load path)
     int          shift[NB][4]; // elements between the aligned base of a class and its first row
-    int          n_cls;
+    int          n_cls, cls_shift; // row classes, log2
+    unsigned     shift_pack;       // shift[s][c] as 2 bits at position 2 * (4 s + c)
+    int          zero_top_row;     // the top node row in y is a Dirichlet row no chunk owns: the last chunk writes its zeros
     // x: even/odd parts of vol*Mh and vol*Kh/hx^2; y, z: full matrices Mh, Kh/hy^2, Kh/hz^2 (row = output node)
     T Mxe[NE * NE], Mxo[NO * NO + 1], Kxe[NE * NE], Kxo[NO * NO + 1];
     T M[N1 * N1], Ky[N1 * N1], Kz[N1 * N1];
@@ -136,7 +139,7 @@ namespace stfem
       for (int k = 0; k < NO; ++k) Ao[i * NO + k] = (T)(0.5L * (A[i * n1 + k] - A[i * n1 + K - k]));
   }
 
-  // number of z chunks: minimise  waves x (layers per chunk + warm-up layer)  for `slots` resident CTAs
+  // number of z chunks: minimise  waves x (layers per chunk + start-up)  for `slots` resident CTAs
   inline int brick_choose_chunks(long long tiles, int layers, long long slots)
   {
     int    best = 1;
@@ -147,7 +150,7 @@ namespace stfem
         const int       real  = (layers + lpc - 1) / lpc;
         const long long ctas  = tiles * real;
         const long long waves = (ctas + slots - 1) / slots;
-        const double    cost  = (double)waves * (lpc + (real > 1 ? 1.0 : 0.0) + 0.75); // 0.75: pipeline fill of a CTA
+        const double    cost  = (double)waves * (lpc + 0.75); // 0.75: pipeline fill / drain of a CTA
         if (cost < best_cost - 1e-9)
           {
             best_cost = cost;
@@ -210,7 +213,10 @@ namespace stfem
     a.first_plane_acc = first_plane_acc ? 1 : 0;
     a.dirichlet       = dirichlet;
     a.tiles_x         = (n[0] + CX - 1) / CX;
-    a.tiles_y         = (n[1] + CY - 1) / CY;
+    // the top node row (y = K n1) is node 0 of the chunk of the non-existing cell n1: one more chunk, i.e. one more tile row
+    // when n1 is a multiple of CY - unless that row is a Dirichlet row, whose zeros the last chunk writes
+    a.zero_top_row    = (n[1] % CY == 0 && (dirichlet & 8u)) ? 1 : 0;
+    a.tiles_y         = a.zero_top_row ? n[1] / CY : (n[1] + 1 + CY - 1) / CY;
     const int layers  = zhi - zlo;
     if (n_chunks <= 0) n_chunks = brick_choose_chunks((long long)a.tiles_x * a.tiles_y, layers, slots);
     if (n_chunks > layers) n_chunks = layers;
@@ -218,14 +224,17 @@ namespace stfem
     a.n_chunks         = (layers + a.layers_per_chunk - 1) / a.layers_per_chunk;
     const long long pitch = (long long)a.np[0] * sizeof(T);
     a.n_cls               = 16 / brick_gcd(16, pitch % 16 == 0 ? 16 : pitch % 16);
+    a.cls_shift            = a.n_cls == 1 ? 0 : (a.n_cls == 2 ? 1 : 2);
     const int       HB     = (C::WY + a.n_cls - 1) / a.n_cls;
     const long long n_rows = (long long)a.np[1] * a.np[2];
     a.use_tma              = 0;
+    a.shift_pack           = 0;
     for (int b = 0; b < NB; ++b)
       {
         a.src[b] = (const T *)src[b];
         a.dst[b] = (T *)dst[b];
         brick_describe_block<T>(src[b], a.np[0], n_rows, a.n_cls, C::WXP, HB, a.desc[b], a.shift[b]);
+        for (int c = 0; c < a.n_cls; ++c) a.shift_pack |= (unsigned)a.shift[b][c] << (2 * (4 * b + c));
       }
   }
 
@@ -302,18 +311,18 @@ namespace stfem
 #pragma unroll
     for (int i = 0; i < NE; ++i)
       {
-        T ea = T(0), eb = T(0);
+        T ea = Ae[i * NE] * e[0], eb = Be[i * NE] * e[0];
 #pragma unroll
-        for (int k = 0; k < NE; ++k)
+        for (int k = 1; k < NE; ++k)
           {
             ea += Ae[i * NE + k] * e[k];
             eb += Be[i * NE + k] * e[k];
           }
         if (i < NO)
           {
-            T oa = T(0), ob = T(0);
+            T oa = Ao[i * NO] * o[0], ob = Bo[i * NO] * o[0];
 #pragma unroll
-            for (int k = 0; k < NO; ++k)
+            for (int k = 1; k < NO; ++k)
               {
                 oa += Ao[i * NO + k] * o[k];
                 ob += Bo[i * NO + k] * o[k];
@@ -340,21 +349,66 @@ namespace stfem
     return cb;
   }
 
+  // K consecutive values to shared memory, as 16-byte stores where the type and K allow (p is 16-byte aligned then)
+  template <typename T, int K>
+  __device__ __forceinline__ void brick_store_run(T *p, const T *v)
+  {
+#ifndef STFEM_HOST_EMULATION
+    if constexpr (sizeof(T) == 8 && K % 2 == 0)
+      {
+#pragma unroll
+        for (int i = 0; i < K; i += 2) *reinterpret_cast<double2 *>(p + i) = make_double2((double)v[i], (double)v[i + 1]);
+        return;
+      }
+    else if constexpr (sizeof(T) == 4 && K % 4 == 0)
+      {
+#pragma unroll
+        for (int i = 0; i < K; i += 4) *reinterpret_cast<float4 *>(p + i) = make_float4((float)v[i], (float)v[i + 1], (float)v[i + 2], (float)v[i + 3]);
+        return;
+      }
+#endif
+#pragma unroll
+    for (int i = 0; i < K; ++i) p[i] = v[i];
+  }
+
+  // mode 0 with several z chunks: the node planes shared by two chunks start from zero (both chunks add their partial sums)
+  template <typename T, int NB>
+  struct BrickZeroArgs
+  {
+    T        *dst[NB];
+    long long plane;  // numbers per node plane
+    int       first, stride, count; // planes first + k * stride, k < count
+  };
+#ifndef STFEM_HOST_EMULATION
+  template <typename T, int NB>
+  __global__ void brick_zero_planes_kernel(const BrickZeroArgs<T, NB> a)
+  {
+    const long long total = a.plane * a.count * NB;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+      {
+        const long long in_plane = e % a.plane;
+        const long long r        = e / a.plane;
+        const int       k = (int)(r % a.count), b = (int)(r / a.count);
+        a.dst[b][(long long)(a.first + k * a.stride) * a.plane + in_plane] = T(0);
+      }
+  }
+#endif
+
   template <typename T, int N1, int NB, int CX, int CY, int MINB>
   __global__ void __launch_bounds__((BrickCfg<T, N1, NB, CX, CY>::NTHREADS), MINB)
     st_vmult_brick_kernel(const __grid_constant__ BrickArgs<T, N1, NB> a)
   {
     using C = BrickCfg<T, N1, NB, CX, CY>;
-    constexpr int K = C::K, TX = C::TX, TY = C::TY, WY = C::WY, WXP = C::WXP, PXP = C::PXP, S = C::STAGES;
+    constexpr int K = C::K, TX = C::TX, WY = C::WY, WXP = C::WXP, PXP = C::PXP, S = C::STAGES, EPV = C::EPV;
     constexpr int CXL = C::CXL, RPW = C::RPW;
     extern __shared__ __align__(128) unsigned char brick_smem[];
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(brick_smem);
-    const int           n_cls = a.n_cls;
-    const int           HB = (WY + n_cls - 1) / n_cls;      // box rows per class
-    const int           sub_elems = C::sub_bytes(n_cls) / (int)sizeof(T);
-    const int           stage_elems = NB * n_cls * sub_elems;
+    const int           cshift = a.cls_shift, cmask = (1 << cshift) - 1; // row classes: 1 << cshift
+    const int           HB = (WY + cmask) >> cshift;                    // box rows per class
+    const int           sub_elems = C::sub_bytes(1 << cshift) / (int)sizeof(T);
+    const int           stage_elems = (NB << cshift) * sub_elems;
     T                  *tiles = reinterpret_cast<T *>(brick_smem + 128);
-    T                  *pq    = tiles + (size_t)S * stage_elems;
+    T                  *pq    = tiles + S * stage_elems;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -369,41 +423,43 @@ namespace stfem
     const int cz0 = a.zlo + chunk * a.layers_per_chunk;
     const int cz1 = min(a.zhi, cz0 + a.layers_per_chunk);
     if (cz0 >= cz1) return;
-    const int start = cz0 > a.zlo ? cz0 - 1 : cz0; // warm-up layer: recomputes the partial sum carried into plane K*cz0
-    const int nq    = K * (cz1 - start) + 1;       // node planes this CTA walks through
+    // The node plane between two z chunks of a launch gets a partial sum from either chunk: both add theirs atomically
+    // (two addends: the result does not depend on their order); in mode 0 the launcher zeroes those planes first.
+    const int start = cz0;
+    const int nq    = K * (cz1 - start) + 1; // node planes this CTA walks through
     const int np0 = a.np[0], np1 = a.np[1], np2 = a.np[2];
     const unsigned dm = a.dirichlet;
+    const int      xb = x0 - K;                    // first node of the tile rows (may be negative)
 
-    // ---- plane loads
+    // ---- plane loads: plane index qq of this CTA into stage qq % S.  Tensor row of tile row 0: r0(qq)
+    const int r0_first = (K * start) * np1 + (y0 - K);
     auto issue = [&](int qq) {
-      const int  stage = qq % S;
-      const long long r0 = (long long)(K * start + qq) * np1 + (y0 - K); // first tensor row of the tile (may be negative)
-      T         *st = tiles + (size_t)stage * stage_elems;
+      T *st = tiles + (qq % S) * stage_elems;
 #ifndef STFEM_HOST_EMULATION
       if (a.use_tma)
         {
           if (tid == 0)
             {
-              brick_hw::mbar_expect_tx(&bars[stage], (unsigned)(NB * n_cls * HB * WXP * (int)sizeof(T)));
+              const int r0 = r0_first + qq * np1;
+              brick_hw::mbar_expect_tx(&bars[qq % S], (unsigned)((NB << cshift) * HB * WXP * (int)sizeof(T)));
               for (int s = 0; s < NB; ++s)
-                for (int c = 0; c < n_cls; ++c)
+                for (int c = 0; c <= cmask; ++c)
                   {
-                    const long long rc = r0 + (((long long)c - r0) & (n_cls - 1)); // first row >= r0 of class c
-                    const int       mc = (int)((rc - c) / n_cls);
-                    brick_hw::tma_load_2d(st + (size_t)(s * n_cls + c) * sub_elems, &a.maps[s][c], (x0 - K + a.shift[s][c]) & ~(C::EPV - 1), mc,
-                                          &bars[stage]);
+                    const int rc = r0 + ((c - r0) & cmask); // first row >= r0 of class c
+                    const int sh = (a.shift_pack >> (2 * (4 * s + c))) & 3;
+                    brick_hw::tma_load_2d(st + ((s << cshift) + c) * sub_elems, &a.maps[s][c], (xb + sh) & ~(EPV - 1), (rc - c) >> cshift, &bars[qq % S]);
                   }
             }
           return;
         }
 #endif
+      const int r0 = r0_first + qq * np1;
       for (int s = 0; s < NB; ++s)
-        for (int c = 0; c < n_cls; ++c)
+        for (int c = 0; c <= cmask; ++c)
           {
-            const long long rc = r0 + (((long long)c - r0) & (n_cls - 1));
-            const int       mc = (int)((rc - c) / n_cls);
-            brick_box_load_plain<T>(st + (size_t)(s * n_cls + c) * sub_elems, a.desc[s][c], (x0 - K + a.shift[s][c]) & ~(C::EPV - 1), mc, tid,
-                                    C::NTHREADS);
+            const int rc = r0 + ((c - r0) & cmask);
+            const int sh = (a.shift_pack >> (2 * (4 * s + c))) & 3;
+            brick_box_load_plain<T>(st + ((s << cshift) + c) * sub_elems, a.desc[s][c], (xb + sh) & ~(EPV - 1), (rc - c) >> cshift, tid, C::NTHREADS);
           }
     };
 
@@ -420,58 +476,116 @@ namespace stfem
       }
 #endif
 
-    // ---- Y+Z phase identity of this thread: lane = x node of the tile, warp = (cell row yc, dst block j)
+    // ---- X phase identity of this thread: lane = (tile row within the warp, cell), all plane-independent pieces hoisted
+    const bool x_lane_ok = lane < RPW * CXL;
+    const int  xr  = x_lane_ok ? lane % RPW : 0;
+    const int  xci = brick_cell_of<CXL, RPW>(x_lane_ok ? lane / RPW : 0); // 0 = halo cell on the low side
+    const int  xyl = warp * RPW + xr;                                     // tile row
+    const bool x_row_in = warp < C::XW && x_lane_ok && xyl < WY;
+    bool       x_valid0;
+    bool       x_zero_u0, x_zero_uK;
+    {
+      const int yg = y0 - K + xyl, cxg = cx0 - 1 + xci;
+      x_valid0  = x_row_in && yg >= 0 && yg < np1 && !((dm & 4u) && yg == 0) && !((dm & 8u) && yg == np1 - 1) && cxg >= 0 && cxg < a.n[0];
+      x_zero_u0 = (dm & 1u) && cxg == 0;
+      x_zero_uK = (dm & 2u) && cxg == a.n[0] - 1;
+    }
+    int x_src_lane = lane; // lane holding the left neighbour cell of the same tile row
+    if (x_lane_ok && xci >= 1)
+      {
+        int cbl = 0;
+#pragma unroll
+        for (int t = 0; t < CXL; ++t)
+          if (brick_cell_of<CXL, RPW>(t) == xci - 1) cbl = t;
+        x_src_lane = xr + RPW * cbl;
+      }
+    const bool x_store  = x_row_in && xci >= 1;
+    const int  x_st_off = xyl * PXP + K * (xci - 1); // P/Q store offset inside a field
+
+    // ---- Y+Z phase identity: lane = x node of the tile, warp = (cell row yc, dst block j)
     const int  yc = warp % CY, jz = warp / CY;
-    const bool yz_warp = warp < C::YW;
     const int  xo = lane <= TX ? lane : TX;
     const int  xg = x0 + xo;
-    const bool last_tile_y = cy0 + CY >= a.n[1];
-    const bool extra       = last_tile_y && yc == CY - 1; // also owns the node row K*CY of the tile (last plane of the mesh)
-    const bool has_below   = cy0 + yc >= 1;               // the cell below this chunk's first node row exists
-    const bool has_above   = cy0 + yc < a.n[1];
-    const bool x_store     = lane <= TX && xg < np0 && (lane < TX || xg == np0 - 1);
-    const bool x_con       = ((dm & 1u) && xg == 0) || ((dm & 2u) && xg == np0 - 1);
-    T          acc[N1][N1]; // [node of the chunk][plane of the current cell layer]
+    const int  cyg = cy0 + yc;                      // cell whose K node rows K*cyg .. K*cyg + K - 1 this thread owns
+    const bool yz_warp = warp < C::YW && cyg <= a.n[1];
+    const bool has_below = cyg >= 1, has_above = cyg < a.n[1];
+    const int  yz_ld_off = (K * yc) * PXP + xo;
+    // stores: node nn of the chunk is written iff st_mask bit nn; its value is forced to 0 iff con_mask bit nn
+    unsigned   st_mask = 0, con_mask = 0;
+    {
+      const bool x_ok  = lane <= TX && xg < np0 && (lane < TX || xg == np0 - 1);
+      const bool x_con = ((dm & 1u) && xg == 0) || ((dm & 2u) && xg == np0 - 1);
 #pragma unroll
-    for (int nn = 0; nn < N1; ++nn)
+      for (int nn = 0; nn < K; ++nn)
+        {
+          const int yg = K * cyg + nn;
+          if (x_ok && yg < np1) st_mask |= 1u << nn;
+          if (x_con || ((dm & 4u) && yg == 0) || ((dm & 8u) && yg == np1 - 1)) con_mask |= 1u << nn;
+        }
+      // the top node row of a mesh whose cell count is a multiple of CY is not owned by any chunk when it is a Dirichlet row
+      // (the launcher then saves the extra tile row): the last chunk writes its zeros
+      if (a.zero_top_row && x_ok && cyg == a.n[1] - 1) st_mask |= 1u << K;
+    }
+    T *const dst_base = a.dst[jz] + ((long long)xg + (long long)np0 * (K * cyg));
+    const long long plane_stride = (long long)np0 * np1;
+    T          acc[K][N1]; // [node of the chunk][plane of the current cell layer]
+#pragma unroll
+    for (int nn = 0; nn < K; ++nn)
 #pragma unroll
       for (int i = 0; i < N1; ++i) acc[nn][i] = T(0);
 
-    // write plane z (local plane index i of the accumulators) of the chunk's nodes
-    auto store_plane = [&](int z, auto itag) {
+    // write plane z (local plane index i of the accumulators) of the chunk's nodes; shared: the plane also receives a
+    // partial sum from the neighbouring z chunk of this launch
+    auto store_plane = [&](int z, auto itag, bool shared) {
       constexpr int i = decltype(itag)::value;
       const bool    z_con = ((dm & 16u) && z == 0) || ((dm & 32u) && z == np2 - 1);
-      const bool    add   = a.mode == 1 || (a.first_plane_acc && z == K * a.zlo);
-#pragma unroll
-      for (int nn = 0; nn < N1; ++nn)
+      T            *p     = dst_base + plane_stride * z;
+      if (shared)
         {
-          if (nn == K && !extra) continue;
-          const int yg = y0 + K * yc + nn;
-          if (!x_store || yg >= np1 || (nn == K && yg != np1 - 1)) continue;
-          const bool con = x_con || z_con || ((dm & 4u) && yg == 0) || ((dm & 8u) && yg == np1 - 1);
-          T         *p   = a.dst[jz] + ((long long)xg + (long long)np0 * ((long long)yg + (long long)np1 * z));
-          if (add)
+          if (!z_con)
             {
-              if (!con) *p += acc[nn][i];
+#pragma unroll
+              for (int nn = 0; nn < K; ++nn)
+                if (((st_mask & ~con_mask) >> nn) & 1u) atomicAdd(p + nn * np0, acc[nn][i]);
             }
-          else
-            *p = con ? T(0) : acc[nn][i];
+        }
+      else if (a.mode == 1 || (a.first_plane_acc && z == K * a.zlo))
+        {
+          if (!z_con)
+            {
+#pragma unroll
+              for (int nn = 0; nn < K; ++nn)
+                if (((st_mask & ~con_mask) >> nn) & 1u) p[nn * np0] += acc[nn][i];
+            }
+        }
+      else if (!z_con && con_mask == 0 && !((st_mask >> K) & 1u))
+        {
+#pragma unroll
+          for (int nn = 0; nn < K; ++nn)
+            if ((st_mask >> nn) & 1u) p[nn * np0] = acc[nn][i];
+        }
+      else
+        {
+#pragma unroll
+          for (int nn = 0; nn < K; ++nn)
+            if ((st_mask >> nn) & 1u) p[nn * np0] = (z_con || ((con_mask >> nn) & 1u)) ? T(0) : acc[nn][i];
+          if ((st_mask >> K) & 1u) p[K * np0] = T(0);
         }
     };
 
     // ---- march through the planes
-    for (int q = 0; q < nq; ++q)
+    int r0 = r0_first;
+    for (int q = 0; q < nq; ++q, r0 += np1)
       {
         const int  zp    = K * start + q; // node plane
         const int  m     = q % K;         // its local index in the current cell layer (0: also node K of the layer below)
         const int  layer = start + q / K;
-        const int  stage = q % S;
         const bool plane_con = ((dm & 16u) && zp == 0) || ((dm & 32u) && zp == np2 - 1);
-        T         *st  = tiles + (size_t)stage * stage_elems;
-        T         *pqb = pq + (size_t)(q & 1) * C::PQ_BUF;
+        T         *st  = tiles + (q % S) * stage_elems;
+        T         *pqb = pq + (q & 1) * C::PQ_BUF;
 #ifndef STFEM_HOST_EMULATION
         if (a.use_tma)
-          brick_hw::mbar_wait(&bars[stage], (unsigned)((q / S) & 1));
+          brick_hw::mbar_wait(&bars[q % S], (unsigned)((q / S) & 1));
         else
 #endif
           {
@@ -482,89 +596,67 @@ namespace stfem
         // ================= X phase
         if (warp < C::XW)
           {
-            const bool lane_ok = lane < RPW * CXL;
-            const int  r  = lane_ok ? lane % RPW : 0;
-            const int  cb = lane_ok ? lane / RPW : 0;
-            const int  ci = brick_cell_of<CXL, RPW>(cb); // 0 = halo cell on the low side
-            const int  yl = warp * RPW + r;
-            const bool row_in = lane_ok && yl < WY;
-            const int  yg  = y0 - K + yl;
-            const int  cxg = cx0 - 1 + ci;
-            const bool valid = row_in && !plane_con && yg >= 0 && yg < np1 && !((dm & 4u) && yg == 0) && !((dm & 8u) && yg == np1 - 1) &&
-                               cxg >= 0 && cxg < a.n[0];
-            T P[NB][N1], Q[NB][N1];
+            const bool valid = x_valid0 && !plane_con;
+            // tile row xyl sits in class c at index idx of that class' box
+            const int g   = r0 + xyl;
+            const int c   = g & cmask;
+            const int idx = (g - (r0 + ((c - r0) & cmask))) >> cshift;
+            T         P[NB][N1], Q[NB][N1];
 #pragma unroll
-            for (int j = 0; j < NB; ++j)
-#pragma unroll
-              for (int i = 0; i < N1; ++i) P[j][i] = Q[j][i] = T(0);
-            if (valid)
+            for (int s = 0; s < NB; ++s)
               {
-                // tile row yl sits in class c at index idx of that class' box
-                const long long r0  = (long long)zp * np1 + (y0 - K);
-                const int       c   = (int)((r0 + yl) & (n_cls - 1));
-                const long long rc  = r0 + (((long long)c - r0) & (n_cls - 1));
-                const int       idx = (int)((r0 + yl - rc) / n_cls);
+                // the box of this class starts at the 16-byte boundary at or below the first node of the tile row
+                const int lead = (xb + ((a.shift_pack >> (2 * (4 * s + c))) & 3)) & (EPV - 1);
+                const T  *row  = st + ((s << cshift) + c) * sub_elems + idx * WXP + lead + K * xci;
+                T         u[N1], av[N1], bv[N1];
 #pragma unroll
-                for (int s = 0; s < NB; ++s)
+                for (int i = 0; i < N1; ++i) u[i] = valid ? row[i] : T(0);
+                if (x_zero_u0) u[0] = T(0);
+                if (x_zero_uK) u[K] = T(0);
+                brick_eo_apply2<T, N1>(u, a.Mxe, a.Mxo, a.Kxe, a.Kxo, av, bv);
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
                   {
-                    // the box of this class starts at the 16-byte boundary at or below the first node of the tile row
-                    const int lead = (x0 - K + a.shift[s][c]) & (C::EPV - 1);
-                    const T  *row  = st + (size_t)(s * n_cls + c) * sub_elems + (size_t)idx * WXP + lead + K * ci;
-                    T        u[N1], av[N1], bv[N1];
+                    const T be = a.beta[j * NB + s], al = a.alpha[j * NB + s];
 #pragma unroll
-                    for (int i = 0; i < N1; ++i) u[i] = row[i];
-                    if ((dm & 1u) && cxg == 0) u[0] = T(0);
-                    if ((dm & 2u) && cxg == a.n[0] - 1) u[K] = T(0);
-                    brick_eo_apply2<T, N1>(u, a.Mxe, a.Mxo, a.Kxe, a.Kxo, av, bv);
-#pragma unroll
-                    for (int j = 0; j < NB; ++j)
+                    for (int i = 0; i < N1; ++i)
                       {
-                        const T be = a.beta[j * NB + s], al = a.alpha[j * NB + s];
-#pragma unroll
-                        for (int i = 0; i < N1; ++i)
+                        if (s == 0)
+                          {
+                            P[j][i] = be * av[i];
+                            Q[j][i] = al * av[i];
+                          }
+                        else
                           {
                             P[j][i] += be * av[i];
-                            P[j][i] += al * bv[i];
                             Q[j][i] += al * av[i];
                           }
+                        P[j][i] += al * bv[i];
                       }
                   }
               }
             // the vertex shared with the left cell: add that cell's partial sum (all lanes take part in the shuffles)
-            int src_lane = lane;
-            if (lane_ok && ci >= 1)
-              {
-                int cbl = 0;
-#pragma unroll
-                for (int t = 0; t < CXL; ++t)
-                  if (brick_cell_of<CXL, RPW>(t) == ci - 1) cbl = t;
-                src_lane = r + RPW * cbl;
-              }
 #pragma unroll
             for (int j = 0; j < NB; ++j)
               {
-                const T pk = __shfl_sync(0xffffffffu, P[j][K], src_lane);
-                const T qk = __shfl_sync(0xffffffffu, Q[j][K], src_lane);
-                if (lane_ok && ci >= 1)
+                const T pk = __shfl_sync(0xffffffffu, P[j][K], x_src_lane);
+                const T qk = __shfl_sync(0xffffffffu, Q[j][K], x_src_lane);
+                if (x_src_lane != lane)
                   {
                     P[j][0] += pk;
                     Q[j][0] += qk;
                   }
               }
-            if (row_in && ci >= 1)
+            if (x_store)
               {
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
                   {
-                    T *pp = pqb + (size_t)(0 * NB + j) * C::PQ_FIELD + (size_t)yl * PXP + K * (ci - 1);
-                    T *qp = pqb + (size_t)(1 * NB + j) * C::PQ_FIELD + (size_t)yl * PXP + K * (ci - 1);
-#pragma unroll
-                    for (int i = 0; i < K; ++i)
-                      {
-                        pp[i] = P[j][i];
-                        qp[i] = Q[j][i];
-                      }
-                    if (ci == CX)
+                    T *pp = pqb + (0 * NB + j) * C::PQ_FIELD + x_st_off;
+                    T *qp = pqb + (1 * NB + j) * C::PQ_FIELD + x_st_off;
+                    brick_store_run<T, K>(pp, P[j]);
+                    brick_store_run<T, K>(qp, Q[j]);
+                    if (xci == CX)
                       {
                         pp[K] = P[j][K];
                         qp[K] = Q[j][K];
@@ -572,7 +664,7 @@ namespace stfem
                   }
               }
           }
-        __syncthreads(); // P, Q of this plane complete; stage `stage` consumed by everybody
+        __syncthreads(); // P, Q of this plane complete; stage q % S consumed by everybody
 #ifndef STFEM_HOST_EMULATION
         if (a.use_tma && q + S < nq) issue(q + S);
 #endif
@@ -580,8 +672,8 @@ namespace stfem
         // ================= Y + Z phase
         if (yz_warp)
           {
-            const T *pp = pqb + (size_t)(0 * NB + jz) * C::PQ_FIELD + (size_t)(K * yc) * PXP + xo;
-            const T *qp = pqb + (size_t)(1 * NB + jz) * C::PQ_FIELD + (size_t)(K * yc) * PXP + xo;
+            const T *pp = pqb + (0 * NB + jz) * C::PQ_FIELD + yz_ld_off;
+            const T *qp = pqb + (1 * NB + jz) * C::PQ_FIELD + yz_ld_off;
             T        p[2 * K + 1], qv[2 * K + 1];
 #pragma unroll
             for (int t = 0; t < 2 * K + 1; ++t)
@@ -589,12 +681,14 @@ namespace stfem
                 p[t]  = pp[t * PXP];
                 qv[t] = qp[t * PXP];
               }
-            T c[N1], d[N1];
+            T c[K], d[K];
             // node 0 of the chunk: vertex row shared by the cell below (its node K) and the cell above (its node 0)
             {
-              T cb_ = T(0), db_ = T(0), ca_ = T(0), da_ = T(0);
+              T cb_ = a.M[K * N1] * p[0], db_ = a.M[K * N1] * qv[0], ca_ = a.M[0] * p[K], da_ = a.M[0] * qv[K];
+              cb_ += a.Ky[K * N1] * qv[0];
+              ca_ += a.Ky[0] * qv[K];
 #pragma unroll
-              for (int t = 0; t < N1; ++t)
+              for (int t = 1; t < N1; ++t)
                 {
                   cb_ += a.M[K * N1 + t] * p[t];
                   cb_ += a.Ky[K * N1 + t] * qv[t];
@@ -607,16 +701,12 @@ namespace stfem
               d[0] = (has_below ? db_ : T(0)) + (has_above ? da_ : T(0));
             }
 #pragma unroll
-            for (int nn = 1; nn < N1; ++nn)
+            for (int nn = 1; nn < K; ++nn)
               {
-                if (nn == K && !extra)
-                  {
-                    c[nn] = d[nn] = T(0);
-                    continue;
-                  }
-                T cc = T(0), dd = T(0);
+                T cc = a.M[nn * N1] * p[K], dd = a.M[nn * N1] * qv[K];
+                cc += a.Ky[nn * N1] * qv[K];
 #pragma unroll
-                for (int t = 0; t < N1; ++t)
+                for (int t = 1; t < N1; ++t)
                   {
                     cc += a.M[nn * N1 + t] * p[K + t];
                     cc += a.Ky[nn * N1 + t] * qv[K + t];
@@ -628,34 +718,30 @@ namespace stfem
             auto zacc = [&](auto mtag) {
               constexpr int mm = decltype(mtag)::value;
 #pragma unroll
-              for (int nn = 0; nn < N1; ++nn)
-                {
-                  if (nn == K && !extra) continue;
+              for (int nn = 0; nn < K; ++nn)
 #pragma unroll
-                  for (int i = 0; i < N1; ++i)
-                    {
-                      acc[nn][i] += a.M[i * N1 + mm] * c[nn];
-                      acc[nn][i] += a.Kz[i * N1 + mm] * d[nn];
-                    }
-                }
+                for (int i = 0; i < N1; ++i)
+                  {
+                    acc[nn][i] += a.M[i * N1 + mm] * c[nn];
+                    acc[nn][i] += a.Kz[i * N1 + mm] * d[nn];
+                  }
             };
             if (m == 0)
               {
                 if (q > 0)
                   {
                     zacc(std::integral_constant<int, K>()); // closes cell layer `layer - 1`
-                    if (layer - 1 >= cz0)
-                      {
-                        const int zb = K * (layer - 1);
-                        if (K > 0) store_plane(zb + 0, std::integral_constant<int, 0>());
-                        if (K > 1) store_plane(zb + 1, std::integral_constant<int, (K > 1 ? 1 : 0)>());
-                        if (K > 2) store_plane(zb + 2, std::integral_constant<int, (K > 2 ? 2 : 0)>());
-                        if (K > 3) store_plane(zb + 3, std::integral_constant<int, (K > 3 ? 3 : 0)>());
-                        if (K > 4) store_plane(zb + 4, std::integral_constant<int, (K > 4 ? 4 : 0)>());
-                        if (K > 5) store_plane(zb + 5, std::integral_constant<int, (K > 5 ? 5 : 0)>());
-                      }
+                    {
+                      const int zb = K * (layer - 1);
+                      store_plane(zb + 0, std::integral_constant<int, 0>(), layer - 1 == cz0 && cz0 > a.zlo);
+                      if (K > 1) store_plane(zb + 1, std::integral_constant<int, (K > 1 ? 1 : 0)>(), false);
+                      if (K > 2) store_plane(zb + 2, std::integral_constant<int, (K > 2 ? 2 : 0)>(), false);
+                      if (K > 3) store_plane(zb + 3, std::integral_constant<int, (K > 3 ? 3 : 0)>(), false);
+                      if (K > 4) store_plane(zb + 4, std::integral_constant<int, (K > 4 ? 4 : 0)>(), false);
+                      if (K > 5) store_plane(zb + 5, std::integral_constant<int, (K > 5 ? 5 : 0)>(), false);
+                    }
 #pragma unroll
-                    for (int nn = 0; nn < N1; ++nn)
+                    for (int nn = 0; nn < K; ++nn)
                       {
                         acc[nn][0] = acc[nn][K];
 #pragma unroll
@@ -677,7 +763,8 @@ namespace stfem
               }
           }
       }
-    // the top plane of the launch range: complete if it is the top of the mesh, else the partial sum of the cells below
-    if (yz_warp && cz1 == a.zhi) store_plane(K * cz1, std::integral_constant<int, 0>());
+    // the top plane of the chunk: shared with the chunk above; at the top of the launch range it is complete (top of the
+    // mesh) or the partial sum of the cells below (z-slab launches)
+    if (yz_warp) store_plane(K * cz1, std::integral_constant<int, 0>(), cz1 < a.zhi);
   }
 } // namespace stfem

@@ -78,10 +78,22 @@ namespace stfem
             a.use_tma = 0; // the driver refused the descriptor: plain loads
             break;
           }
+    cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
+    if (a.n_chunks > 1 && !accumulate)
+      {
+        BrickZeroArgs<T, NB> z;
+        for (int b = 0; b < NB; ++b) z.dst[b] = (T *)dst[b];
+        z.plane  = (long long)a.np[0] * a.np[1];
+        z.first  = (N1 - 1) * (zlo + a.layers_per_chunk);
+        z.stride = (N1 - 1) * a.layers_per_chunk;
+        z.count  = a.n_chunks - 1;
+        const long long total = z.plane * z.count * NB;
+        brick_zero_planes_kernel<T, NB><<<(unsigned)std::min<long long>((total + 255) / 256, (long long)m->ctx->sm_count * 8), 256, 0, stream>>>(z);
+        m->ctx->launches++;
+      }
     const size_t smem = (size_t)C::smem_bytes(a.n_cls);
     auto         kern = st_vmult_brick_kernel<T, N1, NB, CX, CY, MINB>;
     STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaStream_t    stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
     const long long grid   = (long long)a.tiles_x * a.tiles_y * a.n_chunks;
     STFEM_REQUIRE(grid < (1ll << 31), "st_vmult (brick): grid too large");
     kern<<<(unsigned)grid, C::NTHREADS, smem, stream>>>(a);

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -52,6 +53,12 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src)
   const T r = (T)w.buf[src & 31];
   w.bar.arrive_and_wait();
   return r;
+}
+static std::mutex g_atomic_mutex;
+template <class T> inline void atomicAdd(T *p, T v)
+{
+  std::lock_guard<std::mutex> lock(g_atomic_mutex);
+  *p += v;
 }
 using std::max;
 using std::min;
@@ -119,6 +126,14 @@ static int run(const Cmd &cmd, const std::vector<double> &in, std::vector<double
   for (int b = 0; b < NB; ++b)
     for (int c = 0; c < a.n_cls; ++c) std::printf(" %d", a.shift[b][c]);
   std::printf("), smem %d bytes, grid %lld\n", C::smem_bytes(a.n_cls), grid);
+  // what launch_brick does before the kernel: the node planes shared by two z chunks start from zero in mode 0
+  if (a.n_chunks > 1 && cmd.mode == 0)
+    {
+      const long long plane = (long long)a.np[0] * a.np[1];
+      for (int b = 0; b < NB; ++b)
+        for (int k = 1; k < a.n_chunks; ++k)
+          for (long long e = 0; e < plane; ++e) ((T *)dp[b])[(long long)degree * (cmd.zlo + k * a.layers_per_chunk) * plane + e] = T(0);
+    }
   g_warps.clear();
   for (int w = 0; w < C::NWARPS; ++w) g_warps.push_back(std::make_unique<WarpExchange>());
   for (long long blk = 0; blk < grid; ++blk)
