@@ -30,8 +30,17 @@ namespace stfem
     const std::vector<double> &hA = *brick_host_matrix(op, alpha), &hB = *brick_host_matrix(op, beta);
     const int  zlo = op->box_lo ? op->box_lo[2] : 0, zhi = op->box_lo ? op->box_lo[2] + op->box_n[2] : op->mesh->n[2];
     static const bool no_tma = std::getenv("STFEM_BRICK_NO_TMA") != nullptr;
-    const bool tma = op->variant != 70 && !no_tma;
+    const int  tma = (op->variant == 70 || no_tma) ? 0 : (op->variant == 79 ? 2 : 1); // 79: full / empty barrier pipeline instead of CTA barriers
     const int  n_chunks = op->variant >= 80 && op->variant < 90 ? op->variant - 79 : 0; // 0: chosen by the launcher
+    // tuning variants of the headline instance (Q4, two blocks): other tile heights / CTAs per SM
+    if (op->variant == 77 && op->degree == 4 && nb == 2) // X and Y+Z phases on separate warps, one CTA per SM
+      return launch_brick<5, 2, T, 7, 4, 1, true>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 78 && op->degree == 4 && nb == 2)
+      return launch_brick<5, 2, T, 7, 5, 1, true>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 73 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 2, 4>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 74 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 2>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 75 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 6, 1>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 76 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 3>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
     if (op->variant == 71 && op->degree == 4 && nb == 2) // tuning: one CTA per SM with the full register budget
       return launch_brick<5, 2, T, BrickTile<5>::CX, BrickTile<5>::CY, 1>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
 #define STFEM_BRICK_CASE(N1_, NB_, MINB_)                                                                                             \

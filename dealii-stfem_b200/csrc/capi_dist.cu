@@ -1,4 +1,7 @@
 // C ABI + implementation of the multi-GPU layer (see dist.cuh).
+#include <algorithm>
+#include <cstdlib>
+
 #include "dist.cuh"
 #include "op.hpp"
 
@@ -44,6 +47,87 @@ namespace stfem
     return &g_nccl;
   }
 
+  // the neighbours of this brick in the process grid and the node boxes shared with them
+  static void halo_build_plan(HaloPlan &pl, const Partition &part, int nb, const int np[3], int dim, int my_rank)
+  {
+    pl        = HaloPlan();
+    pl.nb     = nb;
+    pl.my_rank = my_rank;
+    for (int d = 0; d < 3; ++d) pl.np[d] = d < dim ? np[d] : 1;
+    for (int i = 0; i < 27; ++i) pl.seg_of[i] = -1;
+    for (int d = 0; d < dim; ++d)
+      for (int sd = 0; sd < 2; ++sd)
+        if (part.neighbor[d][sd] >= 0) pl.has |= 1u << (2 * d + sd);
+    pl.start[0] = 0;
+    for (int oz = -1; oz <= 1; ++oz)
+      for (int oy = -1; oy <= 1; ++oy)
+        for (int ox = -1; ox <= 1; ++ox)
+          {
+            const int o[3] = {ox, oy, oz};
+            if (ox == 0 && oy == 0 && oz == 0) continue;
+            int  c[3];
+            bool ok = true;
+            for (int d = 0; d < 3; ++d)
+              {
+                c[d] = part.coords[d] + o[d];
+                if ((d >= dim && o[d] != 0) || c[d] < 0 || c[d] >= part.grid[d]) ok = false;
+              }
+            if (!ok) continue;
+            const int sgm = pl.n_seg++;
+            pl.rank[sgm]  = part.rank_of(c);
+            long long box = 1;
+            for (int d = 0; d < 3; ++d)
+              {
+                pl.off[sgm][d] = o[d];
+                pl.lo[sgm][d]  = o[d] > 0 ? pl.np[d] - 1 : 0;
+                pl.ext[sgm][d] = o[d] == 0 ? pl.np[d] : 1;
+                box *= pl.ext[sgm][d];
+              }
+            pl.seg_of[(ox + 1) + 3 * (oy + 1) + 9 * (oz + 1)] = sgm;
+            pl.start[sgm + 1] = pl.start[sgm] + box * nb;
+          }
+  }
+
+  // all interface partial sums in one grouped send / receive (see HaloPlan)
+  template <typename T>
+  static int halo_exchange_single_round(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim,
+                                        cudaStream_t stream)
+  {
+    NcclApi *api = nccl_api();
+    HaloPlan &pl = hb.plan;
+    if (pl.nb != nb || pl.np[0] != np[0] || pl.np[1] != (dim > 1 ? np[1] : 1) || pl.np[2] != (dim > 2 ? np[2] : 1) || pl.n_seg == 0)
+      halo_build_plan(pl, part, nb, np, dim, ctx->rank);
+    if (pl.n_seg == 0) return STFEM_OK;
+    const long long total = pl.start[pl.n_seg];
+    const size_t    need  = (size_t)total * sizeof(T);
+    if (hb.bytes_all < need)
+      {
+        if (hb.send_all) cudaFree(hb.send_all);
+        if (hb.recv_all) cudaFree(hb.recv_all);
+        STFEM_CUDA_CHECK(cudaMalloc(&hb.send_all, need));
+        STFEM_CUDA_CHECK(cudaMalloc(&hb.recv_all, need));
+        hb.bytes_all = need;
+      }
+    BlockPtrs bp;
+    for (int b = 0; b < STFEM_MAX_BLOCKS; ++b) bp.p[b] = b < nb ? blocks[b] : nullptr;
+    const int threads = 256;
+    const int grid    = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 8);
+    k_halo_pack<T><<<grid, threads, 0, stream>>>(bp, pl, (T *)hb.send_all);
+    ctx->launches++;
+    STFEM_NCCL_CHECK(api->GroupStart());
+    for (int sgm = 0; sgm < pl.n_seg; ++sgm)
+      {
+        const size_t cnt = (size_t)(pl.start[sgm + 1] - pl.start[sgm]) * sizeof(T);
+        STFEM_NCCL_CHECK(api->Send((const char *)hb.send_all + (size_t)pl.start[sgm] * sizeof(T), cnt, NcclApi::kChar, pl.rank[sgm], (nccl_comm_t)ctx->nccl_comm, stream));
+        STFEM_NCCL_CHECK(api->Recv((char *)hb.recv_all + (size_t)pl.start[sgm] * sizeof(T), cnt, NcclApi::kChar, pl.rank[sgm], (nccl_comm_t)ctx->nccl_comm, stream));
+      }
+    STFEM_NCCL_CHECK(api->GroupEnd());
+    k_halo_unpack_sum<T><<<grid, threads, 0, stream>>>(bp, pl, (const T *)hb.recv_all);
+    ctx->launches++;
+    STFEM_CUDA_CHECK(cudaGetLastError());
+    return STFEM_OK;
+  }
+
   template <typename T>
   int halo_compress_add(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim,
                         cudaStream_t stream)
@@ -52,6 +136,9 @@ namespace stfem
     if (!stream) stream = ctx->stream;
     NcclApi *api = nccl_api();
     STFEM_REQUIRE(api && ctx->nccl_comm, "halo exchange: context has no NCCL communicator (stfem_ctx_comm_init)");
+    STFEM_REQUIRE(nb <= STFEM_MAX_BLOCKS, "halo: too many blocks");
+    static const bool rounds = std::getenv("STFEM_HALO_ROUNDS") != nullptr; // the direction-by-direction exchange of round 1
+    if (!rounds) return halo_exchange_single_round<T>(ctx, part, hb, blocks, nb, np, dim, stream);
     // buffers sized for the largest face
     size_t maxface = 0;
     for (int d = 0; d < dim; ++d)
@@ -260,6 +347,68 @@ int stfem_mesh_set_partition(stfem_mesh_t mesh, const int *proc_grid, const int 
         p.neighbor[d][s] = (c[d] < 0 || c[d] >= p.grid[d]) ? -1 : p.rank_of(c);
       }
   p.active = total > 1;
+  return STFEM_OK;
+}
+
+// TEST HOOK (host only, no GPU, no NCCL): the single-round interface exchange among the n_ranks = prod(proc_grid) bricks of a
+// box partition, run in this process with the very element functions the pack / unpack kernels execute
+// (halo_pack_element / halo_unpack_element, csrc/dist.cuh) and memcpy in place of ncclSend / ncclRecv.
+// data: [n_ranks][nb][np0*np1*np2] doubles, the partial sums of every rank's brick; summed in place.
+int stfem_halo_emulate_host(int dim, const int *proc_grid, const int *np, int nb, double *data)
+{
+  STFEM_REQUIRE(dim >= 1 && dim <= 3 && proc_grid && np && data && nb >= 1 && nb <= STFEM_MAX_BLOCKS, "stfem_halo_emulate_host: bad arguments");
+  int       n_ranks = 1;
+  long long N = 1;
+  for (int d = 0; d < dim; ++d)
+    {
+      n_ranks *= proc_grid[d];
+      N *= np[d];
+    }
+  std::vector<HaloPlan>            plans(n_ranks);
+  std::vector<std::vector<double>> send(n_ranks), recv(n_ranks);
+  std::vector<BlockPtrs>           bps(n_ranks);
+  for (int r = 0; r < n_ranks; ++r)
+    {
+      Partition part;
+      int       rr = r;
+      for (int d = 0; d < 3; ++d)
+        {
+          part.grid[d]   = d < dim ? proc_grid[d] : 1;
+          part.coords[d] = rr % part.grid[d];
+          rr /= part.grid[d];
+        }
+      for (int d = 0; d < 3; ++d)
+        for (int sd = 0; sd < 2; ++sd)
+          {
+            int c[3] = {part.coords[0], part.coords[1], part.coords[2]};
+            c[d] += sd == 0 ? -1 : 1;
+            part.neighbor[d][sd] = (c[d] < 0 || c[d] >= part.grid[d]) ? -1 : part.rank_of(c);
+          }
+      part.active = n_ranks > 1;
+      halo_build_plan(plans[r], part, nb, np, dim, r);
+      for (int b = 0; b < STFEM_MAX_BLOCKS; ++b) bps[r].p[b] = b < nb ? data + ((size_t)r * nb + b) * N : nullptr;
+      const long long total = plans[r].start[plans[r].n_seg];
+      send[r].assign(total, 0.0);
+      recv[r].assign(total, 0.0);
+      for (long long g = 0; g < total; ++g) halo_pack_element<double>(bps[r], plans[r], g, send[r].data());
+    }
+  // "send / receive": segment s of rank r goes to the segment of the opposite offset on rank plans[r].rank[s]
+  for (int r = 0; r < n_ranks; ++r)
+    for (int sgm = 0; sgm < plans[r].n_seg; ++sgm)
+      {
+        const int      peer = plans[r].rank[sgm];
+        const int     *o    = plans[r].off[sgm];
+        const int      t    = plans[peer].seg_of[(-o[0] + 1) + 3 * (-o[1] + 1) + 9 * (-o[2] + 1)];
+        STFEM_REQUIRE(t >= 0 && plans[peer].rank[t] == r, "stfem_halo_emulate_host: neighbour relation is not symmetric");
+        const long long cnt = plans[r].start[sgm + 1] - plans[r].start[sgm];
+        STFEM_REQUIRE(cnt == plans[peer].start[t + 1] - plans[peer].start[t], "stfem_halo_emulate_host: segment sizes differ");
+        std::memcpy(recv[peer].data() + plans[peer].start[t], send[r].data() + plans[r].start[sgm], sizeof(double) * cnt);
+      }
+  for (int r = 0; r < n_ranks; ++r)
+    {
+      const long long total = plans[r].start[plans[r].n_seg];
+      for (long long g = 0; g < total; ++g) halo_unpack_element<double>(bps[r], plans[r], g, recv[r].data());
+    }
   return STFEM_OK;
 }
 

@@ -694,9 +694,12 @@ namespace stfem
     const PartitionInfo &part = op->mesh->part;
     static const bool no_overlap = std::getenv("STFEM_NO_OVERLAP") != nullptr;
     const int *mn = op->mesh->n;
-    const bool overlap = part.active && uses_cart(op) && !no_overlap && mn[0] >= 8 && mn[1] >= 8 && mn[2] >= 8;
-    // the brick kernel writes every DoF exactly once: no zero fill, accumulation (if any) happens in its store
-    const bool brick = !overlap && brick_eligible(op, nb_src, nb_dst, alpha, beta);
+    // the brick kernel writes every DoF exactly once: no zero fill, accumulation (if any) happens in its store.  On
+    // partitioned meshes it runs over the whole brick and ONE grouped exchange follows (latency ~ one send/receive; the
+    // shell / interior overlap below belongs to the per-cell kernel, whose three exchange rounds it was built to hide)
+    static const bool part_no_brick = std::getenv("STFEM_PART_NO_BRICK") != nullptr;
+    const bool brick   = brick_eligible(op, nb_src, nb_dst, alpha, beta) && !(part.active && part_no_brick);
+    const bool overlap = !brick && part.active && uses_cart(op) && !no_overlap && mn[0] >= 8 && mn[1] >= 8 && mn[2] >= 8;
     if ((zero_dst || via_scratch) && !brick)
       for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(target[b], 0, bytes, ctx->stream));
     auto dispatch = [&]() -> int {

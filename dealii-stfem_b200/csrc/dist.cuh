@@ -134,10 +134,125 @@ namespace stfem
       }
   }
 
+  // ---- single-round exchange: every rank of the 3x3x3 neighbourhood that shares nodes with this brick (faces, edges,
+  // corners) gets this rank's partial sums of exactly the shared nodes in ONE grouped send/receive; the receiver then adds
+  // the up to 8 partial sums of a node IN THE ORDER OF THE GLOBAL RANKS, so that every copy of an interface DoF ends up
+  // with bit-identical values (a sum in arrival order would differ in the last bit between the ranks).
+  struct HaloPlan
+  {
+    int       n_seg = 0;            // neighbours sharing nodes with this brick
+    int       rank[26];             // their ranks
+    int       off[26][3];           // their offsets in the process grid, each in {-1, 0, 1}
+    int       lo[26][3], ext[26][3]; // node box shared with them
+    long long start[27];            // element offsets of the segments in the send / receive buffer (all blocks)
+    int       seg_of[27];           // (ox+1) + 3 (oy+1) + 9 (oz+1) -> segment index or -1
+    int       np[3] = {0, 0, 0}, nb = 0, my_rank = 0;
+    unsigned  has = 0;              // bit 2d+s: a neighbour exists on side s of direction d
+  };
+
+  template <typename T>
+  __host__ __device__ inline void halo_pack_element(const BlockPtrs &blocks, const HaloPlan &pl, long long gid, T *out)
+  {
+    int s = 0;
+    while (s + 1 < pl.n_seg && gid >= pl.start[s + 1]) ++s;
+    const long long e   = gid - pl.start[s];
+    const long long box = (long long)pl.ext[s][0] * pl.ext[s][1] * pl.ext[s][2];
+    const int       blk = (int)(e / box);
+    long long       r   = e % box;
+    const int       u = (int)(r % pl.ext[s][0]);
+    r /= pl.ext[s][0];
+    const int       v = (int)(r % pl.ext[s][1]), w = (int)(r / pl.ext[s][1]);
+    const long long node = (long long)(pl.lo[s][0] + u) + (long long)pl.np[0] * ((pl.lo[s][1] + v) + (long long)pl.np[1] * (pl.lo[s][2] + w));
+    out[gid] = ((const T *)blocks.p[blk])[node];
+  }
+
+  // the element of the segment whose offset equals the node's full set of interface flags sums all partial sums of that
+  // node (own + every neighbour sharing it) in rank order and writes the result; all other elements do nothing
+  template <typename T>
+  __host__ __device__ inline void halo_unpack_element(const BlockPtrs &blocks, const HaloPlan &pl, long long gid, const T *in)
+  {
+    int s = 0;
+    while (s + 1 < pl.n_seg && gid >= pl.start[s + 1]) ++s;
+    const long long e   = gid - pl.start[s];
+    const long long box = (long long)pl.ext[s][0] * pl.ext[s][1] * pl.ext[s][2];
+    const int       blk = (int)(e / box);
+    long long       r   = e % box;
+    int             c[3];
+    c[0] = pl.lo[s][0] + (int)(r % pl.ext[s][0]);
+    r /= pl.ext[s][0];
+    c[1] = pl.lo[s][1] + (int)(r % pl.ext[s][1]);
+    c[2] = pl.lo[s][2] + (int)(r / pl.ext[s][1]);
+    int f[3];
+    for (int d = 0; d < 3; ++d)
+      {
+        f[d] = (c[d] == 0 && ((pl.has >> (2 * d)) & 1u)) ? -1 : ((c[d] == pl.np[d] - 1 && ((pl.has >> (2 * d + 1)) & 1u)) ? 1 : 0);
+        if (f[d] != pl.off[s][d]) return;
+      }
+    T  *dst = (T *)blocks.p[blk] + ((long long)c[0] + (long long)pl.np[0] * (c[1] + (long long)pl.np[1] * c[2]));
+    int ranks[8];
+    T   vals[8];
+    int n    = 1;
+    ranks[0] = pl.my_rank;
+    vals[0]  = *dst;
+    for (int m = 1; m < 8; ++m) // non-empty subsets of the node's interface directions
+      {
+        int  o[3];
+        bool ok = true;
+        for (int d = 0; d < 3; ++d)
+          {
+            o[d] = ((m >> d) & 1) ? f[d] : 0;
+            if (((m >> d) & 1) && f[d] == 0) ok = false;
+          }
+        if (!ok) continue;
+        const int t = pl.seg_of[(o[0] + 1) + 3 * (o[1] + 1) + 9 * (o[2] + 1)];
+        if (t < 0) continue;
+        const long long bt = (long long)pl.ext[t][0] * pl.ext[t][1] * pl.ext[t][2];
+        const long long et = (long long)(c[0] - pl.lo[t][0]) + (long long)pl.ext[t][0] * ((c[1] - pl.lo[t][1]) + (long long)pl.ext[t][1] * (c[2] - pl.lo[t][2]));
+        ranks[n] = pl.rank[t];
+        vals[n]  = in[pl.start[t] + (long long)blk * bt + et];
+        ++n;
+      }
+    for (int a = 1; a < n; ++a) // insertion sort by rank
+      {
+        const int ra = ranks[a];
+        const T   va = vals[a];
+        int       b  = a - 1;
+        while (b >= 0 && ranks[b] > ra)
+          {
+            ranks[b + 1] = ranks[b];
+            vals[b + 1]  = vals[b];
+            --b;
+          }
+        ranks[b + 1] = ra;
+        vals[b + 1]  = va;
+      }
+    T sum = vals[0];
+    for (int a = 1; a < n; ++a) sum += vals[a];
+    *dst = sum;
+  }
+
+  template <typename T>
+  __global__ void k_halo_pack(BlockPtrs blocks, HaloPlan pl, T *__restrict__ out)
+  {
+    const long long total = pl.start[pl.n_seg];
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      halo_pack_element<T>(blocks, pl, gid, out);
+  }
+  template <typename T>
+  __global__ void k_halo_unpack_sum(BlockPtrs blocks, HaloPlan pl, const T *__restrict__ in)
+  {
+    const long long total = pl.start[pl.n_seg];
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      halo_unpack_element<T>(blocks, pl, gid, in);
+  }
+
   struct HaloBuffers
   {
     void  *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
     size_t bytes = 0;
+    void  *send_all = nullptr, *recv_all = nullptr; // single-round exchange
+    size_t bytes_all = 0;
+    HaloPlan plan;                                  // cached for (np, nb)
     ~HaloBuffers()
     {
       for (int s = 0; s < 2; ++s)
@@ -145,6 +260,8 @@ namespace stfem
           if (send[s]) cudaFree(send[s]);
           if (recv[s]) cudaFree(recv[s]);
         }
+      if (send_all) cudaFree(send_all);
+      if (recv_all) cudaFree(recv_all);
     }
   };
 

@@ -51,7 +51,8 @@ namespace stfem
   template <> struct BrickTile<4> { static constexpr int CX = 9, CY = 5; };
   template <> struct BrickTile<5> { static constexpr int CX = 7, CY = 4; };
 
-  template <typename T, int N1, int NB, int CX_, int CY_>
+  // SPLIT: the X phase and the Y+Z phase run on separate warps (XW + YW warps, one CTA per SM) instead of sharing them
+  template <typename T, int N1, int NB, int CX_, int CY_, bool SPLIT = false>
   struct BrickCfg
   {
     static constexpr int K = N1 - 1, CX = CX_, CY = CY_;
@@ -66,10 +67,13 @@ namespace stfem
     static constexpr int RPW = 32 / CXL;                     // tile rows per warp in the X phase
     static constexpr int XW = (WY + RPW - 1) / RPW;          // warps with X work
     static constexpr int YW = CY * NB;                       // warps of the Y+Z phase: one per (cell row, dst block)
-    static constexpr int NWARPS = XW > YW ? XW : YW;
+    static constexpr int NWARPS = SPLIT ? XW + YW : (XW > YW ? XW : YW);
     static constexpr int NTHREADS = 32 * NWARPS;
-    static constexpr int STAGES = 3;
-    static constexpr int PXP = ((TX + 1 + EPV - 1) / EPV) * EPV + ((((TX + 1 + EPV - 1) / EPV) & 1) ? 0 : EPV); // odd number of 16-byte words
+    static constexpr int STAGES = 3;  // planes of source tiles in flight
+    static constexpr int NPQ = 3;     // P/Q buffers: X runs one plane ahead of Y+Z with a plane of slack on either side
+    // pitch of a P/Q row: an odd number of 16-byte words, so that the 16-byte stores of the X phase (one run of K values per
+    // lane) spread over all banks; measured faster than scalar stores on an odd pitch in FP64 (fewer issue slots)
+    static constexpr int PXP = ((TX + 1 + EPV - 1) / EPV) * EPV + ((((TX + 1 + EPV - 1) / EPV) & 1) ? 0 : EPV);
     static constexpr int PQ_FIELD = WY * PXP;                // one field of one dst block
     static constexpr int PQ_BUF = 2 * NB * PQ_FIELD;
     static_assert(CXL <= 32 && TX + 1 <= 32, "tile does not fit the lane mappings");
@@ -77,7 +81,7 @@ namespace stfem
     // bytes of one (source block, row class) sub-tile for n_cls classes, padded to 128 bytes
     __host__ __device__ static constexpr int sub_bytes(int n_cls) { return ((((WY + n_cls - 1) / n_cls) * WXP * (int)sizeof(T)) + 127) / 128 * 128; }
     __host__ __device__ static constexpr int stage_bytes(int n_cls) { return NB * n_cls * sub_bytes(n_cls); }
-    __host__ __device__ static constexpr int smem_bytes(int n_cls) { return 128 + STAGES * stage_bytes(n_cls) + 2 * PQ_BUF * (int)sizeof(T); }
+    __host__ __device__ static constexpr int smem_bytes(int n_cls) { return 256 + STAGES * stage_bytes(n_cls) + NPQ * PQ_BUF * (int)sizeof(T); }
   };
 
   template <typename T, int N1, int NB>
@@ -252,7 +256,8 @@ namespace stfem
     {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
     }
-    // bounded wait: a lost transaction must end in a trap, not in a hung GPU
+    // bounded wait: a lost transaction must end in a trap, not in a hung GPU.  Plain polling: measured faster than a
+    // suspend-time hint (slow wake-up) and than __nanosleep back-off
     __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
     {
       unsigned ok = 0;
@@ -276,6 +281,20 @@ namespace stfem
                    : "memory");
     }
   } // namespace brick_hw
+#endif
+
+  // mbarrier wrappers of the kernel: hardware (brick_hw) or the host emulation's (brick_emu, tests/cpp)
+#ifndef STFEM_HOST_EMULATION
+  namespace brick_hw
+  {
+    __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+    {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+    }
+  } // namespace brick_hw
+  namespace brick_sync = brick_hw;
+#else
+  namespace brick_sync = brick_emu;
 #endif
 
   // plain (synchronous) version of one box load: element (i0, i1) of the box = tensor element (c0 + i0, c1 + i1), 0 outside
@@ -394,11 +413,11 @@ namespace stfem
   }
 #endif
 
-  template <typename T, int N1, int NB, int CX, int CY, int MINB>
-  __global__ void __launch_bounds__((BrickCfg<T, N1, NB, CX, CY>::NTHREADS), MINB)
+  template <typename T, int N1, int NB, int CX, int CY, int MINB, bool SPLIT = false>
+  __global__ void __launch_bounds__((BrickCfg<T, N1, NB, CX, CY, SPLIT>::NTHREADS), MINB)
     st_vmult_brick_kernel(const __grid_constant__ BrickArgs<T, N1, NB> a)
   {
-    using C = BrickCfg<T, N1, NB, CX, CY>;
+    using C = BrickCfg<T, N1, NB, CX, CY, SPLIT>;
     constexpr int K = C::K, TX = C::TX, WY = C::WY, WXP = C::WXP, PXP = C::PXP, S = C::STAGES, EPV = C::EPV;
     constexpr int CXL = C::CXL, RPW = C::RPW;
     extern __shared__ __align__(128) unsigned char brick_smem[];
@@ -407,7 +426,8 @@ namespace stfem
     const int           HB = (WY + cmask) >> cshift;                    // box rows per class
     const int           sub_elems = C::sub_bytes(1 << cshift) / (int)sizeof(T);
     const int           stage_elems = (NB << cshift) * sub_elems;
-    T                  *tiles = reinterpret_cast<T *>(brick_smem + 128);
+    T                  *tiles = reinterpret_cast<T *>(brick_smem + 256);
+    T                  *zero_row = reinterpret_cast<T *>(brick_smem + 128); // N1 <= 8 zeros: what an invalid lane of the X phase reads
     T                  *pq    = tiles + S * stage_elems;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -431,28 +451,44 @@ namespace stfem
     const unsigned dm = a.dirichlet;
     const int      xb = x0 - K;                    // first node of the tile rows (may be negative)
 
-    // ---- plane loads: plane index qq of this CTA into stage qq % S.  Tensor row of tile row 0: r0(qq)
+    // ---- barriers: [0,S) tile full (TMA transaction), [S,2S) tile empty (all X warps read it),
+    //      [2S, 2S+NPQ) P/Q full (all X warps wrote the plane), [2S+NPQ, 2S+2NPQ) P/Q empty (all Y+Z warps read it)
+    constexpr int NPQ = C::NPQ;
+    unsigned long long *bar_tfull = bars, *bar_tempty = bars + S, *bar_pfull = bars + 2 * S, *bar_pempty = bars + 2 * S + NPQ;
+    static_assert(2 * S + 2 * NPQ <= 16, "barriers do not fit the 128 bytes reserved for them");
+
+    // ---- plane loads: plane index qq of this CTA into stage qq % S.  Tensor row of tile row 0: r0_first + qq * np1
     const int r0_first = (K * start) * np1 + (y0 - K);
-    auto issue = [&](int qq) {
-      T *st = tiles + (qq % S) * stage_elems;
+    // flow A (TMA): one thread issues the box loads, completion on bar_tfull
+    auto issue_tma = [&](int qq) {
 #ifndef STFEM_HOST_EMULATION
-      if (a.use_tma)
-        {
-          if (tid == 0)
-            {
-              const int r0 = r0_first + qq * np1;
-              brick_hw::mbar_expect_tx(&bars[qq % S], (unsigned)((NB << cshift) * HB * WXP * (int)sizeof(T)));
-              for (int s = 0; s < NB; ++s)
-                for (int c = 0; c <= cmask; ++c)
-                  {
-                    const int rc = r0 + ((c - r0) & cmask); // first row >= r0 of class c
-                    const int sh = (a.shift_pack >> (2 * (4 * s + c))) & 3;
-                    brick_hw::tma_load_2d(st + ((s << cshift) + c) * sub_elems, &a.maps[s][c], (xb + sh) & ~(EPV - 1), (rc - c) >> cshift, &bars[qq % S]);
-                  }
-            }
-          return;
-        }
+      T        *st = tiles + (qq % S) * stage_elems;
+      const int r0 = r0_first + qq * np1;
+      brick_hw::mbar_expect_tx(&bar_tfull[qq % S], (unsigned)((NB << cshift) * HB * WXP * (int)sizeof(T)));
+      for (int s = 0; s < NB; ++s)
+        for (int c = 0; c <= cmask; ++c)
+          {
+            const int rc = r0 + ((c - r0) & cmask); // first row >= r0 of class c
+            const int sh = (a.shift_pack >> (2 * (4 * s + c))) & 3;
+            brick_hw::tma_load_2d(st + ((s << cshift) + c) * sub_elems, &a.maps[s][c], (xb + sh) & ~(EPV - 1), (rc - c) >> cshift, &bar_tfull[qq % S]);
+          }
+#else
+      // host emulation of flow A: the issuing thread copies the boxes itself, then completes the barrier
+      T        *st = tiles + (qq % S) * stage_elems;
+      const int r0 = r0_first + qq * np1;
+      for (int s = 0; s < NB; ++s)
+        for (int c = 0; c <= cmask; ++c)
+          {
+            const int rc = r0 + ((c - r0) & cmask);
+            const int sh = (a.shift_pack >> (2 * (4 * s + c))) & 3;
+            brick_box_load_plain<T>(st + ((s << cshift) + c) * sub_elems, a.desc[s][c], (xb + sh) & ~(EPV - 1), (rc - c) >> cshift, 0, 1);
+          }
+      brick_sync::mbar_arrive(&bar_tfull[qq % S]);
 #endif
+    };
+    // flow B (plain loads, no tensor maps): all threads copy the boxes, CTA-wide barriers around the phases
+    auto load_plain = [&](int qq) {
+      T        *st = tiles + (qq % S) * stage_elems;
       const int r0 = r0_first + qq * np1;
       for (int s = 0; s < NB; ++s)
         for (int c = 0; c <= cmask; ++c)
@@ -463,18 +499,30 @@ namespace stfem
           }
     };
 
-#ifndef STFEM_HOST_EMULATION
-    if (a.use_tma)
+    const bool flow_a = a.use_tma != 0;      // tensor-map loads (1: one CTA barrier per plane, 2: full / empty barrier pipeline)
+    const bool pipe   = a.use_tma == 2;
+    if (tid < 8) zero_row[tid] = T(0);
+    if (!flow_a) __syncthreads();
+    if (flow_a)
       {
         if (tid == 0)
           {
-            for (int s = 0; s < S; ++s) brick_hw::mbar_init(&bars[s], 1);
-            brick_hw::fence_init();
+            for (int s = 0; s < S; ++s)
+              {
+                brick_sync::mbar_init(&bar_tfull[s], 1);
+                brick_sync::mbar_init(&bar_tempty[s], 32 * C::XW);
+              }
+            for (int b = 0; b < NPQ; ++b)
+              {
+                brick_sync::mbar_init(&bar_pfull[b], 32 * C::XW);
+                brick_sync::mbar_init(&bar_pempty[b], 32 * C::YW);
+              }
+            brick_sync::fence_init();
           }
         __syncthreads();
-        for (int qq = 0; qq < S && qq < nq; ++qq) issue(qq);
+        if (tid == C::NTHREADS - 32)
+          for (int qq = 0; qq < S && qq < nq; ++qq) issue_tma(qq);
       }
-#endif
 
     // ---- X phase identity of this thread: lane = (tile row within the warp, cell), all plane-independent pieces hoisted
     const bool x_lane_ok = lane < RPW * CXL;
@@ -500,14 +548,20 @@ namespace stfem
         x_src_lane = xr + RPW * cbl;
       }
     const bool x_store  = x_row_in && xci >= 1;
+    unsigned   x_lead_pack = 0; // lead-in elements of the box of (source block, row class), 2 bits each
+    for (int s = 0; s < NB; ++s)
+      for (int c = 0; c <= cmask; ++c)
+        x_lead_pack |= (unsigned)((xb + ((a.shift_pack >> (2 * (4 * s + c))) & 3)) & (EPV - 1)) << (2 * (4 * s + c));
     const int  x_st_off = xyl * PXP + K * (xci - 1); // P/Q store offset inside a field
 
     // ---- Y+Z phase identity: lane = x node of the tile, warp = (cell row yc, dst block j)
-    const int  yc = warp % CY, jz = warp / CY;
+    const int  ywarp = SPLIT ? (warp >= C::XW ? warp - C::XW : 0) : warp; // index among the Y+Z warps
+    const bool y_role = SPLIT ? warp >= C::XW : warp < C::YW;              // takes part in the Y+Z barrier protocol
+    const int  yc = ywarp % CY, jz = (ywarp / CY) % NB;
     const int  xo = lane <= TX ? lane : TX;
     const int  xg = x0 + xo;
     const int  cyg = cy0 + yc;                      // cell whose K node rows K*cyg .. K*cyg + K - 1 this thread owns
-    const bool yz_warp = warp < C::YW && cyg <= a.n[1];
+    const bool yz_warp = y_role && cyg <= a.n[1];
     const bool has_below = cyg >= 1, has_above = cyg < a.n[1];
     const int  yz_ld_off = (K * yc) * PXP + xo;
     // stores: node nn of the chunk is written iff st_mask bit nn; its value is forced to 0 iff con_mask bit nn
@@ -573,194 +627,264 @@ namespace stfem
         }
     };
 
-    // ---- march through the planes
-    int r0 = r0_first;
-    for (int q = 0; q < nq; ++q, r0 += np1)
-      {
-        const int  zp    = K * start + q; // node plane
-        const int  m     = q % K;         // its local index in the current cell layer (0: also node K of the layer below)
-        const int  layer = start + q / K;
-        const bool plane_con = ((dm & 16u) && zp == 0) || ((dm & 32u) && zp == np2 - 1);
-        T         *st  = tiles + (q % S) * stage_elems;
-        T         *pqb = pq + (q & 1) * C::PQ_BUF;
-#ifndef STFEM_HOST_EMULATION
-        if (a.use_tma)
-          brick_hw::mbar_wait(&bars[q % S], (unsigned)((q / S) & 1));
-        else
-#endif
-          {
-            issue(q);
-            __syncthreads();
-          }
-
-        // ================= X phase
-        if (warp < C::XW)
-          {
-            const bool valid = x_valid0 && !plane_con;
-            // tile row xyl sits in class c at index idx of that class' box
-            const int g   = r0 + xyl;
-            const int c   = g & cmask;
-            const int idx = (g - (r0 + ((c - r0) & cmask))) >> cshift;
-            T         P[NB][N1], Q[NB][N1];
+    // ---- the two phases of one node plane q (local index of this CTA's march)
+    // X: source tile of stage q % S -> P, Q of buffer q % NPQ (X warps only)
+    auto x_phase = [&](int q) {
+      const int  zp = K * start + q;
+      const bool plane_con = ((dm & 16u) && zp == 0) || ((dm & 32u) && zp == np2 - 1);
+      const int  r0 = r0_first + q * np1;
+      T         *st  = tiles + (q % S) * stage_elems;
+      T         *pqb = pq + (q % NPQ) * C::PQ_BUF;
+        {
+          const bool valid = x_valid0 && !plane_con;
+          // tile row xyl sits in class c at index idx of that class' box
+          const int g   = r0 + xyl;
+          const int c   = g & cmask;
+          const int idx = (g - (r0 + ((c - r0) & cmask))) >> cshift;
+          T         P[NB][N1], Q[NB][N1];
 #pragma unroll
-            for (int s = 0; s < NB; ++s)
-              {
-                // the box of this class starts at the 16-byte boundary at or below the first node of the tile row
-                const int lead = (xb + ((a.shift_pack >> (2 * (4 * s + c))) & 3)) & (EPV - 1);
-                const T  *row  = st + ((s << cshift) + c) * sub_elems + idx * WXP + lead + K * xci;
-                T         u[N1], av[N1], bv[N1];
-#pragma unroll
-                for (int i = 0; i < N1; ++i) u[i] = valid ? row[i] : T(0);
-                if (x_zero_u0) u[0] = T(0);
-                if (x_zero_uK) u[K] = T(0);
-                brick_eo_apply2<T, N1>(u, a.Mxe, a.Mxo, a.Kxe, a.Kxo, av, bv);
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                  {
-                    const T be = a.beta[j * NB + s], al = a.alpha[j * NB + s];
-#pragma unroll
-                    for (int i = 0; i < N1; ++i)
-                      {
-                        if (s == 0)
-                          {
-                            P[j][i] = be * av[i];
-                            Q[j][i] = al * av[i];
-                          }
-                        else
-                          {
-                            P[j][i] += be * av[i];
-                            Q[j][i] += al * av[i];
-                          }
-                        P[j][i] += al * bv[i];
-                      }
-                  }
-              }
-            // the vertex shared with the left cell: add that cell's partial sum (all lanes take part in the shuffles)
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-              {
-                const T pk = __shfl_sync(0xffffffffu, P[j][K], x_src_lane);
-                const T qk = __shfl_sync(0xffffffffu, Q[j][K], x_src_lane);
-                if (x_src_lane != lane)
-                  {
-                    P[j][0] += pk;
-                    Q[j][0] += qk;
-                  }
-              }
-            if (x_store)
-              {
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                  {
-                    T *pp = pqb + (0 * NB + j) * C::PQ_FIELD + x_st_off;
-                    T *qp = pqb + (1 * NB + j) * C::PQ_FIELD + x_st_off;
-                    brick_store_run<T, K>(pp, P[j]);
-                    brick_store_run<T, K>(qp, Q[j]);
-                    if (xci == CX)
-                      {
-                        pp[K] = P[j][K];
-                        qp[K] = Q[j][K];
-                      }
-                  }
-              }
-          }
-        __syncthreads(); // P, Q of this plane complete; stage q % S consumed by everybody
-#ifndef STFEM_HOST_EMULATION
-        if (a.use_tma && q + S < nq) issue(q + S);
-#endif
-
-        // ================= Y + Z phase
-        if (yz_warp)
-          {
-            const T *pp = pqb + (0 * NB + jz) * C::PQ_FIELD + yz_ld_off;
-            const T *qp = pqb + (1 * NB + jz) * C::PQ_FIELD + yz_ld_off;
-            T        p[2 * K + 1], qv[2 * K + 1];
-#pragma unroll
-            for (int t = 0; t < 2 * K + 1; ++t)
-              {
-                p[t]  = pp[t * PXP];
-                qv[t] = qp[t * PXP];
-              }
-            T c[K], d[K];
-            // node 0 of the chunk: vertex row shared by the cell below (its node K) and the cell above (its node 0)
+          for (int s = 0; s < NB; ++s)
             {
+              // the box of this class starts at the 16-byte boundary at or below the first node of the tile row
+              const int lead = (x_lead_pack >> (2 * (4 * s + c))) & 3;
+              // an invalid lane (row outside the mesh, constrained row or plane, no such cell) reads zeros: FP32 through a
+              // pointer to a zero row, FP64 by selects (measured: the dependent pointer select costs more there)
+              const T *row = st + ((s << cshift) + c) * sub_elems + idx * WXP + lead + K * xci;
+              if (sizeof(T) == 4 && !valid) row = zero_row;
+              T u[N1], av[N1], bv[N1];
+#pragma unroll
+              for (int i = 0; i < N1; ++i) u[i] = (sizeof(T) == 4 || valid) ? row[i] : T(0);
+              if (x_zero_u0) u[0] = T(0);
+              if (x_zero_uK) u[K] = T(0);
+              brick_eo_apply2<T, N1>(u, a.Mxe, a.Mxo, a.Kxe, a.Kxo, av, bv);
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                {
+                  const T be = a.beta[j * NB + s], al = a.alpha[j * NB + s];
+#pragma unroll
+                  for (int i = 0; i < N1; ++i)
+                    {
+                      if (s == 0)
+                        {
+                          P[j][i] = be * av[i];
+                          Q[j][i] = al * av[i];
+                        }
+                      else
+                        {
+                          P[j][i] += be * av[i];
+                          Q[j][i] += al * av[i];
+                        }
+                      P[j][i] += al * bv[i];
+                    }
+                }
+            }
+          // the vertex shared with the left cell: add that cell's partial sum (all lanes take part in the shuffles)
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            {
+              const T pk = __shfl_sync(0xffffffffu, P[j][K], x_src_lane);
+              const T qk = __shfl_sync(0xffffffffu, Q[j][K], x_src_lane);
+              if (x_src_lane != lane)
+                {
+                  P[j][0] += pk;
+                  Q[j][0] += qk;
+                }
+            }
+          if (x_store)
+            {
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                {
+                  T *pp = pqb + (0 * NB + j) * C::PQ_FIELD + x_st_off;
+                  T *qp = pqb + (1 * NB + j) * C::PQ_FIELD + x_st_off;
+                  brick_store_run<T, K>(pp, P[j]);
+                  brick_store_run<T, K>(qp, Q[j]);
+                  if (xci == CX)
+                    {
+                      pp[K] = P[j][K];
+                      qp[K] = Q[j][K];
+                    }
+                }
+            }
+        }
+    };
+    // Y + Z: P, Q of buffer q % NPQ -> accumulators, stores of completed planes (Y+Z warps with an existing chunk only;
+    // `release` is called once the P, Q values are in registers)
+    auto yz_phase = [&](int q, auto release) {
+      const int m     = q % K; // local index of the plane in the current cell layer (0: also node K of the layer below)
+      const int layer = start + q / K;
+      T        *pqb   = pq + (q % NPQ) * C::PQ_BUF;
+        {
+          const T *pp = pqb + (0 * NB + jz) * C::PQ_FIELD + yz_ld_off;
+          const T *qp = pqb + (1 * NB + jz) * C::PQ_FIELD + yz_ld_off;
+          T        p[2 * K + 1], qv[2 * K + 1];
+#pragma unroll
+          for (int t = 0; t < 2 * K + 1; ++t)
+            {
+              p[t]  = pp[t * PXP];
+              qv[t] = qp[t * PXP];
+            }
+          release(); // the buffer may be rewritten as soon as every Y+Z warp got here
+          T c[K], d[K];
+          // node 0 of the chunk: vertex row shared by the cell below (its node K) and the cell above (its node 0).  The cell
+          // matrices are centrosymmetric (row K = row 0 reversed): with both cells present the two contributions are one row
+          // applied to the sums of the mirrored values
+          // (FP32 only: in FP64 the two extra independent chains of the general form hide the longer pipe latency better)
+          if (sizeof(T) == 4 && has_below && has_above)
+            {
+              T sp = p[K] + p[K], sq = qv[K] + qv[K];
+              T cc = a.M[0] * sp, dd = a.M[0] * sq;
+              cc += a.Ky[0] * sq;
+#pragma unroll
+              for (int t = 1; t < N1; ++t)
+                {
+                  sp = p[K + t] + p[K - t];
+                  sq = qv[K + t] + qv[K - t];
+                  cc += a.M[t] * sp;
+                  cc += a.Ky[t] * sq;
+                  dd += a.M[t] * sq;
+                }
+              c[0] = cc;
+              d[0] = dd;
+            }
+          else
+            {
+              // short independent chains (mass part, stiffness part) instead of one long one: the FP64 pipe latency is
+              // what the Y phase waits for
               T cb_ = a.M[K * N1] * p[0], db_ = a.M[K * N1] * qv[0], ca_ = a.M[0] * p[K], da_ = a.M[0] * qv[K];
-              cb_ += a.Ky[K * N1] * qv[0];
-              ca_ += a.Ky[0] * qv[K];
+              T kb_ = a.Ky[K * N1] * qv[0], ka_ = a.Ky[0] * qv[K];
 #pragma unroll
               for (int t = 1; t < N1; ++t)
                 {
                   cb_ += a.M[K * N1 + t] * p[t];
-                  cb_ += a.Ky[K * N1 + t] * qv[t];
+                  kb_ += a.Ky[K * N1 + t] * qv[t];
                   db_ += a.M[K * N1 + t] * qv[t];
                   ca_ += a.M[t] * p[K + t];
-                  ca_ += a.Ky[t] * qv[K + t];
+                  ka_ += a.Ky[t] * qv[K + t];
                   da_ += a.M[t] * qv[K + t];
                 }
+              cb_ += kb_;
+              ca_ += ka_;
               c[0] = (has_below ? cb_ : T(0)) + (has_above ? ca_ : T(0));
               d[0] = (has_below ? db_ : T(0)) + (has_above ? da_ : T(0));
             }
 #pragma unroll
-            for (int nn = 1; nn < K; ++nn)
-              {
-                T cc = a.M[nn * N1] * p[K], dd = a.M[nn * N1] * qv[K];
-                cc += a.Ky[nn * N1] * qv[K];
+          for (int nn = 1; nn < K; ++nn)
+            {
+              T cc = a.M[nn * N1] * p[K], dd = a.M[nn * N1] * qv[K], ck = a.Ky[nn * N1] * qv[K];
 #pragma unroll
-                for (int t = 1; t < N1; ++t)
+              for (int t = 1; t < N1; ++t)
+                {
+                  cc += a.M[nn * N1 + t] * p[K + t];
+                  ck += a.Ky[nn * N1 + t] * qv[K + t];
+                  dd += a.M[nn * N1 + t] * qv[K + t];
+                }
+              c[nn] = cc + ck;
+              d[nn] = dd;
+            }
+          auto zacc = [&](auto mtag) {
+            constexpr int mm = decltype(mtag)::value;
+#pragma unroll
+            for (int nn = 0; nn < K; ++nn)
+#pragma unroll
+              for (int i = 0; i < N1; ++i)
+                {
+                  acc[nn][i] += a.M[i * N1 + mm] * c[nn];
+                  acc[nn][i] += a.Kz[i * N1 + mm] * d[nn];
+                }
+          };
+          if (m == 0)
+            {
+              if (q > 0)
+                {
+                  zacc(std::integral_constant<int, K>()); // closes cell layer `layer - 1`
                   {
-                    cc += a.M[nn * N1 + t] * p[K + t];
-                    cc += a.Ky[nn * N1 + t] * qv[K + t];
-                    dd += a.M[nn * N1 + t] * qv[K + t];
+                    const int zb = K * (layer - 1);
+                    store_plane(zb + 0, std::integral_constant<int, 0>(), layer - 1 == cz0 && cz0 > a.zlo);
+                    if (K > 1) store_plane(zb + 1, std::integral_constant<int, (K > 1 ? 1 : 0)>(), false);
+                    if (K > 2) store_plane(zb + 2, std::integral_constant<int, (K > 2 ? 2 : 0)>(), false);
+                    if (K > 3) store_plane(zb + 3, std::integral_constant<int, (K > 3 ? 3 : 0)>(), false);
+                    if (K > 4) store_plane(zb + 4, std::integral_constant<int, (K > 4 ? 4 : 0)>(), false);
+                    if (K > 5) store_plane(zb + 5, std::integral_constant<int, (K > 5 ? 5 : 0)>(), false);
                   }
-                c[nn] = cc;
-                d[nn] = dd;
-              }
-            auto zacc = [&](auto mtag) {
-              constexpr int mm = decltype(mtag)::value;
 #pragma unroll
-              for (int nn = 0; nn < K; ++nn)
-#pragma unroll
-                for (int i = 0; i < N1; ++i)
-                  {
-                    acc[nn][i] += a.M[i * N1 + mm] * c[nn];
-                    acc[nn][i] += a.Kz[i * N1 + mm] * d[nn];
-                  }
-            };
-            if (m == 0)
-              {
-                if (q > 0)
-                  {
-                    zacc(std::integral_constant<int, K>()); // closes cell layer `layer - 1`
+                  for (int nn = 0; nn < K; ++nn)
                     {
-                      const int zb = K * (layer - 1);
-                      store_plane(zb + 0, std::integral_constant<int, 0>(), layer - 1 == cz0 && cz0 > a.zlo);
-                      if (K > 1) store_plane(zb + 1, std::integral_constant<int, (K > 1 ? 1 : 0)>(), false);
-                      if (K > 2) store_plane(zb + 2, std::integral_constant<int, (K > 2 ? 2 : 0)>(), false);
-                      if (K > 3) store_plane(zb + 3, std::integral_constant<int, (K > 3 ? 3 : 0)>(), false);
-                      if (K > 4) store_plane(zb + 4, std::integral_constant<int, (K > 4 ? 4 : 0)>(), false);
-                      if (K > 5) store_plane(zb + 5, std::integral_constant<int, (K > 5 ? 5 : 0)>(), false);
+                      acc[nn][0] = acc[nn][K];
+#pragma unroll
+                      for (int i = 1; i < N1; ++i) acc[nn][i] = T(0);
                     }
-#pragma unroll
-                    for (int nn = 0; nn < K; ++nn)
-                      {
-                        acc[nn][0] = acc[nn][K];
-#pragma unroll
-                        for (int i = 1; i < N1; ++i) acc[nn][i] = T(0);
-                      }
-                  }
-                if (q < nq - 1) zacc(std::integral_constant<int, 0>());
-              }
-            else
+                }
+              if (q < nq - 1) zacc(std::integral_constant<int, 0>());
+            }
+          else
+            {
+              switch (m)
+                {
+                  case 1: zacc(std::integral_constant<int, (K > 1 ? 1 : 0)>()); break;
+                  case 2: zacc(std::integral_constant<int, (K > 2 ? 2 : 0)>()); break;
+                  case 3: zacc(std::integral_constant<int, (K > 3 ? 3 : 0)>()); break;
+                  case 4: zacc(std::integral_constant<int, (K > 4 ? 4 : 0)>()); break;
+                  default: zacc(std::integral_constant<int, (K > 5 ? 5 : 0)>()); break;
+                }
+            }
+        }
+    };
+
+    // ---- march through the planes
+    if (flow_a && !pipe)
+      {
+        // one CTA barrier per plane: X(q) | barrier | reload of the stage, Y+Z(q); the P/Q buffers alternate, so the X phase
+        // of the next plane never overwrites what a slower warp still reads
+        for (int q = 0; q < nq; ++q)
+          {
+            brick_sync::mbar_wait(&bar_tfull[q % S], (unsigned)((q / S) & 1));
+            if (warp < C::XW) x_phase(q);
+            __syncthreads();
+            if (tid == C::NTHREADS - 32 && q + S < nq) issue_tma(q + S);
+            if (yz_warp) yz_phase(q, []() {});
+          }
+      }
+    else if (flow_a)
+      {
+        // no CTA-wide barrier: X runs one plane ahead of Y+Z; the full / empty barriers of the three P/Q buffers and of
+        // the source stages leave a plane of slack on either side, so a warp only waits when it is a whole plane ahead
+        const bool x_warp = warp < C::XW, y_warp = y_role, issuer = tid == C::NTHREADS - 32;
+        auto       x_step = [&](int q) {
+          brick_sync::mbar_wait(&bar_tfull[q % S], (unsigned)((q / S) & 1));
+          if (q >= NPQ) brick_sync::mbar_wait(&bar_pempty[q % NPQ], (unsigned)((q / NPQ - 1) & 1));
+          x_phase(q);
+          brick_sync::mbar_arrive(&bar_pfull[q % NPQ]);
+          brick_sync::mbar_arrive(&bar_tempty[q % S]);
+        };
+        if (x_warp) x_step(0);
+        for (int q = 0; q < nq; ++q)
+          {
+            if (x_warp && q + 1 < nq) x_step(q + 1);
+            if (issuer && q + S < nq)
               {
-                switch (m)
-                  {
-                    case 1: zacc(std::integral_constant<int, (K > 1 ? 1 : 0)>()); break;
-                    case 2: zacc(std::integral_constant<int, (K > 2 ? 2 : 0)>()); break;
-                    case 3: zacc(std::integral_constant<int, (K > 3 ? 3 : 0)>()); break;
-                    case 4: zacc(std::integral_constant<int, (K > 4 ? 4 : 0)>()); break;
-                    default: zacc(std::integral_constant<int, (K > 5 ? 5 : 0)>()); break;
-                  }
+                brick_sync::mbar_wait(&bar_tempty[q % S], (unsigned)((q / S) & 1)); // plane q read by every X warp
+                issue_tma(q + S);
               }
+            if (y_warp)
+              {
+                brick_sync::mbar_wait(&bar_pfull[q % NPQ], (unsigned)((q / NPQ) & 1));
+                if (yz_warp)
+                  yz_phase(q, [&]() { brick_sync::mbar_arrive(&bar_pempty[q % NPQ]); });
+                else
+                  brick_sync::mbar_arrive(&bar_pempty[q % NPQ]);
+              }
+          }
+      }
+    else
+      {
+        for (int q = 0; q < nq; ++q)
+          {
+            load_plain(q);
+            __syncthreads();
+            if (warp < C::XW) x_phase(q);
+            __syncthreads();
+            if (yz_warp) yz_phase(q, []() {});
           }
       }
     // the top plane of the chunk: shared with the chunk above; at the top of the launch range it is complete (top of the

@@ -55,11 +55,11 @@ namespace stfem
     return nullptr;
   }
 
-  template <int N1, int NB, typename T, int CX, int CY, int MINB>
+  template <int N1, int NB, typename T, int CX, int CY, int MINB, bool SPLIT = false>
   static int launch_brick(stfem_op *op, void *const *dst, const void *const *src, const std::vector<double> &Alpha, const std::vector<double> &Beta,
-                          bool accumulate, int zlo, int zhi, bool first_plane_acc, bool use_tma, int n_chunks)
+                          bool accumulate, int zlo, int zhi, bool first_plane_acc, int use_tma, int n_chunks)
   {
-    using C = BrickCfg<T, N1, NB, CX, CY>;
+    using C = BrickCfg<T, N1, NB, CX, CY, SPLIT>;
     stfem_mesh *m = op->mesh;
     if (zhi <= zlo) return STFEM_OK;
     BrickArgs<T, N1, NB> a;
@@ -70,7 +70,7 @@ namespace stfem
     brick_fill_args<T, N1, NB, CX, CY>(a, sh.S.data(), sh.D.data(), sh.wq.data(), h, m->n, m->dirichlet, Alpha.data(), Beta.data(), src, dst, zlo, zhi,
                                        accumulate, first_plane_acc, n_chunks, (long long)m->ctx->sm_count * MINB);
     STFEM_REQUIRE(a.n_cls <= C::MAXCLS, "st_vmult (brick): %d row classes", a.n_cls);
-    a.use_tma = use_tma ? 1 : 0;
+    a.use_tma = use_tma;
     for (int b = 0; b < NB && a.use_tma; ++b)
       for (int c = 0; c < a.n_cls; ++c)
         if (!brick_encode<T>(a.desc[b][c], &a.maps[b][c]))
@@ -92,7 +92,7 @@ namespace stfem
         m->ctx->launches++;
       }
     const size_t smem = (size_t)C::smem_bytes(a.n_cls);
-    auto         kern = st_vmult_brick_kernel<T, N1, NB, CX, CY, MINB>;
+    auto         kern = st_vmult_brick_kernel<T, N1, NB, CX, CY, MINB, SPLIT>;
     STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid   = (long long)a.tiles_x * a.tiles_y * a.n_chunks;
     STFEM_REQUIRE(grid < (1ll << 31), "st_vmult (brick): grid too large");

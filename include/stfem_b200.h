@@ -154,6 +154,9 @@ int stfem_partition_brick(int dim, const int *n_global, const double *lower, con
                           const int *coords, int *n_local, int *cell_offset, double *local_lower, double *local_upper,
                           unsigned *dirichlet_faces);
 int stfem_mesh_set_partition(stfem_mesh_t mesh, const int *proc_grid, const int *coords);
+/* host-only test hook: the interface exchange of a box partition among all its bricks inside one process, executing the
+ * same element functions as the pack / unpack kernels (no GPU, no NCCL).  data: [n_ranks][nb][np0*np1*np2] doubles. */
+int stfem_halo_emulate_host(int dim, const int *proc_grid, const int *np, int nb, double *data);
 /* add the partial values of interface DoFs over the ranks sharing them (compress(add) + ghost update);
  * stfem_op_vmult & co. call this internally on partitioned meshes */
 int stfem_op_halo_add(stfem_op_t op, void *const *blocks, int nb);

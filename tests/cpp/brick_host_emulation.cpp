@@ -10,6 +10,8 @@
 // in.bin : Alpha[nb*nb], Beta[nb*nb], src[nb][N], dst0[nb][N]  (doubles; dst0 = initial content of dst);  out.bin: dst[nb][N]
 // misalign: number of T elements the block vectors are shifted off a 16-byte boundary (tests the shifted row classes)
 #include <algorithm>
+#include <atomic>
+#include <new>
 #include <barrier>
 #include <cmath>
 #include <cstdio>
@@ -66,6 +68,41 @@ using std::min;
 namespace stfem
 {
   __attribute__((aligned(128))) unsigned char brick_smem[1 << 18]; // the kernel's `extern __shared__` buffer
+  // mbarrier emulation: the 8 bytes of a barrier hold {pending arrivals, phase}; `count` sits in a side table
+  namespace brick_emu
+  {
+    struct Bar
+    {
+      std::atomic<int>      pending;
+      std::atomic<unsigned> phase;
+    };
+    static_assert(sizeof(Bar) == 8, "emulated barrier must fit the 8 bytes of an mbarrier");
+    static int g_count[64];
+    inline int slot(const unsigned long long *bar) { return (int)(bar - reinterpret_cast<const unsigned long long *>(brick_smem)); }
+    inline void mbar_init(unsigned long long *bar, unsigned count)
+    {
+      Bar *b = reinterpret_cast<Bar *>(bar);
+      new (b) Bar();
+      b->pending.store((int)count);
+      b->phase.store(0u);
+      g_count[slot(bar)] = (int)count;
+    }
+    inline void fence_init() {}
+    inline void mbar_arrive(unsigned long long *bar)
+    {
+      Bar *b = reinterpret_cast<Bar *>(bar);
+      if (b->pending.fetch_sub(1) == 1)
+        {
+          b->pending.store(g_count[slot(bar)]);
+          b->phase.fetch_add(1u);
+        }
+    }
+    inline void mbar_wait(unsigned long long *bar, unsigned parity)
+    {
+      Bar *b = reinterpret_cast<Bar *>(bar);
+      while ((b->phase.load() & 1u) == parity) std::this_thread::yield();
+    }
+  } // namespace brick_emu
 }
 
 #include "../../dealii-stfem_b200/csrc/basis_host.hpp"
@@ -78,13 +115,13 @@ struct Cmd
   int      n[3];
   double   h[3];
   unsigned mask;
-  int      zlo, zhi, mode, first_plane_acc, n_chunks, misalign;
+  int      zlo, zhi, mode, first_plane_acc, n_chunks, misalign, flow_a;
 };
 
-template <int N1, int NB, typename T, int CX, int CY>
+template <int N1, int NB, typename T, int CX, int CY, bool SPLIT>
 static int run(const Cmd &cmd, const std::vector<double> &in, std::vector<double> &out)
 {
-  using C = BrickCfg<T, N1, NB, CX, CY>;
+  using C = BrickCfg<T, N1, NB, CX, CY, SPLIT>;
   const int       degree = N1 - 1;
   const ShapeHost sh(degree);
   long long       N = 1;
@@ -119,13 +156,14 @@ static int run(const Cmd &cmd, const std::vector<double> &in, std::vector<double
   std::memset(&a, 0, sizeof(a));
   brick_fill_args<T, N1, NB, CX, CY>(a, sh.S.data(), sh.D.data(), sh.wq.data(), cmd.h, cmd.n, cmd.mask, in.data(), in.data() + NB * NB, sp, dp,
                                      cmd.zlo, cmd.zhi, cmd.mode != 0, cmd.first_plane_acc != 0, cmd.n_chunks, 296);
+  a.use_tma = cmd.flow_a;
   if ((size_t)C::smem_bytes(a.n_cls) > sizeof(brick_smem)) return 3;
   const long long grid = (long long)a.tiles_x * a.tiles_y * a.n_chunks;
-  std::printf("N1 %d NB %d tile %dx%d cells, %d threads, tiles %d x %d, %d chunks of %d layers, %d row classes (shifts", N1, NB, CX, CY, C::NTHREADS,
+  std::printf("N1 %d NB %d tile %dx%d cells%s, %d threads, tiles %d x %d, %d chunks of %d layers, %d row classes (shifts", N1, NB, CX, CY, SPLIT ? " (split warps)" : "", C::NTHREADS,
               a.tiles_x, a.tiles_y, a.n_chunks, a.layers_per_chunk, a.n_cls);
   for (int b = 0; b < NB; ++b)
     for (int c = 0; c < a.n_cls; ++c) std::printf(" %d", a.shift[b][c]);
-  std::printf("), smem %d bytes, grid %lld\n", C::smem_bytes(a.n_cls), grid);
+  std::printf("), smem %d bytes, grid %lld, flow %s\n", C::smem_bytes(a.n_cls), grid, a.use_tma == 2 ? "A2 (barrier pipeline)" : (a.use_tma ? "A1 (one CTA barrier per plane)" : "B (plain loads)"));
   // what launch_brick does before the kernel: the node planes shared by two z chunks start from zero in mode 0
   if (a.n_chunks > 1 && cmd.mode == 0)
     {
@@ -146,7 +184,7 @@ static int run(const Cmd &cmd, const std::vector<double> &in, std::vector<double
         pool.emplace_back([&a, t, blk]() {
           threadIdx.x = (unsigned)t;
           blockIdx.x  = (unsigned)blk;
-          st_vmult_brick_kernel<T, N1, NB, CX, CY, 1>(a);
+          st_vmult_brick_kernel<T, N1, NB, CX, CY, 1, SPLIT>(a);
         });
       for (auto &th : pool) th.join();
     }
@@ -174,6 +212,8 @@ int main(int argc, char **argv)
   cmd.n_chunks        = std::atoi(argv[14]);
   const int cx = std::atoi(argv[15]), cy = std::atoi(argv[16]);
   cmd.misalign = std::atoi(argv[17]);
+  // 1 (default): box loads by one thread + one CTA barrier per plane; 2: full / empty barrier pipeline; 0: plain loads by all threads
+  cmd.flow_a   = std::getenv("BRICK_EMU_FLOW_B") ? 0 : (std::getenv("BRICK_EMU_PIPE") ? 2 : 1);
   std::vector<double> in, out;
   {
     FILE *f = std::fopen(argv[18], "rb");
@@ -185,11 +225,13 @@ int main(int argc, char **argv)
     if (std::fread(in.data(), sizeof(double), in.size(), f) != in.size()) return 1;
     std::fclose(f);
   }
-  int rc = 4;
+  int        rc    = 4;
+  const bool split = std::getenv("BRICK_EMU_SPLIT") != nullptr; // X and Y+Z phases on separate warps
   // the product's tiles (BrickTile<N1>) and small ones that give several tiles and ragged edges on tiny meshes
 #define CASE(K_, NB_, CX_, CY_)                                                                              \
   if (degree == K_ && nb == NB_ && cx == CX_ && cy == CY_)                                                   \
-    rc = f32 ? run<K_ + 1, NB_, float, CX_, CY_>(cmd, in, out) : run<K_ + 1, NB_, double, CX_, CY_>(cmd, in, out);
+    rc = split ? (f32 ? run<K_ + 1, NB_, float, CX_, CY_, true>(cmd, in, out) : run<K_ + 1, NB_, double, CX_, CY_, true>(cmd, in, out)) : \
+                 (f32 ? run<K_ + 1, NB_, float, CX_, CY_, false>(cmd, in, out) : run<K_ + 1, NB_, double, CX_, CY_, false>(cmd, in, out));
   CASE(4, 2, 7, 4) CASE(4, 2, 3, 2) CASE(4, 1, 3, 2) CASE(4, 3, 3, 2) CASE(4, 1, 7, 4) CASE(4, 3, 7, 4)
   CASE(3, 2, 9, 5) CASE(3, 2, 4, 2) CASE(3, 3, 4, 2) CASE(3, 1, 4, 2)
   CASE(2, 2, 15, 6) CASE(2, 2, 3, 2) CASE(2, 3, 3, 2) CASE(2, 1, 3, 2)

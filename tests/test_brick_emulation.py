@@ -25,7 +25,7 @@ def emulator(tmp_path_factory):
 
 
 def run_emulator(exe, tmp_path, degree, A, B, cells, upper, mask, src, dst0, zlo=0, zhi=None, mode=0, first_plane_acc=0, n_chunks=0,
-                 tile=(7, 4), misalign=0, f32=False):
+                 tile=(7, 4), misalign=0, f32=False, flow_b=False, split=False, pipe=False):
     nb = A.shape[0]
     h = [upper[d] / cells[d] for d in range(3)]
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
@@ -36,7 +36,14 @@ def run_emulator(exe, tmp_path, degree, A, B, cells, upper, mask, src, dst0, zlo
                                                                                           str(tile[1]), str(misalign), fin, fout]
     if f32:
         cmd.append("f32")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ)
+    if split:
+        env["BRICK_EMU_SPLIT"] = "1"        # X phase and Y+Z phase on separate warps (kernel template parameter SPLIT)
+    if pipe:
+        env["BRICK_EMU_PIPE"] = "1"         # full / empty barrier pipeline (kernel_variant 79) instead of one CTA barrier per plane
+    if flow_b:
+        env["BRICK_EMU_FLOW_B"] = "1"       # plain loads + CTA-wide barriers instead of the mbarrier pipeline of the TMA flow
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     return np.fromfile(fout).reshape(nb, -1), r.stdout
 
@@ -75,6 +82,41 @@ def test_emulated_brick_kernel_matches_oracle(emulator, tmp_path, case):
     out, log = run_emulator(emulator, tmp_path, degree, A, B, cells, upper, mask, src, garbage, n_chunks=n_chunks, tile=tile,
                             misalign=misalign)
     assert np.all(np.isfinite(out)), log
+    assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max(), log
+    assert np.all(out[:, space.constrained] == 0)
+
+
+@pytest.mark.parametrize("case", CASES[:4], ids=lambda c: "k%d_%s%d_%s" % (c[0], c[1], c[2], "x".join(map(str, c[3]))))
+def test_emulated_brick_kernel_plain_load_flow(emulator, tmp_path, case):
+    """Flow B of the kernel (no tensor maps: all threads copy the boxes, CTA-wide barriers) gives the same result."""
+    degree, ttype, r, cells, upper, mask, tile, n_chunks, misalign = case
+    space, A, B, src, ref = oracle(degree, ttype, r, cells, upper, mask)
+    out, log = run_emulator(emulator, tmp_path, degree, A, B, cells, upper, mask, src, np.full_like(src, 7.5), n_chunks=n_chunks, tile=tile,
+                            misalign=misalign, flow_b=True)
+    assert "flow B" in log
+    assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max(), log
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[3], CASES[7]], ids=lambda c: "k%d_%s%d_%s" % (c[0], c[1], c[2], "x".join(map(str, c[3]))))
+def test_emulated_brick_kernel_barrier_pipeline(emulator, tmp_path, case):
+    """kernel_variant 79: X one plane ahead of Y+Z, coupled by full / empty barriers of three P/Q buffers, no CTA barrier."""
+    degree, ttype, r, cells, upper, mask, tile, n_chunks, misalign = case
+    space, A, B, src, ref = oracle(degree, ttype, r, cells, upper, mask)
+    out, log = run_emulator(emulator, tmp_path, degree, A, B, cells, upper, mask, src, np.full_like(src, 7.5), n_chunks=n_chunks, tile=tile,
+                            misalign=misalign, pipe=True)
+    assert "A2" in log
+    assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max(), log
+
+
+@pytest.mark.parametrize("flow_b", [False, True])
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3], CASES[5]], ids=lambda c: "k%d_%s%d_%s" % (c[0], c[1], c[2], "x".join(map(str, c[3]))))
+def test_emulated_brick_kernel_split_warps(emulator, tmp_path, case, flow_b):
+    """Template parameter SPLIT: the X phase and the Y+Z phase on separate warps, coupled only by the full / empty barriers."""
+    degree, ttype, r, cells, upper, mask, tile, n_chunks, misalign = case
+    space, A, B, src, ref = oracle(degree, ttype, r, cells, upper, mask)
+    out, log = run_emulator(emulator, tmp_path, degree, A, B, cells, upper, mask, src, np.full_like(src, 7.5), n_chunks=n_chunks, tile=tile,
+                            misalign=misalign, flow_b=flow_b, split=True, pipe=not flow_b)
+    assert "split warps" in log
     assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max(), log
     assert np.all(out[:, space.constrained] == 0)
 
