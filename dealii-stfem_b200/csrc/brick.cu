@@ -20,12 +20,14 @@ namespace stfem
     if (op->box_lo && (op->box_lo[0] != 0 || op->box_lo[1] != 0 || op->box_n[0] != m->n[0] || op->box_n[1] != m->n[1])) return false;
     // tiny levels are launch-latency bound: the march through z only adds latency there
     if (op->variant == 0 && m->n_cells < 512) return false;
+    // one block: only CY warps in the Y+Z phase against ceil((K CY + K + 1) / rows per warp) in the X phase - the per-cell kernel is faster (measured)
+    if (op->variant == 0 && nb_dst == 1) return false;
     return true;
   }
 
   template <typename T>
-  static int launch_brick_any(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, bool accumulate,
-                              bool first_plane_acc)
+  static int launch_brick_any(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, int mode,
+                              const void *const *rhs, bool first_plane_acc)
   {
     const std::vector<double> &hA = *brick_host_matrix(op, alpha), &hB = *brick_host_matrix(op, beta);
     const int  zlo = op->box_lo ? op->box_lo[2] : 0, zhi = op->box_lo ? op->box_lo[2] + op->box_n[2] : op->mesh->n[2];
@@ -34,19 +36,19 @@ namespace stfem
     const int  n_chunks = op->variant >= 80 && op->variant < 90 ? op->variant - 79 : 0; // 0: chosen by the launcher
     // tuning variants of the headline instance (Q4, two blocks): other tile heights / CTAs per SM
     if (op->variant == 77 && op->degree == 4 && nb == 2) // X and Y+Z phases on separate warps, one CTA per SM
-      return launch_brick<5, 2, T, 7, 4, 1, true>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+      return launch_brick<5, 2, T, 7, 4, 1, true>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
     if (op->variant == 78 && op->degree == 4 && nb == 2)
-      return launch_brick<5, 2, T, 7, 5, 1, true>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 73 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 2, 4>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 74 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 2>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 75 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 6, 1>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 76 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 3>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+      return launch_brick<5, 2, T, 7, 5, 1, true>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 73 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 2, 4>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 74 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 2>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 75 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 6, 1>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
+    if (op->variant == 76 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 3>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
     if (op->variant == 71 && op->degree == 4 && nb == 2) // tuning: one CTA per SM with the full register budget
-      return launch_brick<5, 2, T, BrickTile<5>::CX, BrickTile<5>::CY, 1>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, n_chunks);
+      return launch_brick<5, 2, T, BrickTile<5>::CX, BrickTile<5>::CY, 1>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
 #define STFEM_BRICK_CASE(N1_, NB_, MINB_)                                                                                             \
   if (op->degree + 1 == N1_ && nb == NB_)                                                                                             \
     {                                                                                                                                 \
-      return launch_brick<N1_, NB_, T, BrickTile<N1_>::CX, BrickTile<N1_>::CY, MINB_>(op, dst, src, hA, hB, accumulate, zlo, zhi, first_plane_acc, tma, \
+      return launch_brick<N1_, NB_, T, BrickTile<N1_>::CX, BrickTile<N1_>::CY, MINB_>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, \
                                                                                       n_chunks);                                     \
     }
     STFEM_BRICK_CASE(3, 1, 2) STFEM_BRICK_CASE(3, 2, 2) STFEM_BRICK_CASE(3, 3, 1)
@@ -57,10 +59,10 @@ namespace stfem
     return STFEM_ERR_UNSUPPORTED;
   }
 
-  int brick_launch(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, bool accumulate,
-                   bool first_plane_acc)
+  int brick_launch(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, int mode,
+                   const void *const *rhs, bool first_plane_acc)
   {
-    return op->number_type == STFEM_F64 ? launch_brick_any<double>(op, dst, src, nb, alpha, beta, accumulate, first_plane_acc) :
-                                          launch_brick_any<float>(op, dst, src, nb, alpha, beta, accumulate, first_plane_acc);
+    return op->number_type == STFEM_F64 ? launch_brick_any<double>(op, dst, src, nb, alpha, beta, mode, rhs, first_plane_acc) :
+                                          launch_brick_any<float>(op, dst, src, nb, alpha, beta, mode, rhs, first_plane_acc);
   }
 } // namespace stfem

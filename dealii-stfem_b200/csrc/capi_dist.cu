@@ -211,10 +211,19 @@ namespace stfem
     for (int d = 0; d < dim; ++d)
       for (int s = 0; s < 2; ++s)
         if (part.neighbor[d][s] >= 0) faces |= 1u << (2 * d + s);
-    const long long total = (long long)np[0] * np[1] * (dim == 3 ? np[2] : 1) * nb;
-    const int       grid  = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
-    k_scale_interfaces<T><<<grid, 256, 0, ctx->stream>>>(bp, nb, np[0], np[1], dim == 3 ? np[2] : 1, faces);
-    ctx->launches++;
+    const int np2 = dim == 3 ? np[2] : 1;
+    for (int d = 0; d < dim; ++d)
+      {
+        const unsigned sides = (faces >> (2 * d)) & 3u;
+        if (!sides) continue;
+        long long face = 1;
+        for (int e = 0; e < dim; ++e)
+          if (e != d) face *= np[e];
+        const long long total = face * nb * 2;
+        const int       grid  = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 8);
+        k_scale_interface_faces<T><<<grid, 256, 0, ctx->stream>>>(bp, nb, np[0], np[1], np2, d, sides);
+        ctx->launches++;
+      }
     STFEM_CUDA_CHECK(cudaGetLastError());
     return STFEM_OK;
   }

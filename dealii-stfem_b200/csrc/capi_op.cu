@@ -671,16 +671,53 @@ namespace stfem
   }
 
   int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
-               const void *beta, bool zero_dst)
+               const void *beta, bool zero_dst, const void *const *rhs)
   {
     stfem_ctx *ctx = op->mesh->ctx;
     STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (op->timing) STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     const size_t bytes = (size_t)op->N * (op->number_type == STFEM_F64 ? 8 : 4);
+    bool         direct_partial = false; // partitioned mesh: dst already holds rhs / multiplicity, accumulate into it, then exchange
+    if (rhs)
+      {
+        // dst = rhs + A src: one pass of the brick kernel on unpartitioned meshes, else copy + accumulate
+        STFEM_REQUIRE(zero_dst, "op_apply: rhs needs zero_dst");
+        const PartitionInfo &prt = op->mesh->part;
+        auto halo_dst = [&]() -> int {
+          if (!prt.active) return STFEM_OK;
+          if (op->number_type == STFEM_F64) return halo_compress_add<double>(ctx, prt, op->halo, dst, nb_dst, op->np, op->mesh->dim, ctx->stream);
+          return halo_compress_add<float>(ctx, prt, op->halo, dst, nb_dst, op->np, op->mesh->dim, ctx->stream);
+        };
+        if (brick_eligible(op, nb_src, nb_dst, alpha, beta))
+          {
+            // partitioned meshes: every rank adds rhs / multiplicity at its interface nodes (the kernel knows the shared faces),
+            // so the one exchange that sums the partial A src also restores rhs: no scratch vector, no extra pass
+            STFEM_FORWARD(brick_launch(op, dst, src, nb_dst, alpha, beta, 2, rhs, false));
+            STFEM_FORWARD(halo_dst());
+            if (op->timing)
+              {
+                STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+                STFEM_CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+                STFEM_CUDA_CHECK(cudaEventElapsedTime(&op->last_ms, ctx->ev0, ctx->ev1));
+              }
+            return STFEM_OK;
+          }
+        for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemcpyAsync(dst[b], rhs[b], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        zero_dst = false;
+        if (prt.active)
+          {
+            // the same with the per-cell kernels: dst = rhs / multiplicity, the cell loop reduces straight into it, one exchange
+            if (op->number_type == STFEM_F64)
+              STFEM_FORWARD(halo_scale_interfaces<double>(ctx, prt, op->halo, dst, nb_dst, op->np, op->mesh->dim));
+            else
+              STFEM_FORWARD(halo_scale_interfaces<float>(ctx, prt, op->halo, dst, nb_dst, op->np, op->mesh->dim));
+            direct_partial = true;
+          }
+      }
     // partitioned mesh + accumulate: the increment goes to a scratch vector first, so that only the increment is
     // summed over the ranks sharing an interface DoF
     void *const *target = dst;
-    const bool   via_scratch = op->mesh->part.active && !zero_dst;
+    const bool   via_scratch = op->mesh->part.active && !zero_dst && !direct_partial;
     if (via_scratch)
       {
         while ((int)op->d_part_scratch.size() < nb_dst)
@@ -704,7 +741,7 @@ namespace stfem
       for (int b = 0; b < nb_dst; ++b) STFEM_CUDA_CHECK(cudaMemsetAsync(target[b], 0, bytes, ctx->stream));
     auto dispatch = [&]() -> int {
       if (brick)
-        return brick_launch(op, target, src, nb_dst, alpha, beta, !(zero_dst || via_scratch), false);
+        return brick_launch(op, target, src, nb_dst, alpha, beta, (zero_dst || via_scratch) ? 0 : 1, nullptr, false);
       if (op->mesh->dim == 2)
         return op->number_type == STFEM_F64 ? dispatch_degree<2, double>(op, target, src, nb_src, nb_dst, alpha, beta) :
                                               dispatch_degree<2, float>(op, target, src, nb_src, nb_dst, alpha, beta);
@@ -1087,7 +1124,7 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
       int lo[3] = {0, 0, z0}, nn[3] = {mn[0], mn[1], z1 - z0};
       op->box_lo = lo;
       op->box_n  = nn;
-      int rc = brick ? brick_launch(op, d.data(), s.data(), nb, alpha, beta, false, sl > 0) :
+      int rc = brick ? brick_launch(op, d.data(), s.data(), nb, alpha, beta, 0, nullptr, sl > 0) :
                op->number_type == STFEM_F64 ? dispatch_degree<3, double>(op, d.data(), s.data(), nb, nb, alpha, beta) :
                                               dispatch_degree<3, float>(op, d.data(), s.data(), nb, nb, alpha, beta);
       op->box_lo = op->box_n = nullptr;

@@ -112,6 +112,30 @@ namespace stfem
       }
   }
 
+  // the same on the two faces normal to `axis` only (one launch per direction with interfaces: a node on an edge or corner is
+  // halved once per direction it is shared in); work proportional to the faces, not to the vector
+  template <typename T>
+  __global__ void k_scale_interface_faces(BlockPtrs blocks, int nb, int np0, int np1, int np2, int axis, unsigned sides)
+  {
+    const int       a = axis == 0 ? np1 : np0, b = axis == 2 ? np1 : np2; // plane extents (fast, slow)
+    const int       nd = axis == 0 ? np0 : (axis == 1 ? np1 : np2);
+    const long long per = (long long)a * b, total = per * nb * 2;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        const int side = (int)(gid / (per * nb));
+        if (!((sides >> side) & 1u) || (side == 1 && nd == 1)) continue;
+        const long long g   = gid % (per * nb);
+        const int       blk = (int)(g / per);
+        const long long r   = g % per;
+        const int       u = (int)(r % a), v = (int)(r / a), index = side == 0 ? 0 : nd - 1;
+        long long       off;
+        if (axis == 0) off = (long long)index + (long long)np0 * (u + (long long)np1 * v);
+        else if (axis == 1) off = (long long)u + (long long)np0 * (index + (long long)np1 * v);
+        else off = (long long)u + (long long)np0 * (v + (long long)np1 * index);
+        ((T *)blocks.p[blk])[off] *= T(0.5);
+      }
+  }
+
   // brick <-> global copies of the coarse-level agglomeration (csrc/mg.cuh): the local brick [b][bz][by][bx] sits at
   // node offset (o0, o1, o2) of the global array [b][gz][gy][gx]
   template <typename T, bool TO_GLOBAL>

@@ -124,19 +124,12 @@ namespace stfem
       return op_apply(op, dst.block_ptrs(), src.cblock_ptrs(), op->nb_cols, op->nb_rows, op->d_alpha, op->d_beta, true);
     }
 
-    // r = b - A x.  Single GPU: r is initialised with b and the operator kernel reduces -A x into it (no
-    // separate vector update); partitioned meshes go through a temporary so that only A x is summed over ranks.
+    // r = b - A x in one pass of the operator kernel (negated time matrices, rhs = b).  Partitioned meshes: every rank
+    // contributes b / multiplicity at its interface nodes, so the one exchange of the partial sums also restores b.
     int residual(int l, BlockVec<T> &r, const BlockVec<T> &x, const BlockVec<T> &b)
     {
       stfem_op *op = L[l].op;
-      if (op->mesh->part.active)
-        {
-          STFEM_FORWARD(A(l, r, x));
-          v_sadd(r, (T)-1, (T)1, b);
-          return STFEM_OK;
-        }
-      STFEM_FORWARD(v_copy(r, b));
-      return op_apply(op, r.block_ptrs(), x.cblock_ptrs(), op->nb_cols, op->nb_rows, op->d_alpha_neg, op->d_beta_neg, false);
+      return op_apply(op, r.block_ptrs(), x.cblock_ptrs(), op->nb_cols, op->nb_rows, op->d_alpha_neg, op->d_beta_neg, true, b.cblock_ptrs());
     }
     // dst += scale * P^-1 src  (Vanka); partitioned meshes: the increment is summed over ranks before it is added
     int vanka_add(int l, BlockVec<T> &dst, const BlockVec<T> &src, T scale)
@@ -150,12 +143,21 @@ namespace stfem
         }
       if (lv.op->mesh->part.active)
         {
-          if (tmp_part.size() <= (size_t)l) tmp_part.resize(L.size());
-          if (!tmp_part[l].d) STFEM_FORWARD(tmp_part[l].alloc(ctx, src.nb, src.n));
-          STFEM_FORWARD(lv.vanka->vmult(tmp_part[l], src));
-          STFEM_FORWARD(halo_compress_add<T>(ctx, lv.op->mesh->part, lv.op->halo, tmp_part[l].block_ptrs(), src.nb, lv.op->np, lv.op->mesh->dim));
-          v_axpy(dst, scale, tmp_part[l]);
-          return STFEM_OK;
+          // the copies of an interface DoF are weighted with 1 / multiplicity, every rank adds the increments of its own
+          // patches to them, and the exchange sums both: dst + scale * sum of all increments, without a temporary
+          static const bool via_tmp = std::getenv("STFEM_VANKA_VIA_TMP") != nullptr; // round-1 path (A/B comparison)
+          if (via_tmp)
+            {
+              if (tmp_part.size() <= (size_t)l) tmp_part.resize(L.size());
+              if (!tmp_part[l].d) STFEM_FORWARD(tmp_part[l].alloc(ctx, src.nb, src.n));
+              STFEM_FORWARD(lv.vanka->vmult(tmp_part[l], src));
+              STFEM_FORWARD(halo_compress_add<T>(ctx, lv.op->mesh->part, lv.op->halo, tmp_part[l].block_ptrs(), src.nb, lv.op->np, lv.op->mesh->dim));
+              v_axpy(dst, scale, tmp_part[l]);
+              return STFEM_OK;
+            }
+          STFEM_FORWARD(halo_scale_interfaces<T>(ctx, lv.op->mesh->part, lv.op->halo, dst.block_ptrs(), dst.nb, lv.op->np, lv.op->mesh->dim));
+          STFEM_FORWARD(lv.vanka->vmult_add(dst, src, scale));
+          return halo_compress_add<T>(ctx, lv.op->mesh->part, lv.op->halo, dst.block_ptrs(), dst.nb, lv.op->np, lv.op->mesh->dim);
         }
       return lv.vanka->vmult_add(dst, src, scale);
     }
@@ -730,30 +732,49 @@ namespace stfem
               else
                 STFEM_FORWARD(v_copy(Z[j], V[j]));
               STFEM_FORWARD(apply_A(w, Z[j]));
-              // classical Gram-Schmidt, one re-orthogonalisation pass; every pass = one fused multi-dot
-              // (all h_ij and ||w||^2 in one sweep over w) and one fused multi-axpy
+              // Classical Gram-Schmidt with one re-orthogonalisation ("twice is enough"), in three passes over the basis instead
+              // of five: (1) fused multi-dot: all h_ij; (2) w -= V h fused with the inner products of the UPDATED w with V
+              // and with itself; (3) the second update, the normalisation and the copy into the basis in one pass - the norm
+              // of the final vector follows from Pythagoras, ||w' - V h'||^2 = ||w'||^2 - ||h'||^2, which is safe here: after
+              // the first pass h' is at rounding level, so nothing cancels.
               std::vector<const BlockVec<double> *> basis;
               for (int i = 0; i <= j; ++i) basis.push_back(&V[i]);
-              double wnorm2 = 0;
-              for (int pass = 0; pass < 2; ++pass)
+              double              hn = 0;
+              std::vector<double> c(j + 1);
+              STFEM_FORWARD(v_multi_dot(sc, w, basis, h.data()));
+              for (int i = 0; i <= j; ++i)
                 {
-                  std::vector<const BlockVec<double> *> q = basis;
-                  if (pass == 0) q.push_back(&w); // ||w||^2 is only informative in the first pass
-                  STFEM_FORWARD(v_multi_dot(sc, w, q, h.data()));
-                  std::vector<double> c(j + 1);
+                  c[i] = -h[i];
+                  Hm(i, j) += h[i];
+                }
+              if (j + 1 <= MAXK)
+                {
+                  STFEM_FORWARD(v_multi_axpy_dot(sc, w, basis, c.data(), h.data()));
+                  double hh = 0;
+                  for (int i = 0; i <= j; ++i)
+                    {
+                      c[i] = -h[i];
+                      Hm(i, j) += h[i];
+                      hh += h[i] * h[i];
+                    }
+                  hn = std::sqrt(std::max(h[j + 1] - hh, 0.0));
+                  if (hn != 0.0) v_multi_axpy_scale_out(V[j + 1], w, basis, c.data(), 1.0 / hn);
+                }
+              else
+                {
+                  double wnorm2 = 0;
+                  v_multi_axpy(w, basis, c.data());
+                  STFEM_FORWARD(v_multi_dot(sc, w, basis, h.data()));
                   for (int i = 0; i <= j; ++i)
                     {
                       c[i] = -h[i];
                       Hm(i, j) += h[i];
                     }
-                  if (pass == 0)
-                    v_multi_axpy(w, basis, c.data());
-                  else // second pass: the norm of the orthogonalised vector is accumulated in the same sweep
-                    STFEM_FORWARD(v_multi_axpy_norm(sc, w, basis, c.data(), &wnorm2));
+                  STFEM_FORWARD(v_multi_axpy_norm(sc, w, basis, c.data(), &wnorm2));
+                  hn = std::sqrt(std::max(wnorm2, 0.0));
+                  if (hn != 0.0) v_scale_copy(V[j + 1], 1.0 / hn, w);
                 }
-              const double hn = std::sqrt(std::max(wnorm2, 0.0));
-              Hm(j + 1, j)    = hn;
-              if (hn != 0.0) v_scale_copy(V[j + 1], 1.0 / hn, w);
+              Hm(j + 1, j) = hn;
               for (int i = 0; i < j; ++i)
                 {
                   const double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);

@@ -35,14 +35,16 @@ struct stfem_op
 namespace stfem
 {
   int ctx_ensure_aux(stfem_ctx *ctx);
-  // dst (+)= A src with explicit time matrices (device pointers in the operator's number type)
+  // dst (+)= A src with explicit time matrices (device pointers in the operator's number type); rhs != nullptr (with
+  // zero_dst): dst = rhs + A src in one pass (the residual b - A x with the negated matrices)
   int op_apply(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
-               const void *beta, bool zero_dst);
+               const void *beta, bool zero_dst, const void *const *rhs = nullptr);
   // brick kernel (brick.cu): can this application run through it / run it.  The launch honours op->box_lo / box_n in z
   // (cell layers) and op->launch_stream; first_plane_acc: the first node plane of the z range is accumulated
   bool brick_eligible(const stfem_op *op, int nb_src, int nb_dst, const void *alpha, const void *beta);
-  int  brick_launch(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, bool accumulate,
-                    bool first_plane_acc);
+  // mode 0: dst = A src, 1: dst += A src, 2: dst = rhs + A src
+  int  brick_launch(stfem_op *op, void *const *dst, const void *const *src, int nb, const void *alpha, const void *beta, int mode,
+                    const void *const *rhs, bool first_plane_acc);
   // diag K, diag M (double, cudaMalloc'ed, caller frees), constrained rows 0; capi_op.cu
   int op_spatial_diagonals(stfem_op *op, double **dK, double **dM);
 } // namespace stfem

@@ -103,12 +103,14 @@ namespace stfem
     int n[3], np[3];
     int zlo, zhi;        // cell layers [zlo, zhi) of this launch
     int layers_per_chunk, n_chunks, tiles_x, tiles_y;
-    int mode;            // 0: dst = A src, 1: dst += A src
+    int mode;            // 0: dst = A src, 1: dst += A src, 2: dst = rhs + A src
     int first_plane_acc; // plane K*zlo is accumulated even in mode 0 (z-slab pipeline: it holds the partial sum of the slab below)
     int use_tma;
     unsigned dirichlet;
+    unsigned iface;      // bit 2d+s: face s of direction d is shared with another rank (mode 2: rhs enters with weight 1/multiplicity)
     const T *src[NB];
     T       *dst[NB];
+    const T *rhs[NB]; // mode 2
   };
 
 
@@ -169,7 +171,7 @@ namespace stfem
   template <typename T, int N1, int NB, int CX, int CY>
   inline void brick_fill_args(BrickArgs<T, N1, NB> &a, const double *S, const double *D, const double *wq, const double h[3], const int n[3],
                               unsigned dirichlet, const double *Alpha, const double *Beta, const void *const *src, void *const *dst, int zlo,
-                              int zhi, bool accumulate, bool first_plane_acc, int n_chunks, long long slots)
+                              int zhi, int mode, const void *const *rhs, bool first_plane_acc, int n_chunks, long long slots, unsigned iface = 0)
   {
     using C = BrickCfg<T, N1, NB, CX, CY>;
     constexpr int K = N1 - 1;
@@ -213,9 +215,10 @@ namespace stfem
       }
     a.zlo             = zlo;
     a.zhi             = zhi;
-    a.mode            = accumulate ? 1 : 0;
+    a.mode            = mode;
     a.first_plane_acc = first_plane_acc ? 1 : 0;
     a.dirichlet       = dirichlet;
+    a.iface           = mode == 2 ? iface : 0u;
     a.tiles_x         = (n[0] + CX - 1) / CX;
     // the top node row (y = K n1) is node 0 of the chunk of the non-existing cell n1: one more chunk, i.e. one more tile row
     // when n1 is a multiple of CY - unless that row is a Dirichlet row, whose zeros the last chunk writes
@@ -237,6 +240,7 @@ namespace stfem
       {
         a.src[b] = (const T *)src[b];
         a.dst[b] = (T *)dst[b];
+        a.rhs[b] = mode == 2 ? (const T *)rhs[b] : nullptr;
         brick_describe_block<T>(src[b], a.np[0], n_rows, a.n_cls, C::WXP, HB, a.desc[b], a.shift[b]);
         for (int c = 0; c < a.n_cls; ++c) a.shift_pack |= (unsigned)a.shift[b][c] << (2 * (4 * b + c));
       }
@@ -565,7 +569,8 @@ namespace stfem
     const bool has_below = cyg >= 1, has_above = cyg < a.n[1];
     const int  yz_ld_off = (K * yc) * PXP + xo;
     // stores: node nn of the chunk is written iff st_mask bit nn; its value is forced to 0 iff con_mask bit nn
-    unsigned   st_mask = 0, con_mask = 0;
+    unsigned   st_mask = 0, con_mask = 0, wy_mask = 0;
+    T          wx = T(1);
     {
       const bool x_ok  = lane <= TX && xg < np0 && (lane < TX || xg == np0 - 1);
       const bool x_con = ((dm & 1u) && xg == 0) || ((dm & 2u) && xg == np0 - 1);
@@ -575,6 +580,17 @@ namespace stfem
           const int yg = K * cyg + nn;
           if (x_ok && yg < np1) st_mask |= 1u << nn;
           if (x_con || ((dm & 4u) && yg == 0) || ((dm & 8u) && yg == np1 - 1)) con_mask |= 1u << nn;
+        }
+      // mode 2 on a partitioned mesh: every rank sharing a node adds rhs / multiplicity, the exchange then sums to rhs + A src
+      if (a.iface)
+        {
+          if (((a.iface & 1u) && xg == 0) || ((a.iface & 2u) && xg == np0 - 1)) wx = T(0.5);
+#pragma unroll
+          for (int nn = 0; nn <= K; ++nn)
+            {
+              const int yg = K * cyg + nn;
+              if (((a.iface & 4u) && yg == 0) || ((a.iface & 8u) && yg == np1 - 1)) wy_mask |= 1u << nn;
+            }
         }
       // the top node row of a mesh whose cell count is a multiple of CY is not owned by any chunk when it is a Dirichlet row
       // (the launcher then saves the extra tile row): the last chunk writes its zeros
@@ -588,43 +604,131 @@ namespace stfem
 #pragma unroll
       for (int i = 0; i < N1; ++i) acc[nn][i] = T(0);
 
-    // write plane z (local plane index i of the accumulators) of the chunk's nodes; shared: the plane also receives a
-    // partial sum from the neighbouring z chunk of this launch
-    auto store_plane = [&](int z, auto itag, bool shared) {
-      constexpr int i = decltype(itag)::value;
-      const bool    z_con = ((dm & 16u) && z == 0) || ((dm & 32u) && z == np2 - 1);
-      T            *p     = dst_base + plane_stride * z;
-      if (shared)
+    // Write NP consecutive node planes zb .. zb+NP-1 (local plane indices 0 .. NP-1 of the accumulators) of the chunk's nodes.
+    //   mode 0  dst = A src        mode 1  dst += A src        mode 2  dst = rhs + A src   (constrained rows: 0 / dst / rhs)
+    // The plane between two z chunks of the launch (first_shared / last plane with shared_top) gets both partial sums by
+    // atomic adds onto zeros (modes 0, 2; in mode 2 the upper chunk adds rhs as well) or onto dst (mode 1).
+    // All reads (old dst or rhs) are issued first, as one batch: a load-add-store chain per value would expose the memory
+    // latency NP * K times per layer.
+    auto store_planes = [&](int zb, auto nptag, bool first_shared) {
+      constexpr int NP = decltype(nptag)::value;
+      const int     mode = a.mode;
+      T            *p0   = dst_base + plane_stride * zb;
+      const T      *r0p  = (mode == 2 ? a.rhs[jz] : a.dst[jz]) + (dst_base - a.dst[jz]) + plane_stride * zb;
+      const bool    acc0 = a.first_plane_acc && zb == K * a.zlo; // z-slab launches: plane K*zlo holds the partial sum of the slab below
+      if (mode == 0 && !acc0)
         {
-          if (!z_con)
+          // plain assignment: nothing to read
+#pragma unroll
+          for (int i = 0; i < NP; ++i)
             {
+              const int  z     = zb + i;
+              const bool z_con = ((dm & 16u) && z == 0) || ((dm & 32u) && z == np2 - 1);
+              T         *p     = p0 + plane_stride * i;
+              if (i == 0 && first_shared)
+                {
+                  if (!z_con)
+                    {
 #pragma unroll
-              for (int nn = 0; nn < K; ++nn)
-                if (((st_mask & ~con_mask) >> nn) & 1u) atomicAdd(p + nn * np0, acc[nn][i]);
+                      for (int nn = 0; nn < K; ++nn)
+                        if (((st_mask & ~con_mask) >> nn) & 1u) atomicAdd(p + nn * np0, acc[nn][i]);
+                    }
+                }
+              else if (!z_con && con_mask == 0 && !((st_mask >> K) & 1u))
+                {
+#pragma unroll
+                  for (int nn = 0; nn < K; ++nn)
+                    if ((st_mask >> nn) & 1u) p[nn * np0] = acc[nn][i];
+                }
+              else
+                {
+#pragma unroll
+                  for (int nn = 0; nn < K; ++nn)
+                    if ((st_mask >> nn) & 1u) p[nn * np0] = (z_con || ((con_mask >> nn) & 1u)) ? T(0) : acc[nn][i];
+                  if ((st_mask >> K) & 1u) p[K * np0] = T(0);
+                }
             }
+          return;
         }
-      else if (a.mode == 1 || (a.first_plane_acc && z == K * a.zlo))
-        {
-          if (!z_con)
-            {
-#pragma unroll
-              for (int nn = 0; nn < K; ++nn)
-                if (((st_mask & ~con_mask) >> nn) & 1u) p[nn * np0] += acc[nn][i];
-            }
-        }
-      else if (!z_con && con_mask == 0 && !((st_mask >> K) & 1u))
+      T old[NP][K + 1];
+      if (mode != 0 || acc0)
         {
 #pragma unroll
-          for (int nn = 0; nn < K; ++nn)
-            if ((st_mask >> nn) & 1u) p[nn * np0] = acc[nn][i];
+          for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int nn = 0; nn <= K; ++nn)
+              {
+                const bool need = ((st_mask >> nn) & 1u) && (mode != 0 || i == 0) && !(mode == 1 && i == 0 && first_shared);
+                old[i][nn]      = need ? r0p[plane_stride * i + nn * np0] : T(0);
+              }
         }
       else
         {
 #pragma unroll
-          for (int nn = 0; nn < K; ++nn)
-            if ((st_mask >> nn) & 1u) p[nn * np0] = (z_con || ((con_mask >> nn) & 1u)) ? T(0) : acc[nn][i];
-          if ((st_mask >> K) & 1u) p[K * np0] = T(0);
+          for (int i = 0; i < NP; ++i)
+#pragma unroll
+            for (int nn = 0; nn <= K; ++nn) old[i][nn] = T(0);
         }
+      if (mode == 2 && a.iface)
+        {
+#pragma unroll
+          for (int i = 0; i < NP; ++i)
+            {
+              const int z  = zb + i;
+              const T   wz = (((a.iface & 16u) && z == 0) || ((a.iface & 32u) && z == np2 - 1)) ? T(0.5) : T(1);
+#pragma unroll
+              for (int nn = 0; nn <= K; ++nn) old[i][nn] *= wx * wz * (((wy_mask >> nn) & 1u) ? T(0.5) : T(1));
+            }
+        }
+#pragma unroll
+      for (int i = 0; i < NP; ++i)
+        {
+          const int  z      = zb + i;
+          const bool z_con  = ((dm & 16u) && z == 0) || ((dm & 32u) && z == np2 - 1);
+          const bool shared = i == 0 && first_shared;
+          T         *p      = p0 + plane_stride * i;
+#pragma unroll
+          for (int nn = 0; nn < K; ++nn)
+            {
+              if (!((st_mask >> nn) & 1u)) continue;
+              const bool con = z_con || ((con_mask >> nn) & 1u);
+              const T    v   = con ? T(0) : acc[nn][i];
+              if (shared)
+                {
+                  if (mode == 2)
+                    atomicAdd(p + nn * np0, v + old[i][nn]); // this chunk is the upper one of the plane: it brings rhs along
+                  else if (!con)
+                    atomicAdd(p + nn * np0, v);
+                }
+              else if (mode == 1 || (acc0 && i == 0))
+                {
+                  if (!con) p[nn * np0] = old[i][nn] + v;
+                }
+              else
+                p[nn * np0] = old[i][nn] + v; // mode 0: old = 0
+            }
+          // the Dirichlet row on top of the mesh that no chunk owns (see zero_top_row): 0 / untouched / rhs
+          if (((st_mask >> K) & 1u) && mode != 1 && !(acc0 && i == 0) && !shared) p[K * np0] = old[i][K];
+          if (((st_mask >> K) & 1u) && mode == 2 && shared) atomicAdd(p + K * np0, old[i][K]);
+        }
+    };
+    // the top plane of the chunk: if a chunk follows, it is shared with it and this chunk is the LOWER one
+    auto store_top = [&](int z, bool shared_top) {
+      const int  mode  = a.mode;
+      const bool z_con = ((dm & 16u) && z == 0) || ((dm & 32u) && z == np2 - 1);
+      T         *p     = dst_base + plane_stride * z;
+      if (shared_top)
+        {
+          if (!z_con)
+            {
+#pragma unroll
+              for (int nn = 0; nn < K; ++nn)
+                if (((st_mask & ~con_mask) >> nn) & 1u) atomicAdd(p + nn * np0, acc[nn][0]);
+            }
+          return;
+        }
+      store_planes(z, std::integral_constant<int, 1>(), false);
+      (void)mode;
     };
 
     // ---- the two phases of one node plane q (local index of this CTA's march)
@@ -799,13 +903,7 @@ namespace stfem
                 {
                   zacc(std::integral_constant<int, K>()); // closes cell layer `layer - 1`
                   {
-                    const int zb = K * (layer - 1);
-                    store_plane(zb + 0, std::integral_constant<int, 0>(), layer - 1 == cz0 && cz0 > a.zlo);
-                    if (K > 1) store_plane(zb + 1, std::integral_constant<int, (K > 1 ? 1 : 0)>(), false);
-                    if (K > 2) store_plane(zb + 2, std::integral_constant<int, (K > 2 ? 2 : 0)>(), false);
-                    if (K > 3) store_plane(zb + 3, std::integral_constant<int, (K > 3 ? 3 : 0)>(), false);
-                    if (K > 4) store_plane(zb + 4, std::integral_constant<int, (K > 4 ? 4 : 0)>(), false);
-                    if (K > 5) store_plane(zb + 5, std::integral_constant<int, (K > 5 ? 5 : 0)>(), false);
+                    store_planes(K * (layer - 1), std::integral_constant<int, K>(), layer - 1 == cz0 && cz0 > a.zlo);
                   }
 #pragma unroll
                   for (int nn = 0; nn < K; ++nn)
@@ -889,6 +987,6 @@ namespace stfem
       }
     // the top plane of the chunk: shared with the chunk above; at the top of the launch range it is complete (top of the
     // mesh) or the partial sum of the cells below (z-slab launches)
-    if (yz_warp) store_plane(K * cz1, std::integral_constant<int, 0>(), cz1 < a.zhi);
+    if (yz_warp) store_top(K * cz1, cz1 < a.zhi);
   }
 } // namespace stfem

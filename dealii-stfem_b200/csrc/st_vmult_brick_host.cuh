@@ -57,7 +57,7 @@ namespace stfem
 
   template <int N1, int NB, typename T, int CX, int CY, int MINB, bool SPLIT = false>
   static int launch_brick(stfem_op *op, void *const *dst, const void *const *src, const std::vector<double> &Alpha, const std::vector<double> &Beta,
-                          bool accumulate, int zlo, int zhi, bool first_plane_acc, int use_tma, int n_chunks)
+                          int mode, const void *const *rhs, int zlo, int zhi, bool first_plane_acc, int use_tma, int n_chunks)
   {
     using C = BrickCfg<T, N1, NB, CX, CY, SPLIT>;
     stfem_mesh *m = op->mesh;
@@ -67,8 +67,13 @@ namespace stfem
     const ShapeHost &sh = *op->shape;
     double           h[3];
     for (int d = 0; d < 3; ++d) h[d] = (m->upper[d] - m->lower[d]) / m->n[d];
+    unsigned iface = 0; // faces shared with other ranks
+    if (m->part.active)
+      for (int d = 0; d < 3; ++d)
+        for (int sd = 0; sd < 2; ++sd)
+          if (m->part.neighbor[d][sd] >= 0) iface |= 1u << (2 * d + sd);
     brick_fill_args<T, N1, NB, CX, CY>(a, sh.S.data(), sh.D.data(), sh.wq.data(), h, m->n, m->dirichlet, Alpha.data(), Beta.data(), src, dst, zlo, zhi,
-                                       accumulate, first_plane_acc, n_chunks, (long long)m->ctx->sm_count * MINB);
+                                       mode, rhs, first_plane_acc, n_chunks, (long long)m->ctx->sm_count * MINB, iface);
     STFEM_REQUIRE(a.n_cls <= C::MAXCLS, "st_vmult (brick): %d row classes", a.n_cls);
     a.use_tma = use_tma;
     for (int b = 0; b < NB && a.use_tma; ++b)
@@ -79,7 +84,7 @@ namespace stfem
             break;
           }
     cudaStream_t stream = op->launch_stream ? op->launch_stream : m->ctx->stream;
-    if (a.n_chunks > 1 && !accumulate)
+    if (a.n_chunks > 1 && mode != 1)
       {
         BrickZeroArgs<T, NB> z;
         for (int b = 0; b < NB; ++b) z.dst[b] = (T *)dst[b];

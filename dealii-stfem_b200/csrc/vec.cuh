@@ -141,6 +141,19 @@ namespace stfem
         atomicAdd(nrm2, v);
       }
   }
+  // out = scale * (w + sum_k c[k] V_k): the Gram-Schmidt update and the normalisation of the new basis vector in one pass
+  // (w is read, not written: the next Arnoldi step overwrites it anyway)
+  template <typename T>
+  __global__ void k_multi_axpy_scale_out(long long n, MultiCoef<T> mc, T scale, const T *__restrict__ w, T *__restrict__ out)
+  {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        T s = w[i];
+#pragma unroll 4
+        for (int k = 0; k < mc.m; ++k) s += mc.c[k] * mc.v[k][i];
+        out[i] = scale * s;
+      }
+  }
   // y = a * x
   template <typename T>
   __global__ void k_scale_copy(long long n, T a, const T *__restrict__ x, T *__restrict__ y)
@@ -166,6 +179,52 @@ namespace stfem
     return ((m.skip_high & 1u) && ix == m.np[0] - 1) || ((m.skip_high & 2u) && iy == m.np[1] - 1) || ((m.skip_high & 4u) && iz == m.np[2] - 1);
   }
 
+  // w += sum_k c[k] V_k  and, with the UPDATED w,  out[k] += <w, V_k> (k < m),  out[m] += ||w||^2  in the same pass: the
+  // first Gram-Schmidt update fused with the inner products of the re-orthogonalisation pass
+  template <typename T>
+  __global__ void k_multi_axpy_dot(long long n, MultiCoef<T> mc, T *__restrict__ w, double *__restrict__ out, DotMask mask)
+  {
+    double acc[MAXK + 1];
+#pragma unroll
+    for (int k = 0; k <= MAXK; ++k) acc[k] = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      {
+        T vk[MAXK];
+        T s = w[i];
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+          if (k < mc.m)
+            {
+              vk[k] = mc.v[k][i];
+              s += mc.c[k] * vk[k];
+            }
+        w[i] = s;
+        if (mask.active && dot_masked(mask, i)) continue;
+        const double sd = (double)s;
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+          if (k < mc.m) acc[k] += sd * (double)vk[k];
+        acc[MAXK] += sd * sd;
+      }
+    __shared__ double sh[MAXK + 1][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k <= MAXK; ++k)
+      if (k < mc.m || k == MAXK)
+        {
+          double v = acc[k];
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) sh[k][warp] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x <= mc.m)
+      {
+        const int k = threadIdx.x < mc.m ? threadIdx.x : MAXK;
+        double    v = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sh[k][wv];
+        atomicAdd(out + threadIdx.x, v);
+      }
+  }
   // out[k] += <w, V_k>  accumulated in double; warp shuffle + one atomic per warp
   template <typename T>
   __global__ void k_multi_dot(long long n, MultiCoef<T> mc, const T *__restrict__ w, double *__restrict__ out, DotMask mask)
@@ -382,6 +441,49 @@ namespace stfem
     STFEM_FORWARD(stream_sync_checked(ctx, "multi_axpy_norm"));
     *nrm2 = sc.h[0];
     return STFEM_OK;
+  }
+  // w += sum_k c[k] V[k] (at most MAXK vectors), then out[k] = <w, V[k]> and out[m] = ||w||^2 of the updated w.  Synchronises.
+  template <typename T>
+  inline int v_multi_axpy_dot(DotScratch &sc, BlockVec<T> &w, const std::vector<const BlockVec<T> *> &V, const double *c, double *out)
+  {
+    STFEM_FORWARD(sc.init());
+    stfem_ctx *ctx = w.ctx;
+    const int  m   = (int)V.size();
+    STFEM_REQUIRE(m <= MAXK, "multi_axpy_dot: too many vectors");
+    STFEM_CUDA_CHECK(cudaMemsetAsync(sc.d, 0, sizeof(double) * (m + 1), ctx->stream));
+    MultiCoef<T> mc;
+    mc.m = m;
+    for (int k = 0; k < m; ++k)
+      {
+        mc.v[k] = V[k]->d;
+        mc.c[k] = (T)c[k];
+      }
+    k_multi_axpy_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d, sc.mask);
+    ctx->launches++;
+    if (sc.mask.active && ctx->n_ranks > 1 && ctx->nccl_comm)
+      {
+        NcclApi *api = nccl_api();
+        STFEM_REQUIRE(api, "multi_axpy_dot: NCCL unavailable");
+        STFEM_NCCL_CHECK(api->AllReduce(sc.d, sc.d, (size_t)(m + 1), NcclApi::kDouble, NcclApi::kSum, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+      }
+    STFEM_CUDA_CHECK(cudaMemcpyAsync(sc.h, sc.d, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    STFEM_FORWARD(stream_sync_checked(ctx, "multi_axpy_dot"));
+    for (int k = 0; k <= m; ++k) out[k] = sc.h[k];
+    return STFEM_OK;
+  }
+  // out = scale * (w + sum_k c[k] V[k]) for at most MAXK vectors (the caller falls back to separate passes beyond)
+  template <typename T>
+  inline void v_multi_axpy_scale_out(BlockVec<T> &out, const BlockVec<T> &w, const std::vector<const BlockVec<T> *> &V, const double *c, double scale)
+  {
+    MultiCoef<T> mc;
+    mc.m = (int)V.size();
+    for (int k = 0; k < mc.m; ++k)
+      {
+        mc.v[k] = V[k]->d;
+        mc.c[k] = (T)c[k];
+      }
+    k_multi_axpy_scale_out<T><<<grid_for(w.ctx, w.size(), 256), 256, 0, w.ctx->stream>>>(w.size(), mc, (T)scale, w.d, out.d);
+    w.ctx->launches++;
   }
   template <typename T>
   inline void v_scale_copy(BlockVec<T> &y, T a, const BlockVec<T> &x)

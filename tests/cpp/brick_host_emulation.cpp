@@ -154,8 +154,17 @@ static int run(const Cmd &cmd, const std::vector<double> &in, std::vector<double
     }
   BrickArgs<T, N1, NB> a;
   std::memset(&a, 0, sizeof(a));
+  // mode 2 (dst = rhs + A src): rhs = the initial content of dst, dst itself starts as garbage
+  std::vector<T> rbuf;
+  const void    *rp[NB];
+  if (cmd.mode == 2)
+    {
+      rbuf.assign(dst, dst + (size_t)NB * N);
+      for (size_t i = 0; i < (size_t)NB * N; ++i) dst[i] = (T)123.5;
+    }
+  for (int b = 0; b < NB; ++b) rp[b] = cmd.mode == 2 ? rbuf.data() + (size_t)b * N : nullptr;
   brick_fill_args<T, N1, NB, CX, CY>(a, sh.S.data(), sh.D.data(), sh.wq.data(), cmd.h, cmd.n, cmd.mask, in.data(), in.data() + NB * NB, sp, dp,
-                                     cmd.zlo, cmd.zhi, cmd.mode != 0, cmd.first_plane_acc != 0, cmd.n_chunks, 296);
+                                     cmd.zlo, cmd.zhi, cmd.mode, rp, cmd.first_plane_acc != 0, cmd.n_chunks, 296);
   a.use_tma = cmd.flow_a;
   if ((size_t)C::smem_bytes(a.n_cls) > sizeof(brick_smem)) return 3;
   const long long grid = (long long)a.tiles_x * a.tiles_y * a.n_chunks;
@@ -165,7 +174,7 @@ static int run(const Cmd &cmd, const std::vector<double> &in, std::vector<double
     for (int c = 0; c < a.n_cls; ++c) std::printf(" %d", a.shift[b][c]);
   std::printf("), smem %d bytes, grid %lld, flow %s\n", C::smem_bytes(a.n_cls), grid, a.use_tma == 2 ? "A2 (barrier pipeline)" : (a.use_tma ? "A1 (one CTA barrier per plane)" : "B (plain loads)"));
   // what launch_brick does before the kernel: the node planes shared by two z chunks start from zero in mode 0
-  if (a.n_chunks > 1 && cmd.mode == 0)
+  if (a.n_chunks > 1 && cmd.mode != 1)
     {
       const long long plane = (long long)a.np[0] * a.np[1];
       for (int b = 0; b < NB; ++b)

@@ -142,6 +142,18 @@ def test_emulated_brick_kernel_accumulates_and_transposes(emulator, tmp_path):
     assert np.all(out[:, space.constrained] == dst0[:, space.constrained])
 
 
+@pytest.mark.parametrize("mask,tile,cells", [(0x3f, (3, 2), [4, 3, 4]), (0x0c, (3, 2), [5, 2, 3]), (0x00, (7, 4), [8, 5, 2])])
+def test_emulated_brick_kernel_rhs_mode(emulator, tmp_path, mask, tile, cells):
+    """mode 2: dst = rhs + A src in one pass (the residual b - A x of the multigrid smoothers, include/stmg.h / deal.II
+    PreconditionRelaxation), constrained rows = rhs; several z chunks (atomic planes) included."""
+    degree, upper = 4, [1.0, 1.0, 1.0]
+    space, A, B, src, ref = oracle(degree, "CGP", 2, cells, upper, mask)
+    rhs = np.stack([np.random.RandomState(19 + b).uniform(-1, 1, space.n_dofs) for b in range(A.shape[0])])
+    out, log = run_emulator(emulator, tmp_path, degree, -A, -B, cells, upper, mask, src, rhs, mode=2, n_chunks=2, tile=tile)
+    assert np.abs(out - (rhs - ref)).max() <= 1e-13 * max(np.abs(ref).max(), 1.0), log
+    assert np.all(out[:, space.constrained] == rhs[:, space.constrained])
+
+
 def test_emulated_brick_kernel_z_slabs(emulator, tmp_path):
     """Two launches over z slabs of cells (the pipelined host-buffer entry point): the second accumulates its first plane."""
     degree, cells, upper, mask = 4, [3, 2, 4], [1.0, 1.0, 1.0], 0x3f
