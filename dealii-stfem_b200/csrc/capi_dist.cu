@@ -1,6 +1,7 @@
 // C ABI + implementation of the multi-GPU layer (see dist.cuh).
 #include <algorithm>
 #include <cstdlib>
+#include <new>
 
 #include "dist.cuh"
 #include "op.hpp"
@@ -88,6 +89,100 @@ namespace stfem
           }
   }
 
+  // Peer-memory set-up of a plan (collective over the ranks of the communicator): allocate the receive area, hand its IPC
+  // handle + this rank's segment offsets to every neighbour (ncclSend / ncclRecv, once), map theirs.  Falls back to NCCL for
+  // ALL ranks if any rank fails (STFEM_HALO_NCCL=1 forces that).
+  struct HaloHello
+  {
+    cudaIpcMemHandle_t handle;
+    long long          start, total; // this rank's receive area: where the addressee's segment starts, elements per parity (-1: no peer access here)
+    long long          slot;         // the flag of this rank the addressee has to raise
+    char               pad[128 - sizeof(cudaIpcMemHandle_t) - 3 * sizeof(long long)];
+  };
+  static int halo_p2p_setup(stfem_ctx *ctx, HaloBuffers &hb, size_t elem)
+  {
+    HaloP2P  &pp = hb.p2p;
+    HaloPlan &pl = hb.plan;
+    NcclApi  *api = nccl_api();
+    pp.tried = true;
+    pp.ok    = false;
+    pp.elem  = elem;
+    static const bool force_nccl = std::getenv("STFEM_HALO_NCCL") != nullptr;
+    const long long   total = pl.start[pl.n_seg];
+    int               good = force_nccl ? 0 : 1;
+    cudaStreamSynchronize(ctx->stream);
+    if (good)
+      {
+        const size_t bytes = 512 + (size_t)2 * total * elem;
+        if (cudaMalloc(&pp.local, bytes < (2u << 20) ? (2u << 20) : bytes) != cudaSuccess || cudaMemset(pp.local, 0, 512) != cudaSuccess) good = 0;
+      }
+    std::vector<HaloHello> mine(pl.n_seg), theirs(pl.n_seg);
+    HaloHello             *d_buf = nullptr;
+    if (cudaMalloc(&d_buf, sizeof(HaloHello) * 2 * (pl.n_seg > 0 ? pl.n_seg : 1)) != cudaSuccess) good = 0;
+    for (int sgm = 0; sgm < pl.n_seg; ++sgm)
+      {
+        std::memset(&mine[sgm], 0, sizeof(HaloHello));
+        if (good && cudaIpcGetMemHandle(&mine[sgm].handle, pp.local) != cudaSuccess) good = 0;
+        mine[sgm].start = pl.start[sgm];
+        mine[sgm].slot  = sgm;
+        mine[sgm].total = good ? total : -1; // -1: this rank cannot do it
+      }
+    cudaGetLastError();
+    if (d_buf)
+      {
+        cudaMemcpy(d_buf, mine.data(), sizeof(HaloHello) * pl.n_seg, cudaMemcpyHostToDevice);
+        STFEM_NCCL_CHECK(api->GroupStart());
+        for (int sgm = 0; sgm < pl.n_seg; ++sgm)
+          {
+            STFEM_NCCL_CHECK(api->Send(d_buf + sgm, sizeof(HaloHello), NcclApi::kChar, pl.rank[sgm], (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+            STFEM_NCCL_CHECK(api->Recv(d_buf + pl.n_seg + sgm, sizeof(HaloHello), NcclApi::kChar, pl.rank[sgm], (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+          }
+        STFEM_NCCL_CHECK(api->GroupEnd());
+        STFEM_FORWARD(stream_sync_checked(ctx, "halo p2p set-up"));
+        cudaMemcpy(theirs.data(), d_buf + pl.n_seg, sizeof(HaloHello) * pl.n_seg, cudaMemcpyDeviceToHost);
+      }
+    pp.n_peer = 0;
+    for (int sgm = 0; sgm < pl.n_seg && good; ++sgm)
+      {
+        pp.peer_base[sgm] = nullptr;
+        if (theirs[sgm].total < 0 || cudaIpcOpenMemHandle(&pp.peer_base[sgm], theirs[sgm].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+          {
+            good = 0;
+            cudaGetLastError();
+            break;
+          }
+        pp.n_peer = sgm + 1;
+        pp.args.peer_data[sgm]  = (char *)pp.peer_base[sgm] + 512;
+        pp.args.peer_flag[sgm]  = (unsigned *)pp.peer_base[sgm] + theirs[sgm].slot;
+        pp.args.peer_start[sgm] = theirs[sgm].start;
+        pp.args.peer_total[sgm] = theirs[sgm].total;
+      }
+    if (d_buf) cudaFree(d_buf);
+    // everybody or nobody
+    double flag = good ? 1.0 : 0.0, *d_flag = nullptr;
+    STFEM_CUDA_CHECK(cudaMalloc(&d_flag, sizeof(double)));
+    STFEM_CUDA_CHECK(cudaMemcpy(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice));
+    STFEM_NCCL_CHECK(api->AllReduce(d_flag, d_flag, 1, NcclApi::kDouble, 3 /* ncclMin */, (nccl_comm_t)ctx->nccl_comm, ctx->stream));
+    STFEM_FORWARD(stream_sync_checked(ctx, "halo p2p set-up"));
+    STFEM_CUDA_CHECK(cudaMemcpy(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_flag);
+    pp.ok = flag > 0.5;
+    static bool told = false;
+    if (!told && std::getenv("STFEM_HALO_VERBOSE"))
+      {
+        told = true;
+        std::fprintf(stderr, "stfem rank %d: interface exchange over %s (%d neighbours, %lld numbers)\n", ctx->rank,
+                     pp.ok ? "peer memory (CUDA IPC over NVLink)" : "NCCL send/recv", pl.n_seg, total);
+      }
+    if (pp.ok)
+      {
+        pp.args.my_flags = (volatile unsigned *)pp.local;
+        pp.args.seq      = (unsigned *)(pp.local + 256);
+        pp.args.my_data  = pp.local + 512;
+      }
+    return STFEM_OK;
+  }
+
   // all interface partial sums in one grouped send / receive (see HaloPlan)
   template <typename T>
   static int halo_exchange_single_round(stfem_ctx *ctx, const Partition &part, HaloBuffers &hb, void *const *blocks, int nb, const int np[3], int dim,
@@ -96,9 +191,38 @@ namespace stfem
     NcclApi *api = nccl_api();
     HaloPlan &pl = hb.plan;
     if (pl.nb != nb || pl.np[0] != np[0] || pl.np[1] != (dim > 1 ? np[1] : 1) || pl.np[2] != (dim > 2 ? np[2] : 1) || pl.n_seg == 0)
-      halo_build_plan(pl, part, nb, np, dim, ctx->rank);
+      {
+        halo_build_plan(pl, part, nb, np, dim, ctx->rank);
+        hb.p2p.~HaloP2P();
+        new (&hb.p2p) HaloP2P();
+      }
     if (pl.n_seg == 0) return STFEM_OK;
     const long long total = pl.start[pl.n_seg];
+    if (!hb.p2p.tried || hb.p2p.elem != sizeof(T))
+      {
+        if (hb.p2p.tried)
+          {
+            hb.p2p.~HaloP2P();
+            new (&hb.p2p) HaloP2P();
+          }
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cap);
+        STFEM_REQUIRE(cap == cudaStreamCaptureStatusNone, "halo exchange: the first exchange of a vector shape must not happen inside a graph capture");
+        STFEM_FORWARD(halo_p2p_setup(ctx, hb, sizeof(T)));
+      }
+    if (hb.p2p.ok)
+      {
+        BlockPtrs bp;
+        for (int b = 0; b < STFEM_MAX_BLOCKS; ++b) bp.p[b] = b < nb ? blocks[b] : nullptr;
+        const int threads = 256;
+        const int grid    = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 4);
+        k_halo_pack_p2p<T><<<grid, threads, 0, stream>>>(bp, pl, hb.p2p.args);
+        k_halo_signal_p2p<<<1, 32, 0, stream>>>(pl, hb.p2p.args);
+        k_halo_unpack_sum_p2p<T><<<grid, threads, 0, stream>>>(bp, pl, hb.p2p.args);
+        ctx->launches += 3;
+        STFEM_CUDA_CHECK(cudaGetLastError());
+        return STFEM_OK;
+      }
     const size_t    need  = (size_t)total * sizeof(T);
     if (hb.bytes_all < need)
       {

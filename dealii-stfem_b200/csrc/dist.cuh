@@ -270,6 +270,91 @@ namespace stfem
       halo_unpack_element<T>(blocks, pl, gid, in);
   }
 
+  // ---- the same exchange without NCCL: every rank maps its neighbours' receive buffers (CUDA IPC, NVLink peer access) and
+  // the pack kernel STORES the partial sums straight into them; a one-warp kernel then raises a sequence flag in every
+  // neighbour's memory, and the unpack kernel waits for the flags of all neighbours before it sums.  Two receive buffers
+  // alternate (a neighbour can be at most one exchange ahead, see capi_dist.cu), the sequence number lives in device memory
+  // so that the three kernels replay inside CUDA graphs.  One exchange = 3 small kernels and ~2 NVLink latencies instead of
+  // the launch + proxy latency of a grouped ncclSend / ncclRecv.
+  struct HaloP2PArgs
+  {
+    void               *peer_data[26];  // neighbours' receive areas (both parities), mapped into this process
+    unsigned           *peer_flag[26];  // the flag in the neighbour's memory this rank raises
+    long long           peer_start[26]; // where this rank's segment starts in the neighbour's receive area (elements)
+    long long           peer_total[26]; // elements per parity in the neighbour's receive area
+    void               *my_data;        // this rank's receive area: [2][total]
+    volatile unsigned  *my_flags;       // [26] raised by the neighbours
+    unsigned           *seq;            // number of exchanges completed so far
+  };
+
+  template <typename T>
+  __global__ void k_halo_pack_p2p(BlockPtrs blocks, HaloPlan pl, HaloP2PArgs pa)
+  {
+    const long long total  = pl.start[pl.n_seg];
+    const unsigned  parity = (*pa.seq + 1u) & 1u;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      {
+        int s = 0;
+        while (s + 1 < pl.n_seg && gid >= pl.start[s + 1]) ++s;
+        const long long e   = gid - pl.start[s];
+        const long long box = (long long)pl.ext[s][0] * pl.ext[s][1] * pl.ext[s][2];
+        const int       blk = (int)(e / box);
+        long long       r   = e % box;
+        const int       u = (int)(r % pl.ext[s][0]);
+        r /= pl.ext[s][0];
+        const int       v = (int)(r % pl.ext[s][1]), w = (int)(r / pl.ext[s][1]);
+        const long long node = (long long)(pl.lo[s][0] + u) + (long long)pl.np[0] * ((pl.lo[s][1] + v) + (long long)pl.np[1] * (pl.lo[s][2] + w));
+        ((T *)pa.peer_data[s])[(long long)parity * pa.peer_total[s] + pa.peer_start[s] + e] = ((const T *)blocks.p[blk])[node];
+      }
+  }
+  // after the pack kernel (stream order): make its stores visible system-wide, raise the flags, count the exchange
+  static __global__ void k_halo_signal_p2p(HaloPlan pl, HaloP2PArgs pa)
+  {
+    __threadfence_system();
+    const unsigned next = *pa.seq + 1u;
+    __syncwarp();
+    if ((int)threadIdx.x < pl.n_seg)
+      {
+        *(volatile unsigned *)pa.peer_flag[threadIdx.x] = next;
+        __threadfence_system();
+      }
+    __syncwarp();
+    if (threadIdx.x == 0) *pa.seq = next;
+  }
+  template <typename T>
+  __global__ void k_halo_unpack_sum_p2p(BlockPtrs blocks, HaloPlan pl, HaloP2PArgs pa)
+  {
+    const unsigned expected = *pa.seq;
+    if ((int)threadIdx.x < pl.n_seg)
+      {
+        const long long t0 = clock64();
+        while ((int)(pa.my_flags[threadIdx.x] - expected) < 0)
+          if (clock64() - t0 > 20000000000ll) __trap(); // ~10 s: a neighbour never sent - fail instead of hanging the GPU
+      }
+    __syncthreads();
+    __threadfence_system();
+    const long long total = pl.start[pl.n_seg];
+    const T        *in    = (const T *)pa.my_data + (long long)(expected & 1u) * total;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x)
+      halo_unpack_element<T>(blocks, pl, gid, in);
+  }
+
+  struct HaloP2P
+  {
+    bool        tried = false, ok = false;
+    char       *local = nullptr; // [flags 256 B][seq 256 B][receive area: 2 x total elements]
+    size_t      elem = 0;
+    void       *peer_base[26];
+    int         n_peer = 0;
+    HaloP2PArgs args;
+    ~HaloP2P()
+    {
+      for (int i = 0; i < n_peer; ++i)
+        if (peer_base[i]) cudaIpcCloseMemHandle(peer_base[i]);
+      if (local) cudaFree(local);
+    }
+  };
+
   struct HaloBuffers
   {
     void  *send[2] = {nullptr, nullptr}, *recv[2] = {nullptr, nullptr};
@@ -277,6 +362,7 @@ namespace stfem
     void  *send_all = nullptr, *recv_all = nullptr; // single-round exchange
     size_t bytes_all = 0;
     HaloPlan plan;                                  // cached for (np, nb)
+    HaloP2P  p2p;                                   // peer-memory exchange of that plan
     ~HaloBuffers()
     {
       for (int s = 0; s < 2; ++s)

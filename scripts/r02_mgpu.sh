@@ -5,7 +5,7 @@ N=${1:-2}
 REPS=${2:-1}
 out=gpurun_out/r02_mgpu_n$N
 mkdir -p $out
-export NCCL_DEBUG=WARN STFEM_SYNC_TIMEOUT_S=45
+export NCCL_DEBUG=WARN STFEM_SYNC_TIMEOUT_S=45 STFEM_HALO_VERBOSE=1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/mgpu_check.py 2 > $out/mgpu_check.log 2>&1
 echo "mgpu_check rc=$?" >> $out/mgpu_check.log
 for rep in $(seq 1 $REPS); do
