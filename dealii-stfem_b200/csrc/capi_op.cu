@@ -187,6 +187,7 @@ namespace stfem
       }
     a.alpha      = (const T *)alpha;
     a.beta       = (const T *)beta;
+    STFEM_REQUIRE(m->cartesian || op->d_metric, "st_vmult (generic kernel): this operator keeps no stored metric (geometry on the fly); degree / block count not covered by the plane kernel");
     a.geom_mode  = op->d_metric ? 1 : 0;
     a.metric     = (const T *)op->d_metric;
     a.coeff_cell = (const T *)op->d_coeff;
@@ -337,8 +338,8 @@ namespace stfem
     return STFEM_OK;
   }
 
-  // general-geometry 3D path (st_vmult_plane.cuh)
-  template <int N1, typename T, int MAXT, int MINB>
+  // general-geometry 3D path (st_vmult_plane.cuh); OTF: geometry on the fly from the cell vertices
+  template <int N1, typename T, int MAXT, int MINB, bool OTF = false>
   static int launch_plane(stfem_op *op, void *const *dst, const void *const *src, int nb_src, int nb_dst, const void *alpha,
                           const void *beta)
   {
@@ -373,8 +374,15 @@ namespace stfem
     a.coeff_cell = (const T *)op->d_coeff;
     a.dirichlet  = m->dirichlet;
     a.metric     = (const T *)op->d_metric_plane;
+    a.vertices   = m->d_vertices;
+    for (int q = 0; q < N1; ++q)
+      {
+        a.xq[q] = (T)op->shape->xq[q];
+        a.wq[q] = (T)op->shape->wq[q];
+      }
+    if (OTF) STFEM_REQUIRE(m->d_vertices, "st_vmult (general, on-the-fly geometry): the mesh has no vertices");
     const int    tpc      = nb_dst * N1;
-    const size_t per_cell = (size_t)4 * nb_dst * ExchLayout<N1>::CBS * sizeof(T);
+    const size_t per_cell = ((size_t)4 * nb_dst * ExchLayout<N1>::CBS + (OTF ? 3 * N1 * N1 * 3 + 36 : 0)) * sizeof(T);
     const size_t smem_cap = (size_t)(220 * 1024) / MINB;
     STFEM_REQUIRE(tpc <= MAXT && per_cell <= smem_cap, "st_vmult (general): %d threads per cell / %zu bytes do not fit the CTA", tpc, per_cell);
     int    best = 1;
@@ -394,7 +402,7 @@ namespace stfem
       }
     a.cells_per_cta   = best;
     const size_t smem = best * per_cell;
-    auto         kern = st_vmult_plane_kernel<N1, T, MAXT, MINB>;
+    auto         kern = st_vmult_plane_kernel<N1, T, MAXT, MINB, OTF>;
     if (smem > 48 * 1024) STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (a.n_cells + best - 1) / best;
     kern<<<(unsigned)grid, best * tpc, smem, stream>>>(a);
@@ -645,6 +653,21 @@ namespace stfem
             default: break;
           }
       }
+    // general geometry, 3D: geometry on the fly from the cell vertices (kernel_variant 6, or chosen at op_create when the
+    // stored metric would not fit; see stfem_op::geom_otf) - otherwise the precomputed metric below, which is faster
+    if (DIM == 3 && op->variant != 1 && op->geom_otf && nb_dst * (op->degree + 1) <= 128)
+      switch (op->degree)
+        {
+          case 1: return launch_plane<2, T, 128, 2, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          case 2: return launch_plane<3, T, 128, 2, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          case 3:
+            if (op->variant == 11) return launch_plane<4, T, 128, 3, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            return launch_plane<4, T, 128, 2, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          case 4:
+            if (op->variant == 11) return launch_plane<5, T, 128, 2, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+            return launch_plane<5, T, 128, 3, true>(op, dst, src, nb_src, nb_dst, alpha, beta);
+          default: break;
+        }
     if (DIM == 3 && op->variant != 1 && op->d_metric_plane && nb_dst * (op->degree + 1) <= 128)
       switch (op->degree)
         {
@@ -968,11 +991,26 @@ int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *ou
       const int n1 = op->degree + 1;
       const int nq = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
       if (desc->laplace_coeff_q) op->h_coeff_q.assign(desc->laplace_coeff_q, desc->laplace_coeff_q + mesh->n_cells * nq);
-      if (f64)
+      // Geometry on the fly or stored?  Stored (8 numbers per quadrature point, streamed by the plane kernel) is faster
+      // where it fits (measured on B200, Q4, 96^3 cells: 4.2 ms against 5.9 ms in FP64); it costs (degree+1)^3 * 8 numbers per
+      // cell, i.e. 7 GB for that mesh and 95 GB for the 228^3-cell bricks of configs[4].  On the fly (cell vertices only,
+      // 192 B per cell) is taken when the stored copy would need more than a quarter of the free device memory, or on
+      // request (kernel_variant 6; 5 forces the stored metric).
+      if (mesh->dim == 3 && op->degree <= 4 && !mesh->cartesian && !desc->laplace_coeff_q && desc->kernel_variant != 5 && desc->kernel_variant != 1)
+        {
+          size_t free_b = 0, total_b = 0;
+          cudaMemGetInfo(&free_b, &total_b);
+          const size_t need = (size_t)mesh->n_cells * nq * 8 * (f64 ? 8 : 4);
+          op->geom_otf      = desc->kernel_variant == 6 || need > free_b / 4;
+        }
+      if (op->geom_otf)
+        STFEM_FORWARD(mesh_ensure_vertices(mesh));
+      else if (f64)
         STFEM_FORWARD(compute_metric<double>(op.get(), &op->d_metric));
       else
         STFEM_FORWARD(compute_metric<float>(op.get(), &op->d_metric));
-      if (mesh->dim == 3 && op->degree <= 4)
+      // the re-ordered copy the precomputed-metric plane kernel streams: only where that kernel runs
+      if (mesh->dim == 3 && op->degree <= 4 && !op->geom_otf)
         {
           const size_t nvals = (size_t)mesh->n_cells * nq * 8;
           STFEM_CUDA_CHECK(cudaMalloc(&op->d_metric_plane, nvals * (f64 ? 8 : 4) + 16));

@@ -38,6 +38,9 @@ namespace stfem
     const T  *alpha, *beta;
     const T  *coeff_cell;
     const T  *metric; // [cell][qy][qx][4][qz][2]: (Gxx Gxy) (Gxz Gyy) (Gyz Gzz) (JxW 0)
+    // on-the-fly geometry (OTF): the metric is computed in phase B from the cell's 8 vertices instead of being streamed
+    const double *vertices; // (n0+1)(n1+1)(n2+1) points, lexicographic, xyz interleaved
+    T             xq[N1], wq[N1]; // Gauss points / weights on [0,1]
   };
 
   template <typename T> struct Vec2T;
@@ -70,7 +73,12 @@ namespace stfem
       }
   }
 
-  template <int N1, typename T, int MAXT, int MINB>
+  // OTF: MappingQ1 geometry on the fly (reference include/operators.h:973-1004 builds MatrixFree with
+  // MappingQ1 and lets it store J^-1 and JxW per quadrature point; here nothing per quadrature point is stored):
+  // J(xi) = [c0(eta,zeta) | c1(xi,zeta) | c2(xi,eta)], each column a bilinear blend of the four cell edges of that
+  // direction.  Per cell the 3 (k+1)^2 column samples go to shared memory once; phase B then forms, per quadrature point,
+  // the cross products (= rows of det J * J^-1), det J and  G = J^-1 J^-T det J w = (cross_r . cross_s) w / det J.
+  template <int N1, typename T, int MAXT, int MINB, bool OTF = false>
   __global__ void __launch_bounds__(MAXT, MINB) st_vmult_plane_kernel(const __grid_constant__ PlaneArgs<T, N1> a)
   {
     using L           = ExchLayout<N1>;
@@ -81,6 +89,9 @@ namespace stfem
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T        *buf = reinterpret_cast<T *>(smem_raw);
     const int FS  = a.cells_per_cta * a.nb_dst * CBS; // field stride
+    constexpr int JT = 3 * N1 * N1 * 3;               // OTF: column samples of one cell, [column][i][j][component]
+    T        *jtab   = buf + 4 * FS;                  // [cell slot][JT]
+    T        *jedges = jtab + a.cells_per_cta * JT;   // [cell slot][12 edges][3]
 
     const int tid  = threadIdx.x;
     const int tpc  = a.nb_dst * N1;
@@ -111,6 +122,52 @@ namespace stfem
     const int       sy                = a.np[0];
     const int       sz                = a.np[0] * a.np[1];
     const long long base = (long long)(cx * K + i) + (long long)a.np[0] * ((long long)(cy * K) + (long long)a.np[1] * (cz * K));
+
+    if (OTF)
+      {
+        // edge vectors of the cell: edge e = 4 d + (b1 + 2 b2) runs in direction d between the vertices whose other two
+        // coordinates (in increasing direction order) are b1, b2
+        const int tpc_ = a.nb_dst * N1, lt = tid - slot * tpc_;
+        if (active)
+          for (int e = lt; e < 12; e += tpc_)
+            {
+              const int d = e >> 2, b1 = e & 1, b2 = (e >> 1) & 1;
+              int       v0[3];
+              v0[d]                    = 0;
+              v0[d == 0 ? 1 : 0]       = b1;
+              v0[d == 2 ? 1 : 2]       = b2;
+              const long long vid0 = (long long)(cx + v0[0]) + (long long)(a.n[0] + 1) * ((cy + v0[1]) + (long long)(a.n[1] + 1) * (cz + v0[2]));
+              const long long str  = d == 0 ? 1 : (d == 1 ? (long long)(a.n[0] + 1) : (long long)(a.n[0] + 1) * (a.n[1] + 1));
+#pragma unroll
+              for (int comp = 0; comp < 3; ++comp)
+                jedges[(slot * 12 + e) * 3 + comp] = (T)(__ldg(a.vertices + (vid0 + str) * 3 + comp) - __ldg(a.vertices + vid0 * 3 + comp));
+            }
+        __syncthreads();
+        // column d at (i, j): blend over (b1, b2) with weights L(b1, xq[i]) L(b2, xq[j]); (i, j) = the Gauss indices of the two
+        // other directions in increasing order
+        if (active)
+          for (int row = lt; row < 3 * N1; row += tpc_)
+            {
+              const int d = row / N1, i = row - d * N1;
+              const T   xi = a.xq[i];
+              T         f0[3], f1[3];
+#pragma unroll
+              for (int comp = 0; comp < 3; ++comp)
+                {
+                  const T *e = jedges + (slot * 12 + 4 * d) * 3 + comp;
+                  f0[comp]   = e[0] + xi * (e[3] - e[0]);  // b2 = 0: edges (b1 = 0, 1)
+                  f1[comp]   = e[6] + xi * (e[9] - e[6]);  // b2 = 1
+                }
+#pragma unroll
+              for (int j = 0; j < N1; ++j)
+                {
+                  const T xj = a.xq[j];
+#pragma unroll
+                  for (int comp = 0; comp < 3; ++comp) jtab[slot * JT + ((d * N1 + i) * N1 + j) * 3 + comp] = f0[comp] + xj * (f1[comp] - f0[comp]);
+                }
+            }
+        // (visible to phase B after the barrier that ends phase A)
+      }
 
     // ---------------- phase A: gather + temporal contraction
     T v[N1][N1], w[N1][N1]; // [z][y]
@@ -216,12 +273,54 @@ namespace stfem
           for (int x = 0; x < N1; ++x) in[x] = pl[3 * FS + x];
           pl_apply<T, N1, false>(a.S, in, gz);
           // quadrature-point operation
+          T c0[3];
+          if (OTF)
+            {
+#pragma unroll
+              for (int comp = 0; comp < 3; ++comp) c0[comp] = jtab[slot * JT + ((0 * N1 + qy) * N1 + qz) * 3 + comp]; // column 0 at (eta, zeta)
+            }
 #pragma unroll
           for (int qx = 0; qx < N1; ++qx)
             {
-              const V2 *mq  = met + ((size_t)(qy * N1 + qx) * 4) * N1 + qz;
-              const V2  m01 = mq[0], m23 = mq[N1], m45 = mq[2 * N1], m6 = mq[3 * N1];
-              const T   Gxx = m01.x, Gxy = m01.y, Gxz = m23.x, Gyy = m23.y, Gyz = m45.x, Gzz = m45.y, JxW = m6.x;
+              T Gxx, Gxy, Gxz, Gyy, Gyz, Gzz, JxW;
+              if (OTF)
+                {
+                  T c1[3], c2[3];
+#pragma unroll
+                  for (int comp = 0; comp < 3; ++comp)
+                    {
+                      c1[comp] = jtab[slot * JT + ((1 * N1 + qx) * N1 + qz) * 3 + comp]; // column 1 at (xi, zeta)
+                      c2[comp] = jtab[slot * JT + ((2 * N1 + qx) * N1 + qy) * 3 + comp]; // column 2 at (xi, eta)
+                    }
+                  // rows of det J * J^-1
+                  const T r0[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
+                  const T r1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
+                  const T r2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
+                  const T det   = c0[0] * r0[0] + c0[1] * r0[1] + c0[2] * r0[2];
+                  const T wgt   = a.wq[qx] * a.wq[qy] * a.wq[qz];
+                  // 1 / det by two Newton steps from the single-precision reciprocal (46 and 92 bits): a third of the
+                  // instructions of the IEEE division
+                  T rd = (T)(1.0f / (float)det);
+                  if (sizeof(T) == 8)
+                    {
+                      rd = rd * (T(2) - det * rd);
+                      rd = rd * (T(2) - det * rd);
+                    }
+                  const T sc = wgt * rd;
+                  Gxx = (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]) * sc;
+                  Gxy = (r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2]) * sc;
+                  Gxz = (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]) * sc;
+                  Gyy = (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]) * sc;
+                  Gyz = (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]) * sc;
+                  Gzz = (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]) * sc;
+                  JxW = det * wgt;
+                }
+              else
+                {
+                  const V2 *mq  = met + ((size_t)(qy * N1 + qx) * 4) * N1 + qz;
+                  const V2  m01 = mq[0], m23 = mq[N1], m45 = mq[2 * N1], m6 = mq[3 * N1];
+                  Gxx = m01.x, Gxy = m01.y, Gxz = m23.x, Gyy = m23.y, Gyz = m45.x, Gzz = m45.y, JxW = m6.x;
+                }
               const T   a0 = gx[qx], a1 = gy[qx], a2 = gz[qx];
               gx[qx] = Gxx * a0 + Gxy * a1 + Gxz * a2;
               gy[qx] = Gxy * a0 + Gyy * a1 + Gyz * a2;

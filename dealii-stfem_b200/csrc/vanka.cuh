@@ -487,7 +487,7 @@ namespace stfem
       }
     for (int q = 0; q < n1 * n1; ++q) { g.S[q] = op->shape->S[q]; g.D[q] = op->shape->D[q]; }
     for (int q = 0; q < n1; ++q) g.w[q] = op->shape->wq[q];
-    const bool general = op->d_metric != nullptr;
+    const bool general = op->d_metric != nullptr || !op->mesh->cartesian; // (operators with on-the-fly geometry keep no metric)
     const bool dedup   = !general && op->h_coeff_cell.empty();
     args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
     for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }

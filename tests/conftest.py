@@ -10,7 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_next: experimental kernels not yet verified on a GPU (STFEM_RUN_NEXT=1, never part of -m gpu)")
 
 
 @pytest.fixture(scope="session")

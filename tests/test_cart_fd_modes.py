@@ -1,6 +1,6 @@
 """kernel_variant 60 (EXPERIMENTAL fast-diagonalisation form of the Cartesian operator, csrc/st_vmult_cart_fd.cuh): the
 host-side modes (stfem_cart_fd_modes) and the algebra the kernel implements, emulated in numpy cell by cell and compared
-with the oracle's SystemMatrix::vmult.  CPU only; the CUDA kernel itself is exercised by tests/test_next_round_gpu.py."""
+with the oracle's SystemMatrix::vmult.  CPU only; the CUDA kernel itself is exercised by tests/test_cart_fd_gpu.py."""
 import ctypes as C
 
 import numpy as np

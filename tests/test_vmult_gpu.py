@@ -327,6 +327,46 @@ def test_general_geometry_plane_kernel(ctx, k, sub, ttype, r, nts, mask, number_
 
 
 @pytest.mark.parametrize("number_type", [0, 1])
+@pytest.mark.parametrize("k,sub,ttype,r,mask,coef", [(1, [3, 2, 2], "DG", 1, 0x3f, False), (2, [2, 3, 2], "CGP", 2, 0x3f, True),
+                                                     (3, [3, 3, 2], "DG", 2, 0x15, True), (4, [2, 2, 3], "CGP", 2, 0x3f, False),
+                                                     (4, [4, 3, 2], "DG", 1, 0x00, True)])
+def test_general_geometry_on_the_fly(ctx, k, sub, ttype, r, mask, coef, number_type):
+    """Perturbed MappingQ1 cells with the geometry computed on the fly from the cell vertices (kernel_variant 6, and the
+    default when the stored metric would not fit; csrc/st_vmult_plane.cuh, OTF) against the oracle (which applies the reference's stored J^-1 / JxW
+    algorithm, include/operators.h:1135-1173) and against the precomputed-metric kernel (variant 5) and the generic q-point
+    kernel (variant 1); optional per-cell coefficient (Coefficient<dim> constant per cell)."""
+    import dealii_stfem_b200 as st
+    mesh = S.Mesh(3, sub, 0, lower=[0, 0, 0], upper=[1.0, 1.2, 0.8], distort=0.2)
+    space = S.Space(mesh, k, dirichlet_faces=mask)
+    A, B, _, _ = _time_matrices(ttype, r, 1)
+    nb = A.shape[0]
+    dt = np.float64 if number_type == 0 else np.float32
+    Kop = S.MatrixFreeOperator(space, 0.0, 1.0)
+    cc = None
+    if coef:
+        cc = 0.5 + (np.arange(mesh.n_cells) % 5) * 0.4
+        Kop.laplace_coeff = np.repeat(cc[:, None], (k + 1) ** 3, axis=1)
+    Mop = S.MatrixFreeOperator(space, 1.0, 0.0)
+    sysm = S.SystemMatrix(Kop, Mop, A, B)
+    src = _rand_block(nb, space.n_dofs).astype(dt)
+    ref_dst, ref_t = sysm.vmult(src.astype(np.float64)), sysm.Tvmult(src.astype(np.float64))
+    gm = st.Mesh(ctx, mesh.n, lower=mesh.lower, upper=mesh.upper, vertices=mesh.vertices.reshape(-1, 3), dirichlet_faces=mask)
+    outs = {}
+    for variant in (6, 5, 1):
+        op = st.Operator(gm, k, A, B, number_type=number_type, laplace_coeff_cell=cc, variant=variant)
+        d_src, d_dst = op.new_vector().upload(src), op.new_vector()
+        op.vmult(d_dst, d_src)
+        outs[variant] = d_dst.download()
+        assert _rel(outs[variant].astype(np.float64), ref_dst) < TOL[number_type], "variant %d" % variant
+        assert np.all(outs[variant][:, space.constrained] == 0)
+        op.Tvmult(d_dst, d_src)
+        assert _rel(d_dst.download().astype(np.float64), ref_t) < TOL[number_type], "variant %d (T)" % variant
+        d_src.free(); d_dst.free(); op.close()
+    assert _rel(outs[6].astype(np.float64), outs[5].astype(np.float64)) < TOL[number_type]
+    gm.close()
+
+
+@pytest.mark.parametrize("number_type", [0, 1])
 @pytest.mark.parametrize("cells,variant", [([12, 2, 3], 40), ([24, 2, 2], 41), ([8, 3, 2], 42), ([12, 3, 2], 20)])
 def test_cartesian_kernel_tma_and_pipelined_variants(ctx, cells, variant, number_type):
     """Tuning variants of the Cartesian Q4 kernel (cp.async.bulk + mbarrier gather: 40-42; register-prefetch
