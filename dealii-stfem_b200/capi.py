@@ -279,7 +279,7 @@ class MgDesc(C.Structure):
                 ("poly_time_sequence", C.POINTER(C.c_int)), ("n_poly_time", C.c_int), ("smoothing_steps", C.c_int),
                 ("relaxation", C.c_double), ("smoothing_range", C.c_double), ("eig_n_iterations", C.c_int),
                 ("variable", C.c_int), ("restrict_is_transpose_prolongate", C.c_int), ("inner_preconditioner", C.c_int),
-                ("vanka_storage", C.c_int)]
+                ("coarse_grid_maxiter", C.c_int), ("coarse_grid_abstol", C.c_double), ("vanka_storage", C.c_int)]
 
 
 class Multigrid:
@@ -287,9 +287,11 @@ class Multigrid:
 
     def __init__(self, ctx, level_ops, mg_type_level, smoother_types, time_type, n_timesteps_at_once, poly_time_sequence,
                  smoothing_steps=1, relaxation=0.0, smoothing_range=1.0, eig_n_iterations=20, variable=True,
-                 restrict_is_transpose_prolongate=True, inner_preconditioner="vanka", vanka_storage="level"):
+                 restrict_is_transpose_prolongate=True, inner_preconditioner="vanka", vanka_storage="level",
+                 coarse_grid_maxiter=0, coarse_grid_abstol=1e-20):
         """inner_preconditioner: "vanka" (PreconditionVanka, the reference) or "jacobi" (point-Jacobi, diagonal inverse).
-        vanka_storage: "level" (patch inverses in the level precision) or "half" (FP16, dense patches only)."""
+        vanka_storage: "level" (patch inverses in the level precision) or "half" (FP16, dense patches only).
+        coarse_grid_maxiter > 0: GMRES on the coarsest level (coarseGridSmootherType != "Smoother", stmg.h:1240-1302)."""
         self.ctx, self.ops = ctx, list(level_ops)
         nl = len(self.ops)
         d = MgDesc()
@@ -309,6 +311,7 @@ class Multigrid:
         d.restrict_is_transpose_prolongate = int(restrict_is_transpose_prolongate)
         d.inner_preconditioner = {"vanka": 0, "jacobi": 1}[inner_preconditioner]
         d.vanka_storage = {"level": 0, "half": 1}[vanka_storage]
+        d.coarse_grid_maxiter, d.coarse_grid_abstol = int(coarse_grid_maxiter), float(coarse_grid_abstol)
         self.h = C.c_void_p()
         check(lib().stfem_mg_create(ctx.h, C.byref(d), C.byref(self.h)))
 

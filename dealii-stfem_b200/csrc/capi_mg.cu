@@ -33,6 +33,9 @@ int stfem_mg_create(stfem_ctx_t ctx, const stfem_mg_desc *desc, stfem_mg_t *out)
   o.inner_preconditioner = desc->inner_preconditioner;
   STFEM_REQUIRE(desc->vanka_storage == 0 || desc->vanka_storage == 1, "stfem_mg_create: vanka_storage must be 0 or 1");
   o.vanka_storage = desc->vanka_storage;
+  STFEM_REQUIRE(desc->coarse_grid_maxiter >= 0 && desc->coarse_grid_maxiter <= MAXK, "stfem_mg_create: coarse_grid_maxiter must be in 0..%d", MAXK);
+  o.coarse_gmres_maxiter = desc->coarse_grid_maxiter;
+  o.coarse_gmres_abstol  = desc->coarse_grid_abstol;
   STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
   auto mg         = std::make_unique<stfem_mg>();
   mg->number_type = ops[0]->number_type;

@@ -96,6 +96,8 @@ namespace stfem
     bool   variable = true, restrict_is_transpose_prolongate = true;
     int    inner_preconditioner = 0; // 0 PreconditionVanka (the reference, stmg.h:1055-1063), 1 point-Jacobi
     int    vanka_storage = 0;        // 0 level precision (the reference: float), 1 FP16 (dense patch inverses only)
+    int    coarse_gmres_maxiter = 0; // > 0: GMRES on the coarsest level instead of the smoother (stmg.h:1240-1302)
+    double coarse_gmres_abstol = 1e-20;
   };
 
   struct MGBase
@@ -295,11 +297,122 @@ namespace stfem
       return lv.st.prolongate_and_add(fine, coarse);
     }
 
+    // MGCoarseGridIterativeSolver (stmg.h:1267-1275, 1290-1298): SolverGMRES with deal.II's default LEFT preconditioning,
+    // IterationNumberControl(maxiter, abstol) (reaching maxiter is success), at most maxiter basis vectors, zero start
+    // vector, the coarse smoother as preconditioner:  min || P (b - A x) ||  over  span{P b, (P A) P b, ...}.
+    // Vectors in level precision, inner products in double (fused multi-dot), Hessenberg / Givens on the host: this part
+    // of the cycle is not captured in a CUDA graph (the cycle is split around it, see cycle()).
+    std::vector<BlockVec<T>> cg_V;
+    BlockVec<T>              cg_w;
+    int coarse_gmres(BlockVec<T> &x, const BlockVec<T> &b)
+    {
+      MGLevel<T> &lv = L[0];
+      const int   m  = opt.coarse_gmres_maxiter;
+      if ((int)cg_V.size() < m + 1)
+        {
+          cg_V.resize(m + 1);
+          for (auto &v : cg_V) STFEM_FORWARD(v.alloc(ctx, b.nb, b.n));
+          STFEM_FORWARD(cg_w.alloc(ctx, b.nb, b.n));
+        }
+      sc.set_partition(lv.op->mesh->part, lv.op->np, lv.op->mesh->dim);
+      STFEM_FORWARD(x.zero());
+      STFEM_FORWARD(smoother_vmult(0, cg_V[0], b)); // r = P b
+      double beta2 = 0;
+      STFEM_FORWARD(v_dot(sc, cg_V[0], cg_V[0], &beta2));
+      const double beta = std::sqrt(beta2);
+      if (!(beta > 0)) return STFEM_OK;
+      v_scale(cg_V[0], (T)(1.0 / beta));
+      std::vector<double> H((size_t)(m + 1) * m, 0.0), g(m + 1, 0.0), cs(m, 0.0), sn(m, 0.0), h(m + 2, 0.0);
+      auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * m + j]; };
+      g[0]   = beta;
+      int jd = 0;
+      for (int j = 0; j < m; ++j)
+        {
+          STFEM_FORWARD(A(0, lv.r, cg_V[j]));
+          STFEM_FORWARD(smoother_vmult(0, cg_w, lv.r)); // w = P A v_j   (lv.r: smoother_vmult itself works in lv.d2 / lv.t)
+          std::vector<const BlockVec<T> *> basis;
+          for (int i = 0; i <= j; ++i) basis.push_back(&cg_V[i]);
+          for (int pass = 0; pass < 2; ++pass)
+            {
+              STFEM_FORWARD(v_multi_dot(sc, cg_w, basis, h.data()));
+              std::vector<double> c(j + 1);
+              for (int i = 0; i <= j; ++i)
+                {
+                  c[i] = -h[i];
+                  Hm(i, j) += h[i];
+                }
+              v_multi_axpy(cg_w, basis, c.data());
+            }
+          double wn2 = 0;
+          STFEM_FORWARD(v_dot(sc, cg_w, cg_w, &wn2));
+          const double hn = std::sqrt(std::max(wn2, 0.0));
+          Hm(j + 1, j)    = hn;
+          for (int i = 0; i < j; ++i)
+            {
+              const double t = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);
+              Hm(i + 1, j)   = -sn[i] * Hm(i, j) + cs[i] * Hm(i + 1, j);
+              Hm(i, j)       = t;
+            }
+          const double den = std::hypot(Hm(j, j), Hm(j + 1, j));
+          if (den == 0.0) break;
+          cs[j]        = Hm(j, j) / den;
+          sn[j]        = Hm(j + 1, j) / den;
+          Hm(j, j)     = den;
+          Hm(j + 1, j) = 0.0;
+          g[j + 1]     = -sn[j] * g[j];
+          g[j]         = cs[j] * g[j];
+          jd           = j + 1;
+          if (std::fabs(g[j + 1]) < opt.coarse_gmres_abstol || hn == 0.0) break;
+          if (j + 1 < m) v_scale_copy(cg_V[j + 1], (T)(1.0 / hn), cg_w);
+        }
+      if (jd == 0) return STFEM_OK;
+      std::vector<double> y(jd);
+      for (int i = jd - 1; i >= 0; --i)
+        {
+          double s_ = g[i];
+          for (int k = i + 1; k < jd; ++k) s_ -= Hm(i, k) * y[k];
+          y[i] = s_ / Hm(i, i);
+        }
+      std::vector<const BlockVec<T> *> vs;
+      for (int i = 0; i < jd; ++i) vs.push_back(&cg_V[i]);
+      v_multi_axpy(x, vs, y.data());
+      return STFEM_OK;
+    }
+    int coarse_solve()
+    {
+      if (opt.coarse_gmres_maxiter > 0) return coarse_gmres(L[0].sol, L[0].defect);
+      return mg_apply(0, L[0].sol, L[0].defect);
+    }
+    // the two halves of the V-cycle around the coarse solve (each a fixed launch sequence): down = pre-smoothing, residual
+    // and restriction on levels top..1; up = prolongation and post-smoothing on levels 1..top
+    int v_down(int top)
+    {
+      for (int l = top; l >= 1; --l)
+        {
+          MGLevel<T> &lv = L[l];
+          STFEM_FORWARD(mg_apply(l, lv.sol, lv.defect));
+          STFEM_FORWARD(residual(l, lv.d, lv.sol, lv.defect));
+          STFEM_FORWARD(L[l - 1].defect.zero());
+          STFEM_FORWARD(restrict_level(l, L[l - 1].defect, lv.d));
+        }
+      return STFEM_OK;
+    }
+    int v_up(int top)
+    {
+      for (int l = 1; l <= top; ++l)
+        {
+          MGLevel<T> &lv = L[l];
+          STFEM_FORWARD(prolongate_level(l, lv.sol, L[l - 1].sol));
+          for (int s_ = 0; s_ < lv.steps; ++s_) STFEM_FORWARD(smooth_step(l, lv.sol, lv.defect));
+        }
+      return STFEM_OK;
+    }
+
     // Multigrid::level_v_step; defect in L[l].defect, result in L[l].sol
     int v_step(int l)
     {
       MGLevel<T> &lv = L[l];
-      if (l == 0) return mg_apply(0, lv.sol, lv.defect);
+      if (l == 0) return coarse_solve();
       STFEM_FORWARD(mg_apply(l, lv.sol, lv.defect));
       // t = defect - A sol
       {
@@ -535,12 +648,13 @@ namespace stfem
 
     // The V-cycle between the two precision copies is a fixed launch sequence without host decisions: it is
     // captured once into a CUDA graph (after one eager pass has made every lazy allocation) and replayed.
-    cudaGraphExec_t graph_exec = nullptr;
-    long long       graph_launches = 0;
+    cudaGraphExec_t graph_exec = nullptr, graph_up = nullptr;
+    long long       graph_launches = 0, graph_up_launches = 0;
     int             n_vcycles = 0;
     ~Multigrid()
     {
       if (graph_exec) cudaGraphExecDestroy(graph_exec);
+      if (graph_up) cudaGraphExecDestroy(graph_up);
     }
     int cycle()
     {
@@ -551,6 +665,38 @@ namespace stfem
       for (auto &lv : L) timing = timing || lv.op->timing;
       static const bool no_part_graph = std::getenv("STFEM_NO_PART_GRAPH") != nullptr;
       if (no_graph || (part && no_part_graph) || timing || n_vcycles++ == 0) return v_step(top);
+      if (opt.coarse_gmres_maxiter > 0)
+        {
+          // iterative coarse solver: its Hessenberg updates need the host, so the two halves of the cycle are captured
+          // separately and the coarse GMRES runs between them
+          if (top == 0) return coarse_solve();
+          auto capture = [&](cudaGraphExec_t &exec, long long &launches, bool down) -> int {
+            cudaGraph_t     graph = nullptr;
+            const long long l0    = ctx->launches;
+            STFEM_CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+            const int         rc = down ? v_down(top) : v_up(top);
+            const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc != STFEM_OK || ce != cudaSuccess)
+              {
+                if (graph) cudaGraphDestroy(graph);
+                if (rc != STFEM_OK) return rc;
+                STFEM_CUDA_CHECK(ce);
+              }
+            launches      = ctx->launches - l0;
+            ctx->launches = l0;
+            STFEM_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+            cudaGraphDestroy(graph);
+            return STFEM_OK;
+          };
+          if (!graph_exec) STFEM_FORWARD(capture(graph_exec, graph_launches, true));
+          if (!graph_up) STFEM_FORWARD(capture(graph_up, graph_up_launches, false));
+          STFEM_CUDA_CHECK(cudaGraphLaunch(graph_exec, ctx->stream));
+          ctx->launches += graph_launches;
+          STFEM_FORWARD(coarse_solve());
+          STFEM_CUDA_CHECK(cudaGraphLaunch(graph_up, ctx->stream));
+          ctx->launches += graph_up_launches;
+          return STFEM_OK;
+        }
       if (!graph_exec)
         {
           cudaGraph_t     graph = nullptr;

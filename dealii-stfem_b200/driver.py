@@ -206,7 +206,10 @@ class HeatWaveProblem:
                                  eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
                                  restrict_is_transpose_prolongate=p["restrictIsTransposeProlongate"],
                                  inner_preconditioner=p.get("innerPreconditioner", "vanka"),
-                                 vanka_storage=p.get("vankaStorage", "level")) if p.get("useMg", True) else None
+                                 vanka_storage=p.get("vankaStorage", "level"),
+                                 coarse_grid_maxiter=0 if str(p.get("coarseGridSmootherType", "Smoother")) == "Smoother"
+                                 else int(p.get("coarseGridMaxiter", 10)),
+                                 coarse_grid_abstol=float(p.get("coarseGridAbstol", 1e-20))) if p.get("useMg", True) else None
         # ---- fine operators (tp_01.cc:121-168)
         fmesh = self.meshes[refinement]
         self.fmesh = fmesh

@@ -190,6 +190,11 @@ typedef struct stfem_mg_desc {
   int inner_preconditioner;      /* 0 = PreconditionVanka (the reference, stmg.h:1055-1063); 1 = point-Jacobi: the inverse of
                                     SystemMatrix::get_matrix_diagonal (operators.h:613-625) inside Relaxation / Chebyshev.
                                     Not a reference configuration: the cheap smoother BASELINE.json's north_star names. */
+  int coarse_grid_maxiter;       /* 0 = coarsest level solved by the smoother (MGCoarseGridApplySmoother, coarseGridSmootherType
+                                    "Smoother", the reference's default); > 0 = MGCoarseGridIterativeSolver: left-preconditioned
+                                    SolverGMRES with IterationNumberControl(coarse_grid_maxiter, coarse_grid_abstol) and the
+                                    coarse smoother as preconditioner (stmg.h:1240-1302; parameters.h:25-26: 10, 1e-20) */
+  double coarse_grid_abstol;
   int vanka_storage;             /* 0 = patch inverses in the level precision (the reference: float, stmg.h:901);
                                     1 = FP16, normalised per patch, FP32 accumulation: half the HBM traffic of the dense
                                     PreconditionVanka::vmult (stmg.h:832-872).  Levels in Kronecker form are unaffected. */

@@ -221,6 +221,9 @@ namespace stfem
     double       relaxation                       = 0.0;
     bool         restrict_is_transpose_prolongate = true;
     bool         variable                         = true;
+    std::string  coarse_grid_smoother_type        = "Smoother"; // anything else: GMRES on the coarsest level (stmg.h:1240-1302)
+    unsigned int coarse_grid_maxiter              = 10;
+    double       coarse_grid_abstol               = 1e-20;
     int          inner_preconditioner             = 0; // 0 PreconditionVanka (reference), 1 point-Jacobi (not a reference option)
     int          vanka_storage                    = 0; // 0 level precision (reference), 1 FP16 patch inverses
   };
@@ -253,6 +256,8 @@ namespace stfem
       d.restrict_is_transpose_prolongate = data.restrict_is_transpose_prolongate;
       d.inner_preconditioner             = data.inner_preconditioner;
       d.vanka_storage                    = data.vanka_storage;
+      d.coarse_grid_maxiter              = data.coarse_grid_smoother_type == "Smoother" ? 0 : (int)data.coarse_grid_maxiter;
+      d.coarse_grid_abstol               = data.coarse_grid_abstol;
       check(stfem_mg_create(ctx.handle(), &d, &h_));
     }
     ~GMG() { stfem_mg_destroy(h_); }

@@ -296,7 +296,7 @@ class GMG:
     def __init__(self, ttype, level_ops, spaces, mg_type_level, poly_time_sequence, n_timesteps_at_once,
                  precondition_types, dtype, smoothing_steps=1, relaxation=0.0, smoothing_range=1.0,
                  eig_n_iterations=20, variable=True, restrict_is_transpose_prolongate=True,
-                 vanka=None):
+                 vanka=None, coarse_gmres=None):
         self.ops, self.dtype = level_ops, dtype
         nl = len(level_ops)
         self.nl = nl
@@ -324,6 +324,10 @@ class GMG:
                 self.smoothers.append(Chebyshev(level_ops[l], self.vanka[l], smoothing_steps, smoothing_range,
                                                 eig_n_iterations))
         self.steps = [(1 << (nl - 1 - l)) if variable else 1 for l in range(nl)]
+        # coarseGridSmootherType != "Smoother" (stmg.h:1240-1302): MGCoarseGridIterativeSolver with SolverGMRES (left
+        # preconditioning) + IterationNumberControl(coarse_grid_maxiter, coarse_grid_abstol) and the coarse smoother as
+        # preconditioner; coarse_gmres = (maxiter, abstol)
+        self.coarse_gmres = coarse_gmres
 
     def _apply(self, l, rhs):
         """MGSmootherPrecondition::apply (zero initial guess)."""
@@ -342,6 +346,9 @@ class GMG:
     def _v(self, l, defect):
         """Multigrid::level_v_step (A.6)."""
         if l == 0:
+            if self.coarse_gmres is not None:
+                return coarse_gmres(self.ops[0].vmult, self.smoothers[0].vmult, defect, self.coarse_gmres[0], self.coarse_gmres[1],
+                                    self.dtype)
             return self._apply(0, defect)
         A = self.ops[l]
         sol = self._apply(l, defect)
@@ -358,6 +365,55 @@ class GMG:
         """GMG::vmult (stmg.h:1331-1344): double -> level precision -> double."""
         out = self._v(self.nl - 1, src.astype(self.dtype))
         return out.astype(np.float64)
+
+
+# ----------------------------------------------------------------------------- coarse-grid GMRES
+def coarse_gmres(A, P, b, maxiter, abstol, dtype):
+    """SolverGMRES (deal.II default: LEFT preconditioning) with IterationNumberControl(maxiter, abstol) and
+    max_n_tmp_vectors = maxiter, zero start vector: min || P (b - A x) || over the Krylov space of P A
+    (stmg.h:1240-1250, 1267-1275).  Vectors in `dtype`, inner products accumulated in double."""
+    x = np.zeros_like(b)
+    r = P(b)
+    beta = float(np.sqrt(np.vdot(r.astype(np.float64), r.astype(np.float64))))
+    if beta == 0.0:
+        return x
+    V = [(r / dtype(beta)).astype(dtype)]
+    H = np.zeros((maxiter + 1, maxiter))
+    g = np.zeros(maxiter + 1)
+    g[0] = beta
+    cs, sn = np.zeros(maxiter), np.zeros(maxiter)
+    jd = 0
+    for j in range(maxiter):
+        w = P(A(V[j])).astype(dtype)
+        for _ in range(2):
+            h = np.array([np.vdot(v.astype(np.float64), w.astype(np.float64)) for v in V])
+            for hv, v in zip(h, V):
+                w = (w - dtype(hv) * v).astype(dtype)
+            H[:j + 1, j] += h
+        hn = float(np.sqrt(np.vdot(w.astype(np.float64), w.astype(np.float64))))
+        H[j + 1, j] = hn
+        for i in range(j):
+            t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+            H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+            H[i, j] = t
+        den = np.hypot(H[j, j], H[j + 1, j])
+        if den == 0.0:
+            break
+        cs[j], sn[j] = H[j, j] / den, H[j + 1, j] / den
+        H[j, j] = den
+        H[j + 1, j] = 0.0
+        g[j + 1] = -sn[j] * g[j]
+        g[j] = cs[j] * g[j]
+        jd = j + 1
+        if abs(g[j + 1]) < abstol or hn == 0.0:
+            break
+        V.append((w / dtype(hn)).astype(dtype))
+    if jd == 0:
+        return x
+    y = np.linalg.solve(np.triu(H[:jd, :jd]), g[:jd])
+    for yj, v in zip(y, V):
+        x = (x + dtype(yj) * v).astype(dtype)
+    return x
 
 
 # ----------------------------------------------------------------------------- FGMRES

@@ -101,6 +101,46 @@ def test_multigrid_pieces_match_oracle(ctx, name, dim, ref, deg_idx, over):
         m.close()
 
 
+@pytest.mark.parametrize("name,dim,ref,over", [("tf03", 2, 3, {}), ("tf04", 2, 2, {"smoother": "chebyshev", "smoothingSteps": 2}),
+                                               ("tf03", 3, 1, {"mgTimeBeforeSpace": True})])
+def test_coarse_grid_gmres_matches_oracle(ctx, name, dim, ref, over):
+    """coarseGridSmootherType != "Smoother" (include/stmg.h:1240-1302): left-preconditioned GMRES(10) with
+    IterationNumberControl(10, 1e-20) on the coarsest level instead of the smoother.  The V-cycle (eager on the first call,
+    then replayed as two CUDA graphs around the coarse solve) must reproduce the oracle's."""
+    import dealii_stfem_b200 as st
+    p = _params(name, dim, **over)
+    k = p["feDegree"]
+    lv = tp_01.build_levels(p, dim, ref, k, _tau(p, ref), np.float32)
+    omg = stmg.GMG(p["timeType"], lv["ops"], lv["spaces"], lv["mg_type_level"], lv["poly_time"], p["nTimestepsAtOnce"],
+                   lv["ptypes"], np.float32, smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"],
+                   smoothing_range=p["smoothingRange"], eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
+                   coarse_gmres=(10, 1e-20))
+    omg_s = stmg.GMG(p["timeType"], lv["ops"], lv["spaces"], lv["mg_type_level"], lv["poly_time"], p["nTimestepsAtOnce"],
+                     lv["ptypes"], np.float32, smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"],
+                     smoothing_range=p["smoothingRange"], eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
+                     vanka=omg.vanka)
+    meshes, ops = gpu_levels(st, ctx, lv, st.F32)
+    mg = st.Multigrid(ctx, ops, lv["mg_type_level"], lv["ptypes"], p["timeType"], p["nTimestepsAtOnce"], lv["poly_time"],
+                      smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
+                      eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
+                      restrict_is_transpose_prolongate=p["restrictIsTransposeProlongate"], coarse_grid_maxiter=10, coarse_grid_abstol=1e-20)
+    top = lv["ops"][-1]
+    db = st.DeviceBlockVector(ctx, top.nb, top.n, st.F64)
+    dz = st.DeviceBlockVector(ctx, top.nb, top.n, st.F64)
+    for seed in (77, 78, 79):                      # call 1 eager, call 2 captures the two graphs, call 3 replays them
+        b = rand_block(top.nb, top.n, seed, lv["spaces"][-1].constrained)
+        mg.vmult(dz, db.upload(b))
+        z_o = omg.vmult(b)
+        assert rel(dz.download(), z_o) < 2e-3
+        # ... and it is a different preconditioner than the one with the smoother as coarse solver
+        assert rel(z_o, omg_s.vmult(b)) > 1e-6
+    db.free(); dz.free(); mg.close()
+    for o in ops:
+        o.close()
+    for m in meshes:
+        m.close()
+
+
 @pytest.mark.parametrize("name,dim,ref,over", [("tf03", 2, 3, {}), ("tf03", 2, 3, {"mgTimeBeforeSpace": True}),
                                                ("tf04", 2, 3, {}), ("tf01", 2, 3, {}), ("tf07", 2, 3, {}),
                                                ("tf03", 2, 2, {"distortGrid": 0.1, "smoother": "chebyshev", "smoothingSteps": 2}),
