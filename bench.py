@@ -409,7 +409,7 @@ def main():
     grid, coords = [1, 1, 1], [0, 0, 0]
     if world > 1:
         # box partition 2x1x1, 2x2x1, 2x2x2: every rank owns one n^3 brick (unit cube) of the global mesh; the operator
-        # sums interface DoFs over NVLink (ncclSend/ncclRecv) inside every vmult
+        # sums interface DoFs over NVLink (peer-memory stores, NCCL fallback) inside every vmult
         grid = st.dist.proc_grid_for(world, 3)
         coords = st.dist.coords_of(rank, grid)
 
@@ -499,7 +499,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "run": {"kernel_variant": args.variant, "checksum": checksum,
-                    "halo": "interface DoFs summed over NVLink (ncclSend/ncclRecv) inside every step" if world > 1 else "none"},
+                    "halo": "interface DoFs summed over NVLink inside every step (stores into peer memory over CUDA IPC + sequence flags; ncclSend/ncclRecv where IPC is unavailable)" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": dofs_rank * BYTES_PER_DOF,

@@ -5,7 +5,8 @@ namespace stfem
 {
   // BRICK kernel (st_vmult_brick.cuh): 3D Cartesian meshes without a coefficient table, square time matrices that are one
   // of the operator's own (so that their host copies can be passed by value), degree 2-4, <= 3 blocks.
-  // kernel_variant: 0 default (TMA loads; meshes below 512 cells keep the per-cell kernel), 70 plain loads, 71 one CTA per SM,
+  // kernel_variant: 0 default (TMA loads; meshes below 512 cells keep the per-cell kernel), 70 plain loads, 77 split warps,
+  // 79 barrier pipeline, 90 = 0 without the per-SM alternation of the warp roles,
   // 72 = 0 without the size threshold, 80.. forced number of z chunks (variant - 79), 3 = the
   // per-cell kernel of round 1 (st_vmult_cart.cuh) instead.
   bool brick_eligible(const stfem_op *op, int nb_src, int nb_dst, const void *alpha, const void *beta)
@@ -13,7 +14,7 @@ namespace stfem
     static const bool off = std::getenv("STFEM_NO_BRICK") != nullptr;
     const stfem_mesh *m = op->mesh;
     if (off || m->dim != 3 || !m->cartesian || op->d_metric || op->d_coeff) return false;
-    if (!(op->variant == 0 || (op->variant >= 70 && op->variant < 90))) return false;
+    if (!(op->variant == 0 || (op->variant >= 70 && op->variant <= 90))) return false;
     if (nb_src != nb_dst || nb_dst < 1 || nb_dst > 3 || op->degree < 2 || op->degree > 4) return false;
     if (!brick_host_matrix(op, alpha) || !brick_host_matrix(op, beta)) return false;
     if (op->n_xbox > 0) return false;
@@ -37,14 +38,6 @@ namespace stfem
     // tuning variants of the headline instance (Q4, two blocks): other tile heights / CTAs per SM
     if (op->variant == 77 && op->degree == 4 && nb == 2) // X and Y+Z phases on separate warps, one CTA per SM
       return launch_brick<5, 2, T, 7, 4, 1, true>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 78 && op->degree == 4 && nb == 2)
-      return launch_brick<5, 2, T, 7, 5, 1, true>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 73 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 2, 4>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 74 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 2>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 75 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 6, 1>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 76 && op->degree == 4 && nb == 2) return launch_brick<5, 2, T, 7, 3, 3>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
-    if (op->variant == 71 && op->degree == 4 && nb == 2) // tuning: one CTA per SM with the full register budget
-      return launch_brick<5, 2, T, BrickTile<5>::CX, BrickTile<5>::CY, 1>(op, dst, src, hA, hB, mode, rhs, zlo, zhi, first_plane_acc, tma, n_chunks);
 #define STFEM_BRICK_CASE(N1_, NB_, MINB_)                                                                                             \
   if (op->degree + 1 == N1_ && nb == NB_)                                                                                             \
     {                                                                                                                                 \

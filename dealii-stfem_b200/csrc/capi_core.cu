@@ -97,6 +97,7 @@ int stfem_ctx_destroy(stfem_ctx_t ctx)
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->d_sm_counter) cudaFree(ctx->d_sm_counter);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return STFEM_OK;

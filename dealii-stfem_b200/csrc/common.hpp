@@ -64,6 +64,7 @@ struct stfem_ctx
   std::vector<cudaEvent_t> ev_pool;
   void        *nccl_comm = nullptr;          // ncclComm_t when the context is part of a multi-GPU run
   int          rank = 0, n_ranks = 1;
+  unsigned    *d_sm_counter = nullptr;       // one counter per SM: the brick kernel alternates its warp roles per SM with it
 };
 
 namespace stfem

@@ -106,6 +106,7 @@ namespace stfem
     int mode;            // 0: dst = A src, 1: dst += A src, 2: dst = rhs + A src
     int first_plane_acc; // plane K*zlo is accumulated even in mode 0 (z-slab pipeline: it holds the partial sum of the slab below)
     int use_tma;
+    unsigned *sm_counter; // one counter per SM (see xrot in the kernel); null: no rotation of the X warps
     unsigned dirichlet;
     unsigned iface;      // bit 2d+s: face s of direction d is shared with another rank (mode 2: rhs enters with weight 1/multiplicity)
     const T *src[NB];
@@ -417,7 +418,9 @@ namespace stfem
   }
 #endif
 
-  template <typename T, int N1, int NB, int CX, int CY, int MINB, bool SPLIT = false>
+  // GEN = false: the plain product only (mode 0, no accumulated first plane, no interface weights) - the store phase then
+  // has nothing to read and no mode to test (the headline instance)
+  template <typename T, int N1, int NB, int CX, int CY, int MINB, bool SPLIT = false, bool GEN = true>
   __global__ void __launch_bounds__((BrickCfg<T, N1, NB, CX, CY, SPLIT>::NTHREADS), MINB)
     st_vmult_brick_kernel(const __grid_constant__ BrickArgs<T, N1, NB> a)
   {
@@ -435,6 +438,25 @@ namespace stfem
     T                  *pq    = tiles + S * stage_elems;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // The X phase occupies XW of the NWARPS warps, i.e. (warps go round-robin to the four schedulers of an SM) it loads the
+    // schedulers unevenly.  Two CTAs share an SM: every other CTA an SM receives (counted per SM) starts its X warps two
+    // schedulers further on, so that the pair loads all four evenly.
+    int xrot = 0;
+#ifndef STFEM_HOST_EMULATION
+    if (!SPLIT && a.sm_counter)
+      {
+        __shared__ int s_xrot;
+        if (tid == 0)
+          {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_xrot = (atomicAdd(a.sm_counter + smid, 1u) & 1u) ? 2 % C::NWARPS : 0;
+          }
+        __syncthreads();
+        xrot = s_xrot;
+      }
+#endif
+    const int xwarp = SPLIT ? warp : (warp - xrot + C::NWARPS) % C::NWARPS; // index of this warp among the X warps
 
     // ---- this CTA's tile and z chunk
     int       bid   = blockIdx.x;
@@ -532,8 +554,8 @@ namespace stfem
     const bool x_lane_ok = lane < RPW * CXL;
     const int  xr  = x_lane_ok ? lane % RPW : 0;
     const int  xci = brick_cell_of<CXL, RPW>(x_lane_ok ? lane / RPW : 0); // 0 = halo cell on the low side
-    const int  xyl = warp * RPW + xr;                                     // tile row
-    const bool x_row_in = warp < C::XW && x_lane_ok && xyl < WY;
+    const int  xyl = xwarp * RPW + xr;                                    // tile row
+    const bool x_row_in = xwarp < C::XW && x_lane_ok && xyl < WY;
     bool       x_valid0;
     bool       x_zero_u0, x_zero_uK;
     {
@@ -582,7 +604,7 @@ namespace stfem
           if (x_con || ((dm & 4u) && yg == 0) || ((dm & 8u) && yg == np1 - 1)) con_mask |= 1u << nn;
         }
       // mode 2 on a partitioned mesh: every rank sharing a node adds rhs / multiplicity, the exchange then sums to rhs + A src
-      if (a.iface)
+      if (GEN && a.iface)
         {
           if (((a.iface & 1u) && xg == 0) || ((a.iface & 2u) && xg == np0 - 1)) wx = T(0.5);
 #pragma unroll
@@ -612,10 +634,10 @@ namespace stfem
     // latency NP * K times per layer.
     auto store_planes = [&](int zb, auto nptag, bool first_shared) {
       constexpr int NP = decltype(nptag)::value;
-      const int     mode = a.mode;
+      const int     mode = GEN ? a.mode : 0;
       T            *p0   = dst_base + plane_stride * zb;
       const T      *r0p  = (mode == 2 ? a.rhs[jz] : a.dst[jz]) + (dst_base - a.dst[jz]) + plane_stride * zb;
-      const bool    acc0 = a.first_plane_acc && zb == K * a.zlo; // z-slab launches: plane K*zlo holds the partial sum of the slab below
+      const bool    acc0 = GEN && a.first_plane_acc && zb == K * a.zlo; // z-slab launches: plane K*zlo holds the partial sum of the slab below
       if (mode == 0 && !acc0)
         {
           // plain assignment: nothing to read
@@ -650,6 +672,7 @@ namespace stfem
             }
           return;
         }
+      if (!GEN) return;
       T old[NP][K + 1];
       if (mode != 0 || acc0)
         {
@@ -937,7 +960,7 @@ namespace stfem
         for (int q = 0; q < nq; ++q)
           {
             brick_sync::mbar_wait(&bar_tfull[q % S], (unsigned)((q / S) & 1));
-            if (warp < C::XW) x_phase(q);
+            if (xwarp < C::XW) x_phase(q);
             __syncthreads();
             if (tid == C::NTHREADS - 32 && q + S < nq) issue_tma(q + S);
             if (yz_warp) yz_phase(q, []() {});
@@ -947,7 +970,7 @@ namespace stfem
       {
         // no CTA-wide barrier: X runs one plane ahead of Y+Z; the full / empty barriers of the three P/Q buffers and of
         // the source stages leave a plane of slack on either side, so a warp only waits when it is a whole plane ahead
-        const bool x_warp = warp < C::XW, y_warp = y_role, issuer = tid == C::NTHREADS - 32;
+        const bool x_warp = xwarp < C::XW, y_warp = y_role, issuer = tid == C::NTHREADS - 32;
         auto       x_step = [&](int q) {
           brick_sync::mbar_wait(&bar_tfull[q % S], (unsigned)((q / S) & 1));
           if (q >= NPQ) brick_sync::mbar_wait(&bar_pempty[q % NPQ], (unsigned)((q / NPQ - 1) & 1));
@@ -980,7 +1003,7 @@ namespace stfem
           {
             load_plain(q);
             __syncthreads();
-            if (warp < C::XW) x_phase(q);
+            if (xwarp < C::XW) x_phase(q);
             __syncthreads();
             if (yz_warp) yz_phase(q, []() {});
           }

@@ -76,6 +76,18 @@ namespace stfem
                                        mode, rhs, first_plane_acc, n_chunks, (long long)m->ctx->sm_count * MINB, iface);
     STFEM_REQUIRE(a.n_cls <= C::MAXCLS, "st_vmult (brick): %d row classes", a.n_cls);
     a.use_tma = use_tma;
+    // per-SM CTA counter behind the alternating warp roles (kernel_variant 90 switches the alternation off)
+    a.sm_counter = nullptr;
+    if (!SPLIT && op->variant != 90 && C::NWARPS > C::XW && C::NWARPS % 4 == 0)
+      {
+        stfem_ctx *ctx = m->ctx;
+        if (!ctx->d_sm_counter)
+          {
+            STFEM_CUDA_CHECK(cudaMalloc(&ctx->d_sm_counter, 1024 * sizeof(unsigned)));
+            STFEM_CUDA_CHECK(cudaMemsetAsync(ctx->d_sm_counter, 0, 1024 * sizeof(unsigned), ctx->stream));
+          }
+        a.sm_counter = ctx->d_sm_counter;
+      }
     for (int b = 0; b < NB && a.use_tma; ++b)
       for (int c = 0; c < a.n_cls; ++c)
         if (!brick_encode<T>(a.desc[b][c], &a.maps[b][c]))
@@ -97,7 +109,8 @@ namespace stfem
         m->ctx->launches++;
       }
     const size_t smem = (size_t)C::smem_bytes(a.n_cls);
-    auto         kern = st_vmult_brick_kernel<T, N1, NB, CX, CY, MINB, SPLIT>;
+    const bool   gen  = mode != 0 || first_plane_acc; // plain product: the instance without the read / mode logic in the store phase
+    auto         kern = gen ? st_vmult_brick_kernel<T, N1, NB, CX, CY, MINB, SPLIT, true> : st_vmult_brick_kernel<T, N1, NB, CX, CY, MINB, SPLIT, false>;
     STFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid   = (long long)a.tiles_x * a.tiles_y * a.n_chunks;
     STFEM_REQUIRE(grid < (1ll << 31), "st_vmult (brick): grid too large");

@@ -251,7 +251,9 @@ namespace stfem
     // ---------------- phase B: x lines (z = i, y = m): to the Gauss points in x, metric, back
     {
       const V2 *met = reinterpret_cast<const V2 *>(a.metric) + (size_t)cell * (N1 * N1 * 4 * N1);
-#pragma unroll
+      // a real loop over the N1 lines of a thread: the unrolled body (N1 times ~600 instructions) overflowed the instruction
+      // cache (ncu: one "no instruction" stall per issued instruction with the 3 warps per scheduler this kernel runs with)
+#pragma unroll 1
       for (int m = 0; m < N1; ++m)
         {
           const int line = L::blocked ? N1 * i + m : i + N1 * m; // (z, y) = (i, m) for blocked, (m, i) else

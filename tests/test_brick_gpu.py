@@ -35,18 +35,18 @@ CASES = [
 
 
 @pytest.mark.parametrize("number_type", [0, 1])
-@pytest.mark.parametrize("variant", [72, 70, 82, 71])
+@pytest.mark.parametrize("variant", [72, 70, 82, 77, 90])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "k%d_%s_%s%d_m%x" % (c[0], "x".join(map(str, c[1])), c[3], c[4], c[6]))
 def test_brick_kernel_matches_oracle(ctx, case, variant, number_type):
-    """72: TMA loads; 70: plain loads; 82: three z chunks (warm-up layers); 71: one CTA per SM (Q4, two blocks only)."""
+    """72: TMA loads; 70: plain loads; 82: three z chunks (warm-up layers); 77: X and Y+Z phases on separate warps (Q4, two blocks only); 90: 72 without the per-SM alternation of the warp roles."""
     import dealii_stfem_b200 as st
     k, cells, upper, ttype, r, nts, mask = case
     mesh = S.Mesh(3, cells, 0, lower=[0, 0, 0], upper=upper)
     space = S.Space(mesh, k, dirichlet_faces=mask)
     A, B = ft.get_fe_time_weights(ttype, r, 0.05, nts)[:2]
     nb = A.shape[0]
-    if variant == 71 and not (k == 4 and nb == 2):
-        pytest.skip("variant 71 is instantiated for Q4 with two blocks only")
+    if variant == 77 and not (k == 4 and nb == 2):
+        pytest.skip("variant 77 is instantiated for Q4 with two blocks only")
     dt = np.float64 if number_type == 0 else np.float32
     sysm = S.SystemMatrix(S.MatrixFreeOperator(space, 0.0, 1.0), S.MatrixFreeOperator(space, 1.0, 0.0), A, B)
     src = _rand(nb, space.n_dofs).astype(dt)

@@ -132,8 +132,10 @@ def test_coarse_grid_gmres_matches_oracle(ctx, name, dim, ref, over):
         mg.vmult(dz, db.upload(b))
         z_o = omg.vmult(b)
         assert rel(dz.download(), z_o) < 2e-3
-        # ... and it is a different preconditioner than the one with the smoother as coarse solver
-        assert rel(z_o, omg_s.vmult(b)) > 1e-6
+        # ... and, where the coarsest level has more than one free DoF (in 2D it is a single cell with every boundary node
+        # constrained), it is a different preconditioner than the one with the smoother as coarse solver
+        if int((~lv["spaces"][0].constrained).sum()) > 1:
+            assert rel(z_o, omg_s.vmult(b)) > 1e-6
     db.free(); dz.free(); mg.close()
     for o in ops:
         o.close()
