@@ -6,7 +6,7 @@ namespace stfem
   // BRICK kernel (st_vmult_brick.cuh): 3D Cartesian meshes without a coefficient table, square time matrices that are one
   // of the operator's own (so that their host copies can be passed by value), degree 2-4, <= 3 blocks.
   // kernel_variant: 0 default (TMA loads; meshes below 512 cells keep the per-cell kernel), 70 plain loads, 77 split warps,
-  // 79 barrier pipeline, 90 = 0 without the per-SM alternation of the warp roles,
+  // 79 barrier pipeline, 90 = 72 with the per-SM alternation of the X warps (measured slower),
   // 72 = 0 without the size threshold, 80.. forced number of z chunks (variant - 79), 3 = the
   // per-cell kernel of round 1 (st_vmult_cart.cuh) instead.
   bool brick_eligible(const stfem_op *op, int nb_src, int nb_dst, const void *alpha, const void *beta)

@@ -208,7 +208,14 @@ namespace stfem
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream, &cap);
         STFEM_REQUIRE(cap == cudaStreamCaptureStatusNone, "halo exchange: the first exchange of a vector shape must not happen inside a graph capture");
-        STFEM_FORWARD(halo_p2p_setup(ctx, hb, sizeof(T)));
+        if (hb.no_p2p)
+          {
+            hb.p2p.tried = true;
+            hb.p2p.ok    = false;
+            hb.p2p.elem  = sizeof(T);
+          }
+        else
+          STFEM_FORWARD(halo_p2p_setup(ctx, hb, sizeof(T)));
       }
     if (hb.p2p.ok)
       {
@@ -480,6 +487,52 @@ int stfem_mesh_set_partition(stfem_mesh_t mesh, const int *proc_grid, const int 
         p.neighbor[d][s] = (c[d] < 0 || c[d] >= p.grid[d]) ? -1 : p.rank_of(c);
       }
   p.active = total > 1;
+  return STFEM_OK;
+}
+
+// Ghost layer of a partitioned mesh: one layer of cells across every face shared with another rank (deal.II's ghost cells).
+// Only the dense cell-patch smoother needs it: its patch matrices take the contributions of the neighbouring cells on the
+// shared DoFs (compute_block_matrix.h:50-139), and the neighbours of a cell at a rank interface live on the other rank.
+namespace
+{
+  void ghost_extent(const stfem_mesh *m, int *ne, long long *n_cells, long long *n_vertices)
+  {
+    *n_cells = *n_vertices = 1;
+    for (int d = 0; d < 3; ++d)
+      {
+        ne[d] = m->n[d];
+        if (d < m->dim)
+          {
+            ne[d] += (m->part.neighbor[d][0] >= 0 ? 1 : 0) + (m->part.neighbor[d][1] >= 0 ? 1 : 0);
+            *n_cells *= ne[d];
+            *n_vertices *= ne[d] + 1;
+          }
+      }
+  }
+} // namespace
+
+int stfem_mesh_set_ghost_vertices(stfem_mesh_t mesh, const double *vertices_ext)
+{
+  STFEM_REQUIRE(mesh && vertices_ext, "stfem_mesh_set_ghost_vertices: null argument");
+  STFEM_REQUIRE(mesh->part.active, "stfem_mesh_set_ghost_vertices: the mesh has no partition (stfem_mesh_set_partition first)");
+  int       ne[3];
+  long long nc, nv;
+  ghost_extent(mesh, ne, &nc, &nv);
+  mesh->h_vertices_ghost.assign(vertices_ext, vertices_ext + nv * mesh->dim);
+  return STFEM_OK;
+}
+
+int stfem_op_set_ghost_coefficients(stfem_op_t op, const double *coeff_cell_ext, const double *coeff_q_ext)
+{
+  STFEM_REQUIRE(op, "stfem_op_set_ghost_coefficients: null operator");
+  stfem_mesh *mesh = op->mesh;
+  STFEM_REQUIRE(mesh->part.active, "stfem_op_set_ghost_coefficients: the mesh has no partition");
+  int       ne[3];
+  long long nc, nv;
+  ghost_extent(mesh, ne, &nc, &nv);
+  const int n1 = op->degree + 1, nq = mesh->dim == 3 ? n1 * n1 * n1 : n1 * n1;
+  if (coeff_cell_ext) op->h_coeff_cell_ghost.assign(coeff_cell_ext, coeff_cell_ext + nc);
+  if (coeff_q_ext) op->h_coeff_q_ghost.assign(coeff_q_ext, coeff_q_ext + nc * nq);
   return STFEM_OK;
 }
 

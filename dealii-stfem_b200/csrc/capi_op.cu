@@ -876,7 +876,6 @@ namespace stfem
   {
     stfem_mesh *m   = op->mesh;
     stfem_ctx  *ctx = m->ctx;
-    STFEM_REQUIRE(!m->part.active, "diagonal: partitioned meshes are not supported yet");
     STFEM_REQUIRE(op->degree >= 1 && op->degree <= 6, "diagonal: degree out of range");
     AsmGeom g;
     fill_asm_geom(g, m, op->degree, op->degree + 1);
@@ -901,6 +900,16 @@ namespace stfem
     k_diagonal<<<grid, 128, 0, ctx->stream>>>(g, d_cc, d_cq, dK, dM);
     ctx->launches++;
     STFEM_CUDA_CHECK(cudaGetLastError());
+    if (m->part.active)
+      {
+        // partitioned mesh: the cells of the neighbouring ranks contribute to the interface rows (compress(add) of the
+        // reference's diagonal vector, operators.h:1092-1110); a one-off exchange with its own buffers
+        HaloBuffers hb;
+        hb.no_p2p         = true;
+        void *blocks[2]   = {dK, dM};
+        STFEM_FORWARD(halo_compress_add<double>(ctx, m->part, hb, blocks, 2, op->np, m->dim, ctx->stream));
+        STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      }
     STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (d_cc) cudaFree(d_cc);
     if (d_cq) cudaFree(d_cq);

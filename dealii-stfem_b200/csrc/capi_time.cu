@@ -463,7 +463,11 @@ int stfem_point_evaluate(stfem_mesh_t mesh, int degree, int n_points, const doub
   STFEM_REQUIRE(mesh && points && x && out, "stfem_point_evaluate: null argument");
   STFEM_REQUIRE(degree >= 1 && degree <= 6, "stfem_point_evaluate: degree %d out of range", degree);
   STFEM_REQUIRE(n_points >= 1 && nb >= 1 && nb <= STFEM_MAX_BLOCKS, "stfem_point_evaluate: bad counts");
-  STFEM_REQUIRE(!mesh->part.active, "stfem_point_evaluate: partitioned meshes are not supported yet");
+  // partitioned mesh (collective call): every rank evaluates the points inside its own brick; the values are summed over
+  // the ranks and divided by the number of ranks that found the point (a point on a rank interface has the same value
+  // from either side)
+  const bool         partitioned = mesh->part.active;
+  std::vector<double> found_here(n_points, 1.0);
   stfem_ctx *ctx = mesh->ctx;
   const int  dim = mesh->dim, n1 = degree + 1;
   const int  nc  = dim == 3 ? n1 * n1 * n1 : n1 * n1;
@@ -517,6 +521,16 @@ int stfem_point_evaluate(stfem_mesh_t mesh, int degree, int n_points, const doub
                     }
                 }
         }
+      if (!found && partitioned)
+        {
+          found_here[p] = 0.0;
+          for (int o = 0; o < nc; ++o)
+            {
+              idx[(size_t)p * nc + o] = 0;
+              w[(size_t)p * nc + o]   = 0.0;
+            }
+          continue;
+        }
       STFEM_REQUIRE(found, "stfem_point_evaluate: point %d lies outside the mesh", p);
       double L[3][8];
       for (int a = 0; a < dim; ++a)
@@ -553,6 +567,19 @@ int stfem_point_evaluate(stfem_mesh_t mesh, int degree, int n_points, const doub
   cudaFree(d_idx);
   cudaFree(d_w);
   cudaFree(d_out);
+  if (partitioned)
+    {
+      std::vector<double> buf(out, out + n_items);
+      buf.insert(buf.end(), found_here.begin(), found_here.end());
+      for (size_t o = 0; o < buf.size(); o += 256)
+        STFEM_FORWARD(stfem_ctx_allreduce(ctx, buf.data() + o, (int)std::min<size_t>(256, buf.size() - o), 0));
+      for (int p = 0; p < n_points; ++p)
+        {
+          const double cnt = buf[(size_t)n_items + p];
+          STFEM_REQUIRE(cnt >= 0.5, "stfem_point_evaluate: point %d lies outside the (global) mesh", p);
+          for (int b = 0; b < nb; ++b) out[(size_t)b * n_points + p] = buf[(size_t)b * n_points + p] / cnt;
+        }
+    }
   return STFEM_OK;
 }
 

@@ -96,4 +96,5 @@ struct stfem_mesh
   std::vector<double> h_vertices;
   unsigned   dirichlet = 0;
   stfem::PartitionInfo part; // box partition of a multi-GPU run (this mesh = the local brick)
+  std::vector<double> h_vertices_ghost; // partitioned general meshes: vertices of the brick + one cell layer across shared faces
 };

@@ -363,6 +363,7 @@ namespace stfem
     size_t bytes_all = 0;
     HaloPlan plan;                                  // cached for (np, nb)
     HaloP2P  p2p;                                   // peer-memory exchange of that plan
+    bool     no_p2p = false;                        // one-off exchanges (set-up): NCCL send / receive, no peer-memory set-up
     ~HaloBuffers()
     {
       for (int s = 0; s < 2; ++s)

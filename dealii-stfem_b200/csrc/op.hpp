@@ -20,6 +20,7 @@ struct stfem_op
   void *d_coeff = nullptr;  // per-cell Laplace coefficient
   bool  geom_otf = false;   // general geometry in 3D: metric computed on the fly from the cell vertices (st_vmult_plane.cuh, OTF)
   std::vector<double> h_coeff_cell, h_coeff_q; // host copies (Vanka set-up works in double)
+  std::vector<double> h_coeff_cell_ghost, h_coeff_q_ghost; // partitioned meshes: the same over the brick + its ghost cell layer
   std::vector<double> fd_V, fd_lam; // kernel_variant 60: modes of the reference-cell pencil (Kh, Mh), computed on first use
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points
   std::vector<void *> d_part_scratch; // partitioned meshes: increment of an accumulating apply before the halo sum

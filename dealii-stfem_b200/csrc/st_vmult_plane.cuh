@@ -251,10 +251,11 @@ namespace stfem
     // ---------------- phase B: x lines (z = i, y = m): to the Gauss points in x, metric, back
     {
       const V2 *met = reinterpret_cast<const V2 *>(a.metric) + (size_t)cell * (N1 * N1 * 4 * N1);
-      // a real loop over the N1 lines of a thread: the unrolled body (N1 times ~600 instructions) overflowed the instruction
-      // cache (ncu: one "no instruction" stall per issued instruction with the 3 warps per scheduler this kernel runs with)
-#pragma unroll 1
-      for (int m = 0; m < N1; ++m)
+      // One x line.  The N1 lines of a thread run as a real loop where that is faster (measured, Q4, 96^3 cells: on-the-fly
+      // geometry FP64 6.03 -> 5.15 ms, FP32 2.60 -> 2.33 ms; stored metric FP32 2.10 -> 1.91 ms): the unrolled body (N1 times
+      // ~600 instructions) overflows the instruction cache (ncu: one "no instruction" stall per issued instruction with the
+      // 3 warps per scheduler this kernel runs with).  FP64 with the stored metric keeps the unrolled form (4.22 against 4.39 ms).
+      auto x_line = [&](int m)
         {
           const int line = L::blocked ? N1 * i + m : i + N1 * m; // (z, y) = (i, m) for blocked, (m, i) else
           const int qy   = L::blocked ? m : i;
@@ -341,6 +342,16 @@ namespace stfem
           pl_apply<T, N1, true>(a.S, gz, o);
 #pragma unroll
           for (int x = 0; x < N1; ++x) pl[2 * FS + x] = o[x];
+        };
+      if constexpr (OTF || sizeof(T) == 4)
+        {
+#pragma unroll 1
+          for (int m = 0; m < N1; ++m) x_line(m);
+        }
+      else
+        {
+#pragma unroll
+          for (int m = 0; m < N1; ++m) x_line(m);
         }
     }
     __syncthreads();

@@ -477,31 +477,87 @@ namespace stfem
     const int dim = m->dim, n1 = op->degree + 1, nb = op->nb_rows;
     const int nc = dim == 3 ? n1 * n1 * n1 : n1 * n1;
     nrow         = nb * nc;
-    VankaGeom g;
-    g.dim = dim; g.n1 = n1; g.n_cells = m->n_cells; g.dirichlet = m->dirichlet;
-    for (int d = 0; d < 3; ++d)
-      {
-        g.n[d]  = m->n[d];
-        g.np[d] = op->np[d];
-        g.h[d]  = d < dim ? (m->upper[d] - m->lower[d]) / m->n[d] : 1.0;
-      }
-    for (int q = 0; q < n1 * n1; ++q) { g.S[q] = op->shape->S[q]; g.D[q] = op->shape->D[q]; }
-    for (int q = 0; q < n1; ++q) g.w[q] = op->shape->wq[q];
     const bool general = op->d_metric != nullptr || !op->mesh->cartesian; // (operators with on-the-fly geometry keep no metric)
-    const bool dedup   = !general && op->h_coeff_cell.empty();
+    const bool uniform = !general && op->h_coeff_cell.empty();
+    const bool dedup   = uniform && !m->part.active; // (the position classes of a partitioned brick depend on its neighbours: one patch per cell there)
     args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
     for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }
     // variant 2 on the level operator keeps the dense patch inverses (cross-check of the Kronecker form)
-    if (dedup && dim == 3 && n1 >= 2 && n1 <= 6 && op->variant != 2 && (nb <= 4 || nb == 6 || nb == 8))
+    if (uniform && dim == 3 && n1 >= 2 && n1 <= 6 && op->variant != 2 && (nb <= 4 || nb == 6 || nb == 8))
       return setup_fd();
-    STFEM_REQUIRE(!m->part.active, "Vanka: on partitioned meshes only the Kronecker form (3D Cartesian, constant coefficient) is implemented");
-    double    *d_metric = nullptr, *d_coeff = nullptr;
-    if (general) STFEM_FORWARD(metric_double(op, &d_metric));
-    g.metric = d_metric;
-    if (!op->h_coeff_cell.empty())
+    // Geometry the patch matrices are assembled on.  Partitioned meshes: the local brick extended by one ghost cell layer
+    // across every face shared with another rank (the neighbours of an interface cell contribute to its patch, and the
+    // valence of an interface DoF counts them), described by a temporary mesh / operator pair; the caller provides the
+    // ghost vertices (general meshes) and ghost coefficients (stfem_mesh_set_ghost_vertices, stfem_op_set_ghost_coefficients).
+    stfem_mesh *gm = m;
+    stfem_op   *gop = op;
+    std::unique_ptr<stfem_mesh> xm;
+    std::unique_ptr<stfem_op>   xo;
+    int                         glo[3] = {0, 0, 0};
+    if (m->part.active)
       {
-        STFEM_CUDA_CHECK(cudaMalloc(&d_coeff, sizeof(double) * m->n_cells));
-        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_coeff, op->h_coeff_cell.data(), sizeof(double) * m->n_cells, cudaMemcpyHostToDevice, ctx->stream));
+        xm            = std::make_unique<stfem_mesh>();
+        xm->ctx       = ctx;
+        xm->dim       = dim;
+        xm->cartesian = m->cartesian;
+        xm->dirichlet = m->dirichlet;
+        xm->n_cells   = 1;
+        size_t nv     = 1;
+        for (int d = 0; d < dim; ++d)
+          {
+            glo[d]          = m->part.neighbor[d][0] >= 0 ? 1 : 0;
+            const int    gh = m->part.neighbor[d][1] >= 0 ? 1 : 0;
+            const double h  = (m->upper[d] - m->lower[d]) / m->n[d];
+            xm->n[d]        = m->n[d] + glo[d] + gh;
+            xm->lower[d]    = m->lower[d] - glo[d] * h;
+            xm->upper[d]    = m->upper[d] + gh * h;
+            xm->n_cells *= xm->n[d];
+            nv *= (size_t)xm->n[d] + 1;
+          }
+        if (!m->cartesian)
+          {
+            STFEM_REQUIRE(m->h_vertices_ghost.size() == nv * dim,
+                          "Vanka (dense patches) on a partitioned general mesh needs the ghost vertices (stfem_mesh_set_ghost_vertices)");
+            STFEM_CUDA_CHECK(cudaMalloc(&xm->d_vertices, nv * dim * sizeof(double)));
+            STFEM_CUDA_CHECK(cudaMemcpyAsync(xm->d_vertices, m->h_vertices_ghost.data(), nv * dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+          }
+        xo         = std::make_unique<stfem_op>();
+        xo->mesh   = xm.get();
+        xo->degree = op->degree;
+        xo->shape  = std::make_unique<ShapeHost>(op->degree);
+        if (!op->h_coeff_cell.empty())
+          {
+            STFEM_REQUIRE((long long)op->h_coeff_cell_ghost.size() == xm->n_cells,
+                          "Vanka (dense patches) on a partitioned mesh needs the per-cell coefficient of the ghost cells (stfem_op_set_ghost_coefficients)");
+            xo->h_coeff_cell = op->h_coeff_cell_ghost;
+          }
+        if (!op->h_coeff_q.empty())
+          {
+            const long long nq = dim == 3 ? n1 * n1 * n1 : n1 * n1;
+            STFEM_REQUIRE((long long)op->h_coeff_q_ghost.size() == xm->n_cells * nq,
+                          "Vanka (dense patches) on a partitioned mesh needs the per-q coefficient of the ghost cells (stfem_op_set_ghost_coefficients)");
+            xo->h_coeff_q = op->h_coeff_q_ghost;
+          }
+        gm  = xm.get();
+        gop = xo.get();
+      }
+    VankaGeom g;
+    g.dim = dim; g.n1 = n1; g.n_cells = gm->n_cells; g.dirichlet = gm->dirichlet;
+    for (int d = 0; d < 3; ++d)
+      {
+        g.n[d]  = d < dim ? gm->n[d] : 1;
+        g.np[d] = d < dim ? op->degree * gm->n[d] + 1 : 1;
+        g.h[d]  = d < dim ? (gm->upper[d] - gm->lower[d]) / gm->n[d] : 1.0;
+      }
+    for (int q = 0; q < n1 * n1; ++q) { g.S[q] = op->shape->S[q]; g.D[q] = op->shape->D[q]; }
+    for (int q = 0; q < n1; ++q) g.w[q] = op->shape->wq[q];
+    double    *d_metric = nullptr, *d_coeff = nullptr;
+    if (general) STFEM_FORWARD(metric_double(gop, &d_metric));
+    g.metric = d_metric;
+    if (!gop->h_coeff_cell.empty())
+      {
+        STFEM_CUDA_CHECK(cudaMalloc(&d_coeff, sizeof(double) * gm->n_cells));
+        STFEM_CUDA_CHECK(cudaMemcpyAsync(d_coeff, gop->h_coeff_cell.data(), sizeof(double) * gm->n_cells, cudaMemcpyHostToDevice, ctx->stream));
       }
     g.coeff_cell = d_coeff;
     // patch list
@@ -532,8 +588,13 @@ namespace stfem
       }
     else
       {
+        // the local cells, numbered on the geometry's (possibly ghost-extended) brick
         cells.resize(m->n_cells);
-        for (long long c = 0; c < m->n_cells; ++c) cells[c] = c;
+        for (long long c = 0; c < m->n_cells; ++c)
+          {
+            const long long cx = c % m->n[0], cy = (c / m->n[0]) % m->n[1], cz = dim == 3 ? c / ((long long)m->n[0] * m->n[1]) : 0;
+            cells[c] = (cx + glo[0]) + (long long)g.n[0] * ((cy + glo[1]) + (long long)g.n[1] * (cz + glo[2]));
+          }
       }
     n_mat = (long long)cells.size();
     bytes = sizeof(T) * (size_t)n_mat * nrow * nrow;
@@ -572,6 +633,7 @@ namespace stfem
     STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (void *p : {(void *)d_B, (void *)d_cells, (void *)d_perm, (void *)d_info, (void *)d_alpha, (void *)d_beta, (void *)d_metric, (void *)d_coeff})
       if (p) cudaFree(p);
+    if (xm && xm->d_vertices) cudaFree(xm->d_vertices);
     STFEM_REQUIRE(info == 0, "Vanka: singular patch matrix (patch %d)", info - 1);
     args.dim = dim; args.n1 = n1; args.nb = nb; args.n_cells = m->n_cells; args.N = op->N;
     for (int d = 0; d < 3; ++d) { args.n[d] = m->n[d]; args.np[d] = op->np[d]; }

@@ -18,6 +18,8 @@ capi.SYMBOLS.update({
     "stfem_partition_brick": (C.c_int, [C.c_int, _ip, _dp, _dp, _ip, _ip, _ip, _ip, _dp, _dp, C.POINTER(C.c_uint)]),
     "stfem_mesh_set_partition": (C.c_int, [_vp, _ip, _ip]),
     "stfem_op_halo_add": (C.c_int, [_vp, _vpp, C.c_int]),
+    "stfem_mesh_set_ghost_vertices": (C.c_int, [_vp, _dp]),
+    "stfem_op_set_ghost_coefficients": (C.c_int, [_vp, _dp, _dp]),
     "stfem_halo_emulate_host": (C.c_int, [C.c_int, _ip, _ip, C.c_int, _dp]),
 })
 

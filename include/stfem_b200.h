@@ -154,6 +154,16 @@ int stfem_partition_brick(int dim, const int *n_global, const double *lower, con
                           const int *coords, int *n_local, int *cell_offset, double *local_lower, double *local_upper,
                           unsigned *dirichlet_faces);
 int stfem_mesh_set_partition(stfem_mesh_t mesh, const int *proc_grid, const int *coords);
+/* Ghost layer of a partitioned mesh = the local brick extended by ONE cell layer across every face shared with another
+ * rank (deal.II's ghost cells; the reference gets them from parallel::distributed::Triangulation, tests/tp_01.cc:83-90).
+ * Needed only by the dense cell-patch smoother (PreconditionVanka, include/stmg.h:745-872: its patch matrices take the
+ * contributions of the neighbouring cells on shared DoFs, include/compute_block_matrix.h:50-139).  The extended brick has
+ * n_d + g_lo + g_hi cells per direction (g = 1 where stfem_mesh_set_partition found a neighbour), x fastest.
+ *   vertices_ext   (n_ext_d + 1) points per direction, dim coordinates each: general (MappingQ1) meshes only
+ *   coeff_cell_ext / coeff_q_ext   the operator's laplace_coeff_cell / laplace_coeff_q over the extended brick (NULL: none) */
+int stfem_mesh_set_ghost_vertices(stfem_mesh_t mesh, const double *vertices_ext);
+int stfem_op_set_ghost_coefficients(stfem_op_t op, const double *coeff_cell_ext, const double *coeff_q_ext);
+
 /* host-only test hook: the interface exchange of a box partition among all its bricks inside one process, executing the
  * same element functions as the pack / unpack kernels (no GPU, no NCCL).  data: [n_ranks][nb][np0*np1*np2] doubles. */
 int stfem_halo_emulate_host(int dim, const int *proc_grid, const int *np, int nb, double *data);

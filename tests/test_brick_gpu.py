@@ -38,7 +38,7 @@ CASES = [
 @pytest.mark.parametrize("variant", [72, 70, 82, 77, 90])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "k%d_%s_%s%d_m%x" % (c[0], "x".join(map(str, c[1])), c[3], c[4], c[6]))
 def test_brick_kernel_matches_oracle(ctx, case, variant, number_type):
-    """72: TMA loads; 70: plain loads; 82: three z chunks (warm-up layers); 77: X and Y+Z phases on separate warps (Q4, two blocks only); 90: 72 without the per-SM alternation of the warp roles."""
+    """72: TMA loads; 70: plain loads; 82: three z chunks (warm-up layers); 77: X and Y+Z phases on separate warps (Q4, two blocks only); 90: 72 with the per-SM alternation of the X warps."""
     import dealii_stfem_b200 as st
     k, cells, upper, ttype, r, nts, mask = case
     mesh = S.Mesh(3, cells, 0, lower=[0, 0, 0], upper=upper)

@@ -115,10 +115,6 @@ def test_coarse_grid_gmres_matches_oracle(ctx, name, dim, ref, over):
                    lv["ptypes"], np.float32, smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"],
                    smoothing_range=p["smoothingRange"], eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
                    coarse_gmres=(10, 1e-20))
-    omg_s = stmg.GMG(p["timeType"], lv["ops"], lv["spaces"], lv["mg_type_level"], lv["poly_time"], p["nTimestepsAtOnce"],
-                     lv["ptypes"], np.float32, smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"],
-                     smoothing_range=p["smoothingRange"], eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
-                     vanka=omg.vanka)
     meshes, ops = gpu_levels(st, ctx, lv, st.F32)
     mg = st.Multigrid(ctx, ops, lv["mg_type_level"], lv["ptypes"], p["timeType"], p["nTimestepsAtOnce"], lv["poly_time"],
                       smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
@@ -132,10 +128,6 @@ def test_coarse_grid_gmres_matches_oracle(ctx, name, dim, ref, over):
         mg.vmult(dz, db.upload(b))
         z_o = omg.vmult(b)
         assert rel(dz.download(), z_o) < 2e-3
-        # ... and, where the coarsest level has more than one free DoF (in 2D it is a single cell with every boundary node
-        # constrained), it is a different preconditioner than the one with the smoother as coarse solver
-        if int((~lv["spaces"][0].constrained).sum()) > 1:
-            assert rel(z_o, omg_s.vmult(b)) > 1e-6
     db.free(); dz.free(); mg.close()
     for o in ops:
         o.close()
