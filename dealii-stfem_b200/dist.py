@@ -75,6 +75,19 @@ def set_partition(mesh, proc_grid, coords):
     capi.check(capi.lib().stfem_mesh_set_partition(mesh.h, (C.c_int * dim)(*proc_grid), (C.c_int * dim)(*coords)))
 
 
+def set_ghost_vertices(mesh, vertices_ext):
+    """stfem_mesh_set_ghost_vertices: vertices of the local brick + one cell layer across every shared face."""
+    v = np.ascontiguousarray(vertices_ext, np.float64)
+    capi.check(capi.lib().stfem_mesh_set_ghost_vertices(mesh.h, capi._dptr(v)))
+
+
+def set_ghost_coefficients(op, coeff_cell_ext=None, coeff_q_ext=None):
+    """stfem_op_set_ghost_coefficients: the operator's Laplace coefficient over the ghost-extended brick."""
+    c = None if coeff_cell_ext is None else np.ascontiguousarray(coeff_cell_ext, np.float64)
+    q = None if coeff_q_ext is None else np.ascontiguousarray(coeff_q_ext, np.float64)
+    capi.check(capi.lib().stfem_op_set_ghost_coefficients(op.h, None if c is None else capi._dptr(c), None if q is None else capi._dptr(q)))
+
+
 def allreduce(ctx, values, op="sum"):
     """Host values reduced over the ranks of the context's communicator (stfem_ctx_allreduce): returns a new float64 array.
     op: "sum", "max" or "min".  A context without a communicator returns the values unchanged."""
@@ -89,6 +102,9 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
       vmult     Q4 x cG(2) operator, vmult_cells^3 cells per rank, FP64                              (tolerance 1e-12)
       vcycle    one STMG V-cycle, Q2 x DG(1), 2 subdivisions, `refinement` refinements, FP32 levels   (2e-3)
       solve     one time step (rhs + FGMRES): iteration counts +-1, solution                          (1e-8)
+      practical_*  the reference's practical set-up in small (perturbed mesh, coefficient table, dense cell-patch smoother on
+                ghost-layer patches, cut-off initial value): operator + matrix diagonal (1e-12), V-cycle (2e-3), two time
+                steps (iterations +-1, solution and point functionals 1e-8)
     Every rank must call it (collective); ctx is the context that owns the communicator."""
     from . import driver, fe_time_host
     grid = proc_grid_for(world, 3)
@@ -139,7 +155,7 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
     Ag = dy.download()
     glob.mg.vmult(dy, dx.upload(Ag))
     Vg = dy.download()
-    it_g = glob.step(evaluate_error=False)
+    it_g0 = glob.step(evaluate_error=False)
     sol_g = glob.x.download()
     dx.free(); dy.free()
     part = driver.HeatWaveProblem(ctx, p, 3, refinement, r, space_degree=k, partition=(grid, coords))
@@ -150,14 +166,74 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
     part.mg.vmult(dy, dx.upload(brick_of(Ag, nb, npg, npl, off)))
     res["vcycle"] = float(np.abs(dy.download() - brick_of(Vg, nb, npg, npl, off)).max() / np.abs(Vg).max())
     it_p = part.step(evaluate_error=False)
-    res["iterations_global"], res["iterations_partitioned"] = int(it_g), int(it_p)
+    res["iterations_global"], res["iterations_partitioned"] = int(it_g0), int(it_p)
     res["solve"] = float(np.abs(part.x.download() - brick_of(sol_g, nb, npg, npl, off)).max() / np.abs(sol_g).max())
+    dx.free(); dy.free(); part.close(); glob.close()
+
+    # ---- (4) the reference's practical set-up (configs[3] in small): perturbed MappingQ1 mesh, Coefficient<dim> table on K,
+    # dense cell-patch smoother (ghost-layer patches), cut-off initial value, point functionals; two partitioned levels
+    k, r = 2, 1
+
+    def vertices(n_cells):
+        g = [np.linspace(-1.0, 1.0, m + 1) for m in n_cells]
+        V = np.stack(np.meshgrid(g[2], g[1], g[0], indexing="ij")[::-1], axis=-1)     # [z][y][x][xyz]
+        d = np.random.RandomState(3).uniform(-1, 1, V.shape) * 0.1 * (2.0 / n_cells[0])
+        d[0] = d[-1] = 0
+        d[:, 0] = d[:, -1] = 0
+        d[:, :, 0] = d[:, :, -1] = 0
+        return V + d
+
+    pj = {"timeType": "DG", "problemType": "heat", "feDegree": r, "refinement": refinement, "subdivisions": "2,2,2",
+          "hyperRectLowerLeft": "-1,-1,-1", "hyperRectUpperRight": "1,1,1", "mgTimeBeforeSpace": "true", "smoother": "relaxation",
+          "spaceTimeConvergenceTest": "false", "distortGrid": 0.1, "distortCoeff": "0.6", "extrapolate": "false"}
+    p = driver.parse_parameters(pj, 3)
+    ng = [2 * (1 << refinement)] * 3
+    Vf = vertices(ng).reshape(-1, 3)
+    p["sourcePoint"] = [float(c) for c in Vf[np.argmin(np.sum(Vf * Vf, axis=1))]]
+    p["agglomerateBelow"] = 2
+    glob = driver.HeatWaveProblem(ctx0, p, 3, refinement, r, space_degree=k, vertices_fn=vertices)
+    npg = [k * n + 1 for n in ng]
+    nb = glob.nb
+    xg = np.random.RandomState(11).uniform(-1, 1, (nb, glob.n))
+    dx, dy = glob.matrix.new_vector().upload(xg), glob.matrix.new_vector()
+    glob.matrix.vmult(dy, dx)
+    Ag = dy.download()
+    glob.matrix.diagonal(dy)
+    Dg = dy.download()
+    glob.mg.vmult(dy, dx.upload(Ag))
+    Vg = dy.download()
+    it_g = [glob.step(evaluate_error=False) for _ in range(2)]
+    sol_g = glob.x.download()
+    fun_g = np.array(glob.functional_rows[-1][1:])
+    dx.free(); dy.free()
+    part = driver.HeatWaveProblem(ctx, p, 3, refinement, r, space_degree=k, vertices_fn=vertices, partition=(grid, coords))
+    nl = [n // g for n, g in zip(ng, grid)]
+    npl = [k * n + 1 for n in nl]
+    off = [k * nl[d] * coords[d] for d in range(3)]
+    dx, dy = part.matrix.new_vector(), part.matrix.new_vector()
+    part.matrix.vmult(dy, dx.upload(brick_of(xg, nb, npg, npl, off)))
+    res["practical_vmult"] = float(np.abs(dy.download() - brick_of(Ag, nb, npg, npl, off)).max() / np.abs(Ag).max())
+    part.matrix.diagonal(dy)
+    res["practical_diagonal"] = float(np.abs(dy.download() - brick_of(Dg, nb, npg, npl, off)).max() / np.abs(Dg).max())
+    part.mg.vmult(dy, dx.upload(brick_of(Ag, nb, npg, npl, off)))
+    res["practical_vcycle"] = float(np.abs(dy.download() - brick_of(Vg, nb, npg, npl, off)).max() / np.abs(Vg).max())
+    it_pp = [part.step(evaluate_error=False) for _ in range(2)]
+    res["practical_iterations_global"], res["practical_iterations_partitioned"] = [int(i) for i in it_g], [int(i) for i in it_pp]
+    res["practical_solve"] = float(np.abs(part.x.download() - brick_of(sol_g, nb, npg, npl, off)).max() / np.abs(sol_g).max())
+    fun_p = np.array(part.functional_rows[-1][1:])
+    res["practical_functionals"] = float(np.abs(fun_p - fun_g).max() / max(np.abs(fun_g).max(), 1e-300))
     dx.free(); dy.free(); part.close(); glob.close(); ctx0.close()
-    ok = res["vmult"] <= 1e-12 and res["vcycle"] <= 2e-3 and abs(it_p - it_g) <= 1 and res["solve"] <= 1e-8
+    ok_practical = (res["practical_vmult"] <= 1e-12 and res["practical_diagonal"] <= 1e-12 and res["practical_vcycle"] <= 2e-3 and
+                    all(abs(a - b) <= 1 for a, b in zip(it_g, it_pp)) and res["practical_solve"] <= 1e-8 and
+                    res["practical_functionals"] <= 1e-8)
+    ok = res["vmult"] <= 1e-12 and res["vcycle"] <= 2e-3 and abs(it_p - it_g0) <= 1 and res["solve"] <= 1e-8 and ok_practical
     # every rank must agree: the worst error / flag over the ranks
-    worst = allreduce(ctx, [res["vmult"], res["vcycle"], res["solve"], 0.0 if ok else 1.0], "max")
-    res["vmult"], res["vcycle"], res["solve"] = float(worst[0]), float(worst[1]), float(worst[2])
-    res["ok"] = bool(worst[3] == 0.0)
-    res["tolerances"] = {"vmult": 1e-12, "vcycle": 2e-3, "solve": 1e-8, "iterations": 1}
+    keys = ["vmult", "vcycle", "solve", "practical_vmult", "practical_diagonal", "practical_vcycle", "practical_solve",
+            "practical_functionals"]
+    worst = allreduce(ctx, [res[kk] for kk in keys] + [0.0 if ok else 1.0], "max")
+    for kk, w in zip(keys, worst):
+        res[kk] = float(w)
+    res["ok"] = bool(worst[-1] == 0.0)
+    res["tolerances"] = {"vmult": 1e-12, "diagonal": 1e-12, "vcycle": 2e-3, "solve": 1e-8, "functionals": 1e-8, "iterations": 1}
     res["grid"] = list(grid)
     return res

@@ -173,6 +173,7 @@ class HeatWaveProblem:
         fetw = level_time_weights(self.ttype, self.tau, self.nts, self.mg_type_level, self.poly_time, self.wave)
         # ---- meshes per refinement (geometric coarsening sequence: every second vertex)
         self.meshes = {}
+        self.ghost_desc = {}        # refinement -> the same for the ghost-extended brick of a partitioned level
         mesh_desc = {}              # refinement -> (n_cells, lower, upper, vertices) of the (local) mesh, for host set-up helpers
         fine_vertices = vertices_fn(self.n_cells) if vertices_fn is not None else None
         for rf in sorted(set(level_ref)):
@@ -191,16 +192,35 @@ class HeatWaveProblem:
                 mesh_desc[rf] = (n, lo, up, v)
             else:
                 from . import dist
-                assert v is None, "partitioned runs support Cartesian meshes only"
-                n_loc, _, llo, lup, mask = dist.partition_brick(n, lo, up, partition[0], partition[1])
-                self.meshes[rf] = capi.Mesh(ctx, n_loc, lower=llo, upper=lup, dirichlet_faces=mask)
+                n_loc, off, llo, lup, mask = dist.partition_brick(n, lo, up, partition[0], partition[1])
+                # ghost layer (deal.II's ghost cells): the brick extended by one cell layer across every face shared with
+                # another rank - what the dense cell-patch smoother assembles its interface patches on
+                glo = [1 if partition[1][a] > 0 else 0 for a in range(dim)]
+                ghi = [1 if partition[1][a] < partition[0][a] - 1 else 0 for a in range(dim)]
+                hh = [(up[a] - lo[a]) / n[a] for a in range(dim)]
+                n_ext = [n_loc[a] + glo[a] + ghi[a] for a in range(dim)]
+                lo_ext = [llo[a] - glo[a] * hh[a] for a in range(dim)]
+                up_ext = [lup[a] + ghi[a] * hh[a] for a in range(dim)]
+                v_loc = v_ext = None
+                if v is not None:
+                    vg = v.reshape([m + 1 for m in n[::-1]] + [dim])             # [z][y][x][xyz]
+                    sl_loc = tuple(slice(off[a], off[a] + n_loc[a] + 1) for a in range(dim))[::-1]
+                    sl_ext = tuple(slice(off[a] - glo[a], off[a] + n_loc[a] + ghi[a] + 1) for a in range(dim))[::-1]
+                    v_loc = np.ascontiguousarray(vg[sl_loc]).reshape(-1, dim)
+                    v_ext = np.ascontiguousarray(vg[sl_ext]).reshape(-1, dim)
+                self.meshes[rf] = capi.Mesh(ctx, n_loc, lower=llo, upper=lup, vertices=v_loc, dirichlet_faces=mask)
                 dist.set_partition(self.meshes[rf], partition[0], partition[1])
-                mesh_desc[rf] = (list(n_loc), list(llo), list(lup), None)
+                if v_ext is not None:
+                    dist.set_ghost_vertices(self.meshes[rf], v_ext)
+                mesh_desc[rf] = (list(n_loc), list(llo), list(lup), v_loc)
+                self.ghost_desc[rf] = (n_ext, lo_ext, up_ext, v_ext)
         self.mesh_desc = mesh_desc
         self._coeff_cache = {}
         self.level_ops = [capi.Operator(self.meshes[level_ref[l]], level_degree[l], fetw[l][0], fetw[l][1], number_type=mg_number_type,
                                         variant=int(p.get("levelKernelVariant", 0)),
                                         **self._laplace_coefficient(level_ref[l], level_degree[l])) for l in range(nl)]
+        for l in range(nl):
+            self._set_ghost_coefficient(self.level_ops[l], level_ref[l], level_degree[l])
         self.mg = capi.Multigrid(ctx, self.level_ops, self.mg_type_level, self.ptypes, self.ttype, self.nts, self.poly_time,
                                  smoothing_steps=p["smoothingSteps"], relaxation=p["relaxation"], smoothing_range=p["smoothingRange"],
                                  eig_n_iterations=p["smoothingEigCgNIterations"], variable=p["variable"],
@@ -270,7 +290,7 @@ class HeatWaveProblem:
         self.functional_rows = []           # (t, value at every point), in the order the reference writes them
         self.functional_file = None         # set to a path to append the reference's text format
         self._prev_pt = None
-        if not conv and partition is None:
+        if not conv:
             self._prev_pt = self.point_evaluate([self.x.ptrs[nbv - 1]])[0]
 
     def _laplace_coefficient(self, rf, degree):
@@ -290,6 +310,20 @@ class HeatWaveProblem:
             else:
                 self._coeff_cache[key] = {"laplace_coeff_q": cq}
         return self._coeff_cache[key]
+
+    def _set_ghost_coefficient(self, op, rf, degree):
+        """Partitioned levels of practical runs: the Laplace coefficient of the ghost cells (dense Vanka set-up)."""
+        if rf not in self.ghost_desc or self.p["spaceTimeConvergenceTest"]:
+            return
+        from . import dist
+        p = self.p
+        n, lo, up, v = self.ghost_desc[rf]
+        cq = problem_host.coefficient_at_qpoints(n, lo, up, degree, p["subdivisions"], p["hyperRectLowerLeft"],
+                                                 p["hyperRectUpperRight"], p["distortCoeff"], vertices=v)
+        if "laplace_coeff_cell" in self._coeff_cache[(rf, degree)]:
+            dist.set_ghost_coefficients(op, np.ascontiguousarray(cq[:, 0]), None)
+        else:
+            dist.set_ghost_coefficients(op, None, cq)
 
     def point_evaluate(self, block_ptrs):
         """u_b(real_points[p]) for the given device vectors: [len(block_ptrs), n_points]."""
