@@ -143,6 +143,26 @@ def cpu_reference_run(cfg, n_cells, steps, warmup):
     return nb * space.n_dofs / dt, dt * 1e3, threads, nb * space.n_dofs
 
 
+def bind_host_to_gpu(dev):
+    """CPU affinity of this process := the cores NVML reports as local to CUDA device `dev` (matched by PCI bus id)."""
+    try:
+        import pynvml
+        import torch
+        pr = torch.cuda.get_device_properties(dev)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local cores reported)"
+        os.sched_setaffinity(0, cpus)
+        return "%d cores local to GPU %s" % (len(cpus), bus)
+    except Exception as e:            # measurement nicety only: never fail the bench over it
+        return "unchanged (%s)" % type(e).__name__
+
+
 def ncu_traffic(cfg_name, n_cells):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, read from the committed ncu capture
     of the same command (profiles/): (bytes, provenance) - not measured in this run."""
@@ -396,6 +416,10 @@ def main():
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
 
+    # N > 1: every rank stays on the cores next to its GPU, so that its pinned buffers come from the NUMA node the GPU's PCIe
+    # root belongs to (torchrun does not bind; unbound, eight ranks crossing the socket interconnect share its bandwidth)
+    host_binding = bind_host_to_gpu(dev) if world > 1 else "none (single rank)"
+
     ctx = st.Context(dev)
 
     def barrier():
@@ -485,8 +509,14 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     checksum = float(np.abs(hy).sum())
+    # the floor of that path: the same buffers copied up and down concurrently with no kernel in between (all ranks at once)
+    hy2, py2 = st.capi.pinned_array((nb, op.n), np.float64)
+    barrier()
+    copy_ms = op.host_copy_floor(hy2, hx, reps=3)
+    barrier()
+    st.capi.free_pinned(py2)
 
-    ms_total, e2e_ms, kernel_ms = (float(v) for v in st.dist.allreduce(ctx, [ms_total, e2e_ms, kernel_ms], "max"))
+    ms_total, e2e_ms, kernel_ms, copy_ms = (float(v) for v in st.dist.allreduce(ctx, [ms_total, e2e_ms, kernel_ms, copy_ms], "max"))
     ms_step = ms_total / args.steps
     total_dofs = dofs_rank * world
     value = total_dofs / (ms_step * 1e-3)
@@ -507,7 +537,10 @@ def main():
                                  "time of one operator application on the library stream (one st_vmult_brick_kernel launch, no "
                                  "memset); the kernel is FP64-pipe bound, see DESIGN.md 3.1"},
             "e2e": {"value": total_dofs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(dofs_rank * 8), "d2h_bytes_per_step": int(dofs_rank * 8)},
+                    "h2d_bytes_per_step": int(dofs_rank * 8), "d2h_bytes_per_step": int(dofs_rank * 8),
+                    "copy_floor_ms": copy_ms, "host_binding": host_binding,
+                    "note": "copy_floor_ms = the same pinned buffers uploaded and downloaded concurrently without a kernel, all "
+                            "ranks at once, max over ranks (stfem_op_host_copy_floor): what PCIe + host memory allow for this step"},
             "gpu_launches": int(launches), "clocks": clocks}
     if parity is not None:
         line["parity_multi_gpu"] = parity

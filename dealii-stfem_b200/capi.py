@@ -59,6 +59,7 @@ SYMBOLS = {
     "stfem_op_vmult_slice_add": (C.c_int, [_vp, _vpp, _vp]),
     "stfem_op_diagonal": (C.c_int, [_vp, _vpp]),
     "stfem_op_vmult_host": (C.c_int, [_vp, _vpp, _vpp, C.c_int]),
+    "stfem_op_host_copy_floor": (C.c_int, [_vp, _vpp, _vpp, C.c_int, C.POINTER(C.c_double)]),
     "stfem_op_set_timing": (C.c_int, [_vp, C.c_int]),
     "stfem_op_last_kernel_ms": (C.c_float, [_vp]),
     "stfem_mg_create": (C.c_int, [_vp, _vp, _vpp]),
@@ -253,6 +254,15 @@ class Operator:
     def diagonal(self, dst):
         """get_matrix_diagonal (operators.h:613-625) into a block vector of the operator's number type."""
         check(lib().stfem_op_diagonal(self.h, dst.ptrs))
+
+    def host_copy_floor(self, dst, src, reps=3):
+        """Milliseconds per round of uploading src and downloading dst concurrently without a kernel (stfem_op_host_copy_floor)."""
+        nb = self.nb_rows
+        dp = (C.c_void_p * nb)(*[dst[b].ctypes.data for b in range(nb)])
+        spp = (C.c_void_p * nb)(*[src[b].ctypes.data for b in range(nb)])
+        ms = C.c_double()
+        check(lib().stfem_op_host_copy_floor(self.h, dp, spp, int(reps), C.byref(ms)))
+        return ms.value
 
     def vmult_host(self, dst, src, transpose=False):
         """dst, src: numpy [nb, N] (C-contiguous rows; pinned or pageable)."""

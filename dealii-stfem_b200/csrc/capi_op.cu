@@ -1,5 +1,6 @@
 // C ABI: space-time operator (SystemMatrix + MatrixFreeOperator of the reference,
 // include/operators.h:516-663 and :967-1191).
+#include <chrono>
 #include <cstdlib>
 
 #include "basis_host.hpp"
@@ -1048,6 +1049,8 @@ int stfem_op_destroy(stfem_op_t op)
     if (p) cudaFree(p);
   for (void *p : op->d_part_scratch)
     if (p) cudaFree(p);
+  if (op->d_xface) cudaFree(op->d_xface);
+  if (op->h_xface) cudaFreeHost(op->h_xface);
   delete op;
   return STFEM_OK;
 }
@@ -1098,6 +1101,26 @@ int stfem_op_diagonal(stfem_op_t op, void *const *diag)
   return STFEM_OK;
 }
 
+} // extern "C"
+
+namespace stfem
+{
+  // the node column x = ix of every block, packed: out[(b * n_rows + r)] = blocks[b][r * np0 + ix]
+  template <typename T>
+  __global__ void k_pack_xface(BlockPtrs blocks, int nb, long long n_rows, int np0, int ix, T *__restrict__ out)
+  {
+    const long long total = n_rows * nb;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+      {
+        const int       b = (int)(e / n_rows);
+        const long long r = e - (long long)b * n_rows;
+        out[e]            = static_cast<const T *>(blocks.p[b])[r * np0 + ix];
+      }
+  }
+} // namespace stfem
+
+extern "C" {
+
 int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const *src_host, int transpose)
 {
   STFEM_REQUIRE(op && dst_host && src_host, "stfem_op_vmult_host: null argument");
@@ -1123,7 +1146,17 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
   const void *alpha = transpose ? op->d_alphaT : op->d_alpha, *beta = transpose ? op->d_betaT : op->d_beta;
   const int  *mn = op->mesh->n;
   static const bool no_pipeline = std::getenv("STFEM_NO_PIPELINE") != nullptr;
-  if (!uses_cart(op) || op->mesh->part.active || mn[2] < 4 || no_pipeline)
+  // partitioned meshes: pipelined only with the brick kernel (whole x-y cross-sections per slab, no overlap scheme needed)
+  bool part_pipeline = false;
+  if (op->mesh->part.active && uses_cart(op) && mn[2] >= 4 && !no_pipeline)
+    {
+      int lo0[3] = {0, 0, 0}, nn0[3] = {mn[0], mn[1], 1};
+      op->box_lo = lo0;
+      op->box_n  = nn0;
+      part_pipeline = brick_eligible(op, nb, nb, alpha, beta);
+      op->box_lo = op->box_n = nullptr;
+    }
+  if (!uses_cart(op) || (op->mesh->part.active && !part_pipeline) || mn[2] < 4 || no_pipeline)
     {
       for (int b = 0; b < nb; ++b)
         STFEM_CUDA_CHECK(cudaMemcpyAsync(op->d_scratch[nb + b], src_host[b], bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1183,9 +1216,123 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
       for (int b = 0; b < nb; ++b)
         STFEM_CUDA_CHECK(cudaMemcpyAsync((char *)dst_host[b] + q0 * plane, (const char *)d[b] + q0 * plane, (q1 - q0) * plane, cudaMemcpyDeviceToHost, down));
     }
+  if (part_pipeline)
+    {
+      // Partitioned mesh: the planes downloaded above hold this rank's partial sums at the interface nodes.  Sum them over
+      // the ranks (one exchange, after the last slab), then download the interface nodes once more - behind the bulk copies
+      // on the same stream, so the final values land last: z faces as whole planes, y faces as strided rows, x faces
+      // packed by a kernel into a pinned staging buffer and scattered by the host after the synchronisation.
+      const stfem::PartitionInfo &prt = op->mesh->part;
+      if (op->number_type == STFEM_F64)
+        STFEM_FORWARD(halo_compress_add<double>(ctx, prt, op->halo, d.data(), nb, op->np, 3, ctx->stream));
+      else
+        STFEM_FORWARD(halo_compress_add<float>(ctx, prt, op->halo, d.data(), nb, op->np, 3, ctx->stream));
+      const long long n_rows = (long long)op->np[1] * op->np[2];
+      const int       n_xf   = (prt.neighbor[0][0] >= 0 ? 1 : 0) + (prt.neighbor[0][1] >= 0 ? 1 : 0);
+      const size_t    xbytes = (size_t)n_rows * nb * esz;
+      if (n_xf > 0)
+        {
+          if (op->xface_bytes < 2 * xbytes)
+            {
+              if (op->d_xface) cudaFree(op->d_xface);
+              if (op->h_xface) cudaFreeHost(op->h_xface);
+              STFEM_CUDA_CHECK(cudaMalloc(&op->d_xface, 2 * xbytes));
+              STFEM_CUDA_CHECK(cudaHostAlloc(&op->h_xface, 2 * xbytes, cudaHostAllocDefault));
+              op->xface_bytes = 2 * xbytes;
+            }
+          BlockPtrs bp;
+          for (int b = 0; b < STFEM_MAX_BLOCKS; ++b) bp.p[b] = b < nb ? d[b] : nullptr;
+          int slot = 0;
+          for (int sd = 0; sd < 2; ++sd)
+            if (prt.neighbor[0][sd] >= 0)
+              {
+                const int ix = sd == 0 ? 0 : op->np[0] - 1;
+                const int grid = (int)std::min<long long>((n_rows * nb + 255) / 256, (long long)ctx->sm_count * 4);
+                if (esz == 8)
+                  k_pack_xface<double><<<grid, 256, 0, ctx->stream>>>(bp, nb, n_rows, op->np[0], ix, (double *)((char *)op->d_xface + slot * xbytes));
+                else
+                  k_pack_xface<float><<<grid, 256, 0, ctx->stream>>>(bp, nb, n_rows, op->np[0], ix, (float *)((char *)op->d_xface + slot * xbytes));
+                ctx->launches++;
+                ++slot;
+              }
+          STFEM_CUDA_CHECK(cudaGetLastError());
+        }
+      STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_pool[2 * n_slabs], ctx->stream));
+      STFEM_CUDA_CHECK(cudaStreamWaitEvent(down, ctx->ev_pool[2 * n_slabs], 0));
+      const size_t row = (size_t)op->np[0] * esz;
+      for (int b = 0; b < nb; ++b)
+        {
+          for (int sd = 0; sd < 2; ++sd)
+            {
+              if (prt.neighbor[2][sd] >= 0)
+                {
+                  const size_t o = (sd == 0 ? 0 : (size_t)op->np[2] - 1) * plane;
+                  STFEM_CUDA_CHECK(cudaMemcpyAsync((char *)dst_host[b] + o, (const char *)d[b] + o, plane, cudaMemcpyDeviceToHost, down));
+                }
+              if (prt.neighbor[1][sd] >= 0)
+                {
+                  const size_t o = (sd == 0 ? 0 : (size_t)op->np[1] - 1) * row;
+                  STFEM_CUDA_CHECK(cudaMemcpy2DAsync((char *)dst_host[b] + o, plane, (const char *)d[b] + o, plane, row, (size_t)op->np[2], cudaMemcpyDeviceToHost, down));
+                }
+            }
+        }
+      if (n_xf > 0) STFEM_CUDA_CHECK(cudaMemcpyAsync(op->h_xface, op->d_xface, n_xf * xbytes, cudaMemcpyDeviceToHost, down));
+      STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_join, down));
+      STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+      STFEM_FORWARD(stream_sync_checked(ctx, "stfem_op_vmult_host"));
+      int slot = 0;
+      for (int sd = 0; sd < 2; ++sd)
+        if (prt.neighbor[0][sd] >= 0)
+          {
+            const size_t ix = sd == 0 ? 0 : (size_t)op->np[0] - 1;
+            for (int b = 0; b < nb; ++b)
+              {
+                const char *src = (const char *)op->h_xface + slot * xbytes + (size_t)b * n_rows * esz;
+                char       *dh  = (char *)dst_host[b] + ix * esz;
+                if (esz == 8)
+                  for (long long r = 0; r < n_rows; ++r) *(double *)(dh + (size_t)r * row) = ((const double *)src)[r];
+                else
+                  for (long long r = 0; r < n_rows; ++r) *(float *)(dh + (size_t)r * row) = ((const float *)src)[r];
+              }
+            ++slot;
+          }
+      return STFEM_OK;
+    }
   STFEM_CUDA_CHECK(cudaEventRecord(ctx->ev_join, down));
   STFEM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   return stream_sync_checked(ctx, "stfem_op_vmult_host");
+}
+
+/* Measurement helper: the copy floor of stfem_op_vmult_host - the operator's nb blocks uploaded and downloaded concurrently
+ * (two copy streams, no kernel), host wall time of `reps` rounds in milliseconds per round. */
+int stfem_op_host_copy_floor(stfem_op_t op, void *const *dst_host, const void *const *src_host, int reps, double *ms_per_round)
+{
+  STFEM_REQUIRE(op && dst_host && src_host && ms_per_round && reps >= 1, "stfem_op_host_copy_floor: bad arguments");
+  stfem_ctx   *ctx   = op->mesh->ctx;
+  const int    nb    = op->nb_rows;
+  const size_t bytes = (size_t)op->N * (op->number_type == STFEM_F64 ? 8 : 4);
+  STFEM_CUDA_CHECK(cudaSetDevice(ctx->device));
+  STFEM_FORWARD(ctx_ensure_aux(ctx));
+  if (op->d_scratch.size() < (size_t)2 * nb)
+    {
+      for (void *p : op->d_scratch) cudaFree(p);
+      op->d_scratch.assign(2 * nb, nullptr);
+      for (auto &p : op->d_scratch) STFEM_CUDA_CHECK(cudaMalloc(&p, bytes + 16));
+    }
+  STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r)
+    {
+      for (int b = 0; b < nb; ++b)
+        {
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(op->d_scratch[nb + b], src_host[b], bytes, cudaMemcpyHostToDevice, ctx->aux[0]));
+          STFEM_CUDA_CHECK(cudaMemcpyAsync(dst_host[b], op->d_scratch[b], bytes, cudaMemcpyDeviceToHost, ctx->aux[1]));
+        }
+      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->aux[0]));
+      STFEM_CUDA_CHECK(cudaStreamSynchronize(ctx->aux[1]));
+    }
+  *ms_per_round = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
+  return STFEM_OK;
 }
 
 int stfem_op_set_timing(stfem_op_t op, int enable)

@@ -24,6 +24,8 @@ struct stfem_op
   std::vector<double> fd_V, fd_lam; // kernel_variant 60: modes of the reference-cell pencil (Kh, Mh), computed on first use
   std::vector<void *> d_scratch; // device staging for the host-buffer entry points
   std::vector<void *> d_part_scratch; // partitioned meshes: increment of an accumulating apply before the halo sum
+  void  *d_xface = nullptr, *h_xface = nullptr; // host-buffer entry point on partitioned meshes: packed x faces (device, pinned host)
+  size_t xface_bytes = 0;
   stfem::HaloBuffers halo;
   // launch context of the next kernel dispatch (set by op_apply's callers inside this file): cell sub-box, stream
   const int   *box_lo = nullptr, *box_n = nullptr;

@@ -138,6 +138,10 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
     dx, dy = pop.new_vector().upload(brick_of(xg, nb, npg, npl, off)), pop.new_vector()
     pop.vmult(dy, dx)
     res["vmult"] = float(np.abs(dy.download() - brick_of(Ag, nb, npg, npl, off)).max() / np.abs(Ag).max())
+    # the same through the host-buffer entry point (slab pipeline + interface nodes downloaded again after the exchange)
+    xh, yh = brick_of(xg, nb, npg, npl, off), np.full((nb, pop.n), 7.5)
+    pop.vmult_host(yh, xh)
+    res["vmult_host"] = float(np.abs(yh - brick_of(Ag, nb, npg, npl, off)).max() / np.abs(Ag).max())
     dx.free(); dy.free(); pop.close(); pm.close()
 
     # ---- (2), (3) V-cycle and a full time step through the product driver
@@ -226,9 +230,9 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
     ok_practical = (res["practical_vmult"] <= 1e-12 and res["practical_diagonal"] <= 1e-12 and res["practical_vcycle"] <= 2e-3 and
                     all(abs(a - b) <= 1 for a, b in zip(it_g, it_pp)) and res["practical_solve"] <= 1e-8 and
                     res["practical_functionals"] <= 1e-8)
-    ok = res["vmult"] <= 1e-12 and res["vcycle"] <= 2e-3 and abs(it_p - it_g0) <= 1 and res["solve"] <= 1e-8 and ok_practical
+    ok = res["vmult"] <= 1e-12 and res["vmult_host"] <= 1e-12 and res["vcycle"] <= 2e-3 and abs(it_p - it_g0) <= 1 and res["solve"] <= 1e-8 and ok_practical
     # every rank must agree: the worst error / flag over the ranks
-    keys = ["vmult", "vcycle", "solve", "practical_vmult", "practical_diagonal", "practical_vcycle", "practical_solve",
+    keys = ["vmult", "vmult_host", "vcycle", "solve", "practical_vmult", "practical_diagonal", "practical_vcycle", "practical_solve",
             "practical_functionals"]
     worst = allreduce(ctx, [res[kk] for kk in keys] + [0.0 if ok else 1.0], "max")
     for kk, w in zip(keys, worst):

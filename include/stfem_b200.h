@@ -127,6 +127,10 @@ int stfem_cart_fd_modes(int degree, double *V, double *lam);
 int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const *src_host,
                         int transpose);
 
+/* Measurement helper: the copy floor of stfem_op_vmult_host - the operator's blocks uploaded and downloaded concurrently
+ * on two copy streams without any kernel; host wall time per round in milliseconds (bench.py: e2e.copy_floor_ms). */
+int stfem_op_host_copy_floor(stfem_op_t op, void *const *dst_host, const void *const *src_host, int reps, double *ms_per_round);
+
 /* time of the last vmult kernel sequence on this operator, measured with CUDA events on the
  * context stream (ms); enabled with stfem_op_set_timing(op, 1) */
 int stfem_op_set_timing(stfem_op_t op, int enable);
