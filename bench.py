@@ -188,25 +188,34 @@ def perturbed_leg(st, ctx, cfg, n, steps=20):
     d[:, 0] = d[:, -1] = 0
     d[:, :, 0] = d[:, :, -1] = 0
     mesh = st.Mesh(ctx, [n, n, n], vertices=(V + d).reshape(-1, 3))
-    op = st.Operator(mesh, cfg["degree"], A, B, number_type=st.F64)
-    nb = op.nb_rows
-    x, y = op.new_vector(), op.new_vector()
-    x.upload(np.sin(0.1 * np.arange(op.n)[None, :] + np.arange(nb)[:, None]))
-    for _ in range(3):
-        op.vmult(y, x)
-    ctx.timer_start()
-    for _ in range(steps):
-        op.vmult(y, x)
-    ms = ctx.timer_stop() / steps
-    dofs = op.n * nb
-    alg = dofs * BYTES_PER_DOF + n ** 3 * 200
-    metric_bytes = n ** 3 * (cfg["degree"] + 1) ** 3 * 8 * 8
     peak, _ = measured_peak()
-    out = {"metric": "space-time DoFs/s, operator vmult on a perturbed mesh (MappingQ1 cells), FP64",
-           "value": dofs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "cells": n ** 3, "distortion": 0.15,
-           "algorithmic_bytes_per_launch": alg, "achieved_GBs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
-           "streamed_metric_bytes": metric_bytes, "note": "algorithmic = 16 B/DoF + 200 B/cell (SURVEY 8d)"}
-    x.free(); y.free(); op.close(); mesh.close()
+    out = {"metric": "space-time DoFs/s, operator vmult on a perturbed mesh (MappingQ1 cells), FP64", "unit": UNIT}
+    # default = stored metric where it fits (this mesh: 7 GB); kernel_variant 6 = geometry on the fly from the cell vertices
+    for key, variant in (("stored_metric", 0), ("on_the_fly", 6)):
+        op = st.Operator(mesh, cfg["degree"], A, B, number_type=st.F64, variant=variant)
+        nb = op.nb_rows
+        x, y = op.new_vector(), op.new_vector()
+        x.upload(np.sin(0.1 * np.arange(op.n)[None, :] + np.arange(nb)[:, None]))
+        for _ in range(3):
+            op.vmult(y, x)
+        ctx.timer_start()
+        for _ in range(steps):
+            op.vmult(y, x)
+        ms = ctx.timer_stop() / steps
+        dofs = op.n * nb
+        alg = dofs * BYTES_PER_DOF + n ** 3 * 200
+        leg = {"value": dofs / (ms * 1e-3), "ms_per_step": ms, "achieved_GBs": alg / (ms * 1e-3) / 1e9,
+               "frac": alg / (ms * 1e-3) / 1e9 / peak}
+        if key == "stored_metric":
+            out.update(leg)
+            out.update({"cells": n ** 3, "distortion": 0.15, "algorithmic_bytes_per_launch": alg,
+                        "streamed_metric_bytes": n ** 3 * (cfg["degree"] + 1) ** 3 * 8 * 8,
+                        "note": "algorithmic = 16 B/DoF + 200 B/cell (SURVEY 8d); value = the default kernel (stored metric); the "
+                                "kernel is bound by the FP64 pipe (1.4 ms at the FP64 peak, stored; 2.1 ms on the fly), DESIGN.md 3.2"})
+        else:
+            out[key] = leg
+        x.free(); y.free(); op.close()
+    mesh.close()
     return out
 
 
@@ -535,7 +544,7 @@ def main():
                          "algorithmic_bytes_per_launch": dofs_rank * BYTES_PER_DOF,
                          "note": "algorithmic bytes = 16 B per space-time DoF (read src once, write dst once); kernel_ms = CUDA-event "
                                  "time of one operator application on the library stream (one st_vmult_brick_kernel launch, no "
-                                 "memset); the kernel is FP64-pipe bound, see DESIGN.md 3.1"},
+                                 "memset); the kernel is FP64-pipe / latency bound, see DESIGN.md 3.0"},
             "e2e": {"value": total_dofs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(dofs_rank * 8), "d2h_bytes_per_step": int(dofs_rank * 8),
                     "copy_floor_ms": copy_ms, "host_binding": host_binding,

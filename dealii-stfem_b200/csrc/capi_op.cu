@@ -1169,7 +1169,9 @@ int stfem_op_vmult_host(stfem_op_t op, void *const *dst_host, const void *const 
   // node planes slab s has completed (copy engine 2) run concurrently; PCIe is used in both directions at once.
   STFEM_FORWARD(ctx_ensure_aux(ctx));
   const int    k       = op->degree;
-  const int    n_slabs = mn[2] < 16 ? mn[2] : 16;
+  static const int slabs_env = std::getenv("STFEM_HOST_SLABS") ? std::atoi(std::getenv("STFEM_HOST_SLABS")) : 0; // tuning
+  const int    slabs_max = slabs_env > 0 ? slabs_env : 16;
+  const int    n_slabs = mn[2] < slabs_max ? mn[2] : slabs_max;
   const size_t plane   = (size_t)op->np[0] * op->np[1] * esz; // bytes of one z plane of nodes
   while (ctx->ev_pool.size() < (size_t)2 * n_slabs + 1)
     {
