@@ -75,6 +75,23 @@ def set_partition(mesh, proc_grid, coords):
     capi.check(capi.lib().stfem_mesh_set_partition(mesh.h, (C.c_int * dim)(*proc_grid), (C.c_int * dim)(*coords)))
 
 
+def ghost_layers(proc_grid, coords):
+    """(g_lo, g_hi) per direction: 1 where another rank continues the mesh (one ghost cell layer), else 0."""
+    dim = len(proc_grid)
+    return [1 if coords[a] > 0 else 0 for a in range(dim)], [1 if coords[a] < proc_grid[a] - 1 else 0 for a in range(dim)]
+
+
+def brick_vertices(vertices_global, n_global, cell_offset, n_local, g_lo=None, g_hi=None):
+    """Vertices of one brick of a structured mesh (optionally extended by its ghost layers) out of the global lexicographic
+    vertex array ([..., z][y][x][xyz], x fastest): returns [(n_local + g_lo + g_hi + 1) points per direction, dim]."""
+    dim = len(n_global)
+    g_lo = [0] * dim if g_lo is None else g_lo
+    g_hi = [0] * dim if g_hi is None else g_hi
+    vg = np.asarray(vertices_global, np.float64).reshape([m + 1 for m in n_global[::-1]] + [dim])
+    sl = tuple(slice(cell_offset[a] - g_lo[a], cell_offset[a] + n_local[a] + g_hi[a] + 1) for a in range(dim))[::-1]
+    return np.ascontiguousarray(vg[sl]).reshape(-1, dim)
+
+
 def set_ghost_vertices(mesh, vertices_ext):
     """stfem_mesh_set_ghost_vertices: vertices of the local brick + one cell layer across every shared face."""
     v = np.ascontiguousarray(vertices_ext, np.float64)

@@ -195,19 +195,15 @@ class HeatWaveProblem:
                 n_loc, off, llo, lup, mask = dist.partition_brick(n, lo, up, partition[0], partition[1])
                 # ghost layer (deal.II's ghost cells): the brick extended by one cell layer across every face shared with
                 # another rank - what the dense cell-patch smoother assembles its interface patches on
-                glo = [1 if partition[1][a] > 0 else 0 for a in range(dim)]
-                ghi = [1 if partition[1][a] < partition[0][a] - 1 else 0 for a in range(dim)]
+                glo, ghi = dist.ghost_layers(partition[0], partition[1])
                 hh = [(up[a] - lo[a]) / n[a] for a in range(dim)]
                 n_ext = [n_loc[a] + glo[a] + ghi[a] for a in range(dim)]
                 lo_ext = [llo[a] - glo[a] * hh[a] for a in range(dim)]
                 up_ext = [lup[a] + ghi[a] * hh[a] for a in range(dim)]
                 v_loc = v_ext = None
                 if v is not None:
-                    vg = v.reshape([m + 1 for m in n[::-1]] + [dim])             # [z][y][x][xyz]
-                    sl_loc = tuple(slice(off[a], off[a] + n_loc[a] + 1) for a in range(dim))[::-1]
-                    sl_ext = tuple(slice(off[a] - glo[a], off[a] + n_loc[a] + ghi[a] + 1) for a in range(dim))[::-1]
-                    v_loc = np.ascontiguousarray(vg[sl_loc]).reshape(-1, dim)
-                    v_ext = np.ascontiguousarray(vg[sl_ext]).reshape(-1, dim)
+                    v_loc = dist.brick_vertices(v, n, off, n_loc)
+                    v_ext = dist.brick_vertices(v, n, off, n_loc, glo, ghi)
                 self.meshes[rf] = capi.Mesh(ctx, n_loc, lower=llo, upper=lup, vertices=v_loc, dirichlet_faces=mask)
                 dist.set_partition(self.meshes[rf], partition[0], partition[1])
                 if v_ext is not None:

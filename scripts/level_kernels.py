@@ -1,7 +1,7 @@
 """The two kernels that dominate a V-cycle, on the FINEST multigrid level of configs[1] (3D heat, Q4 x cG(2), 96^3 cells, FP32):
 PreconditionVanka::vmult in Kronecker form (k_vanka_fd) and the level operator (st_vmult_brick_kernel<float>), timed with
 CUDA events through stfem_mg_level_apply.    python scripts/level_kernels.py [refinement]
-(profile with:  ncu --set full -k regex:k_vanka_fd -s 4 -c 1 ...   /   -k regex:st_vmult_brick -s 4 -c 1 ...)"""
+(profile with:  PROFILE=1 ncu --profile-from-start off --set full -k regex:k_vanka_fd -s 4 -c 1 ...   /   -k regex:st_vmult_brick ...)"""
 import os
 import sys
 
@@ -21,6 +21,11 @@ lop = prob.level_ops[-1]
 dx, dy = lop.new_vector(), lop.new_vector()
 dx.upload(np.sin(0.1 * np.arange(lop.n)[None, :] + np.arange(lop.nb_rows)[:, None]).astype(np.float32))
 dofs = lop.n * lop.nb_rows
+if os.environ.get("PROFILE"):
+    # ncu --profile-from-start off: only the launches below are candidates (the set-up launches hundreds of small kernels)
+    import ctypes
+    ctx.synchronize()
+    ctypes.CDLL("libcudart.so").cudaProfilerStart()
 for what, name, bytes_per_dof in ((0, "PreconditionVanka::vmult (k_vanka_fd, float)", 12), (4, "level operator vmult (brick kernel, float)", 8)):
     for _ in range(3):
         prob.mg.level_apply(level, what, dy, dx)

@@ -172,3 +172,37 @@ def test_partitioned_transfers_reproduce_global_transfers(world, dim, n_fine, k)
         err_r, err_p = results[r]
         assert err_r < 1e-13, (r, err_r)
         assert err_p < 1e-13, (r, err_p)
+
+
+def test_ghost_layer_vertices_are_slices_of_the_global_mesh():
+    """Host logic of the ghost cell layer (dist.ghost_layers / brick_vertices, used by the driver for partitioned
+    general-geometry meshes): the union of the local bricks is the global mesh, and a brick's ghost-extended vertex array
+    contains exactly the first vertex layer of its neighbours."""
+    import dealii_stfem_b200 as st
+    n, grid = [4, 6, 2], [2, 2, 1]
+    g = [np.linspace(0.0, 1.0, m + 1) for m in n]
+    V = np.stack(np.meshgrid(g[2], g[1], g[0], indexing="ij")[::-1], axis=-1)          # [z][y][x][xyz]
+    V = V + 0.01 * np.random.RandomState(0).uniform(-1, 1, V.shape)
+    seen = np.zeros(V.shape[:3], bool)
+    for rank in range(4):
+        coords = st.dist.coords_of(rank, grid)
+        n_loc, off, llo, lup, mask = st.dist.partition_brick(n, [0.0] * 3, [1.0] * 3, grid, coords)
+        glo, ghi = st.dist.ghost_layers(grid, coords)
+        assert glo == [int(c > 0) for c in coords] and ghi == [int(c < gg - 1) for c, gg in zip(coords, grid)]
+        v_loc = st.dist.brick_vertices(V, n, off, n_loc).reshape(n_loc[2] + 1, n_loc[1] + 1, n_loc[0] + 1, 3)
+        v_ext = st.dist.brick_vertices(V, n, off, n_loc, glo, ghi)
+        ne = [n_loc[a] + glo[a] + ghi[a] for a in range(3)]
+        v_ext = v_ext.reshape(ne[2] + 1, ne[1] + 1, ne[0] + 1, 3)
+        # the local brick sits inside the extended one at offset g_lo
+        inner = v_ext[glo[2]:glo[2] + n_loc[2] + 1, glo[1]:glo[1] + n_loc[1] + 1, glo[0]:glo[0] + n_loc[0] + 1]
+        assert np.array_equal(inner, v_loc)
+        # ... and both are slices of the global array
+        assert np.array_equal(v_loc, V[off[2]:off[2] + n_loc[2] + 1, off[1]:off[1] + n_loc[1] + 1, off[0]:off[0] + n_loc[0] + 1])
+        if glo[0]:
+            assert np.array_equal(v_ext[glo[2]:glo[2] + n_loc[2] + 1, glo[1]:glo[1] + n_loc[1] + 1, 0],
+                                  V[off[2]:off[2] + n_loc[2] + 1, off[1]:off[1] + n_loc[1] + 1, off[0] - 1])
+        if ghi[1]:
+            assert np.array_equal(v_ext[glo[2]:glo[2] + n_loc[2] + 1, -1, glo[0]:glo[0] + n_loc[0] + 1],
+                                  V[off[2]:off[2] + n_loc[2] + 1, off[1] + n_loc[1] + 1, off[0]:off[0] + n_loc[0] + 1])
+        seen[off[2]:off[2] + n_loc[2] + 1, off[1]:off[1] + n_loc[1] + 1, off[0]:off[0] + n_loc[0] + 1] = True
+    assert seen.all()
