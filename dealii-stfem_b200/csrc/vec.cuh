@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.hpp"
@@ -277,6 +278,121 @@ namespace stfem
       }
   }
 
+  // ---- Gram-Schmidt kernels with the number of basis vectors M as a compile-time constant and TWO entries per thread and
+  // sweep (16-byte loads): the generic kernels above keep (M + 1) 8-byte loads per thread in flight, i.e. about 16 KB per SM
+  // for M = 3 - less than half of what the HBM latency-bandwidth product asks for (measured: k_multi_axpy_dot 2.4 TB/s,
+  // k_multi_dot 4.3 TB/s).  Same arithmetic, same summation structure (per-thread partial sums in double, warp shuffle,
+  // one atomic per CTA and vector).
+  template <typename T> struct Pair;
+  template <> struct Pair<double> { using type = double2; };
+  template <> struct Pair<float> { using type = float2; };
+
+  template <int NACC>
+  __device__ __forceinline__ void block_reduce_atomic(double (&acc)[NACC], double *__restrict__ out)
+  {
+    __shared__ double sh[NACC][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k)
+      {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[k][warp] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < NACC)
+      {
+        double v = 0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += sh[threadIdx.x][wv];
+        atomicAdd(out + threadIdx.x, v);
+      }
+  }
+
+  // out[k] += <w, V_k>, k < M
+  template <typename T, int M>
+  __global__ void __launch_bounds__(256) k_multi_dot_m(long long n, MultiCoef<T> mc, const T *__restrict__ w, double *__restrict__ out, DotMask mask)
+  {
+    using T2 = typename Pair<T>::type;
+    double acc[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) acc[k] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x * 2;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride)
+      {
+        if (i + 1 < n)
+          {
+            const T2 w2 = *reinterpret_cast<const T2 *>(w + i);
+            T2       v2[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) v2[k] = *reinterpret_cast<const T2 *>(mc.v[k] + i);
+            const bool   m0 = mask.active && dot_masked(mask, i), m1 = mask.active && dot_masked(mask, i + 1);
+            const double a0 = m0 ? 0.0 : (double)w2.x, a1 = m1 ? 0.0 : (double)w2.y;
+#pragma unroll
+            for (int k = 0; k < M; ++k) acc[k] += a0 * (double)v2[k].x + a1 * (double)v2[k].y;
+          }
+        else if (!(mask.active && dot_masked(mask, i)))
+          {
+            const double a0 = (double)w[i];
+#pragma unroll
+            for (int k = 0; k < M; ++k) acc[k] += a0 * (double)mc.v[k][i];
+          }
+      }
+    block_reduce_atomic<M>(acc, out);
+  }
+
+  // w += sum_k c[k] V_k, then with the updated w: out[k] += <w, V_k> (k < M), out[M] += ||w||^2
+  template <typename T, int M>
+  __global__ void __launch_bounds__(256) k_multi_axpy_dot_m(long long n, MultiCoef<T> mc, T *__restrict__ w, double *__restrict__ out, DotMask mask)
+  {
+    using T2 = typename Pair<T>::type;
+    double acc[M + 1];
+#pragma unroll
+    for (int k = 0; k <= M; ++k) acc[k] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x * 2;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride)
+      {
+        if (i + 1 < n)
+          {
+            T2 w2 = *reinterpret_cast<const T2 *>(w + i);
+            T2 v2[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) v2[k] = *reinterpret_cast<const T2 *>(mc.v[k] + i);
+#pragma unroll
+            for (int k = 0; k < M; ++k)
+              {
+                w2.x += mc.c[k] * v2[k].x;
+                w2.y += mc.c[k] * v2[k].y;
+              }
+            *reinterpret_cast<T2 *>(w + i) = w2;
+            const bool   m0 = mask.active && dot_masked(mask, i), m1 = mask.active && dot_masked(mask, i + 1);
+            const double a0 = m0 ? 0.0 : (double)w2.x, a1 = m1 ? 0.0 : (double)w2.y;
+#pragma unroll
+            for (int k = 0; k < M; ++k) acc[k] += a0 * (double)v2[k].x + a1 * (double)v2[k].y;
+            acc[M] += a0 * a0 + a1 * a1;
+          }
+        else
+          {
+            T s = w[i];
+            T vk[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k)
+              {
+                vk[k] = mc.v[k][i];
+                s += mc.c[k] * vk[k];
+              }
+            w[i] = s;
+            if (!(mask.active && dot_masked(mask, i)))
+              {
+                const double sd = (double)s;
+#pragma unroll
+                for (int k = 0; k < M; ++k) acc[k] += sd * (double)vk[k];
+                acc[M] += sd * sd;
+              }
+          }
+      }
+    block_reduce_atomic<M + 1>(acc, out);
+  }
+
   // ------------------------------------------------------------------ host wrappers
   inline int grid_for(stfem_ctx *ctx, long long n, int threads)
   {
@@ -353,6 +469,17 @@ namespace stfem
     }
   };
 
+  // the specialised Gram-Schmidt kernels read pairs of entries: every vector must start on a 16-byte boundary
+  // (STFEM_GS_GENERIC=1 keeps the generic kernels, for A/B timing)
+  template <typename T>
+  inline bool gs_specialised(const T *w, const MultiCoef<T> &mc)
+  {
+    static const bool generic = std::getenv("STFEM_GS_GENERIC") != nullptr;
+    if (generic) return false;
+    bool ok = ((unsigned long long)w & 15ull) == 0;
+    for (int k = 0; k < mc.m; ++k) ok = ok && ((unsigned long long)mc.v[k] & 15ull) == 0;
+    return ok;
+  }
   // out[k] = <w, V[k]> for k < m (any m: chunks of MAXK).  Synchronises the stream.
   template <typename T>
   inline int v_multi_dot(DotScratch &sc, const BlockVec<T> &w, const std::vector<const BlockVec<T> *> &V, double *out)
@@ -367,7 +494,15 @@ namespace stfem
         MultiCoef<T> mc;
         mc.m = std::min(MAXK, m - k0);
         for (int k = 0; k < mc.m; ++k) mc.v[k] = V[k0 + k]->d;
-        k_multi_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0, sc.mask);
+        const int grid = grid_for(ctx, (w.size() + 1) / 2, 256);
+        switch (gs_specialised(w.d, mc) ? mc.m : 0)
+          {
+#define STFEM_MD_CASE(M_) case M_: k_multi_dot_m<T, M_><<<grid, 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0, sc.mask); break;
+            STFEM_MD_CASE(1) STFEM_MD_CASE(2) STFEM_MD_CASE(3) STFEM_MD_CASE(4) STFEM_MD_CASE(5) STFEM_MD_CASE(6) STFEM_MD_CASE(7) STFEM_MD_CASE(8)
+            STFEM_MD_CASE(9) STFEM_MD_CASE(10)
+#undef STFEM_MD_CASE
+            default: k_multi_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d + k0, sc.mask);
+          }
         ctx->launches++;
       }
     if (sc.mask.active && ctx->n_ranks > 1 && ctx->nccl_comm) // vectors on agglomerated (global) levels are complete on every rank
@@ -458,7 +593,15 @@ namespace stfem
         mc.v[k] = V[k]->d;
         mc.c[k] = (T)c[k];
       }
-    k_multi_axpy_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d, sc.mask);
+    const int grid = grid_for(ctx, (w.size() + 1) / 2, 256);
+    switch (gs_specialised(w.d, mc) ? m : 0)
+      {
+#define STFEM_MAD_CASE(M_) case M_: k_multi_axpy_dot_m<T, M_><<<grid, 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d, sc.mask); break;
+        STFEM_MAD_CASE(1) STFEM_MAD_CASE(2) STFEM_MAD_CASE(3) STFEM_MAD_CASE(4) STFEM_MAD_CASE(5) STFEM_MAD_CASE(6) STFEM_MAD_CASE(7) STFEM_MAD_CASE(8)
+        STFEM_MAD_CASE(9)
+#undef STFEM_MAD_CASE
+        default: k_multi_axpy_dot<T><<<grid_for(ctx, w.size(), 256), 256, 0, ctx->stream>>>(w.size(), mc, w.d, sc.d, sc.mask);
+      }
     ctx->launches++;
     if (sc.mask.active && ctx->n_ranks > 1 && ctx->nccl_comm)
       {
