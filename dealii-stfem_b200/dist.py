@@ -113,7 +113,7 @@ def allreduce(ctx, values, op="sum"):
     return v
 
 
-def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
+def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12, extended=False):
     """Partitioned run against the single-GPU run of the same GLOBAL problem, computed redundantly by every rank on its own
     GPU (a second context without communicator): returns a dict of relative errors / iteration counts and "ok".
       vmult     Q4 x cG(2) operator, vmult_cells^3 cells per rank, FP64                              (tolerance 1e-12)
@@ -122,6 +122,8 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
       practical_*  the reference's practical set-up in small (perturbed mesh, coefficient table, dense cell-patch smoother on
                 ghost-layer patches, cut-off initial value): operator + matrix diagonal (1e-12), V-cycle (2e-3), two time
                 steps (iterations +-1, solution and point functionals 1e-8)
+      extended  (scripts/mgpu_check.py only) the practical set-up once more with the point-Jacobi inner preconditioner and
+                Chebyshev smoothing: iterations +-1, solution 1e-8
     Every rank must call it (collective); ctx is the context that owns the communicator."""
     from . import driver, fe_time_host
     grid = proc_grid_for(world, 3)
@@ -243,14 +245,29 @@ def parity_check(ctx, device, rank, world, refinement=2, vmult_cells=12):
     res["practical_solve"] = float(np.abs(part.x.download() - brick_of(sol_g, nb, npg, npl, off)).max() / np.abs(sol_g).max())
     fun_p = np.array(part.functional_rows[-1][1:])
     res["practical_functionals"] = float(np.abs(fun_p - fun_g).max() / max(np.abs(fun_g).max(), 1e-300))
-    dx.free(); dy.free(); part.close(); glob.close(); ctx0.close()
-    ok_practical = (res["practical_vmult"] <= 1e-12 and res["practical_diagonal"] <= 1e-12 and res["practical_vcycle"] <= 2e-3 and
+    dx.free(); dy.free(); part.close(); glob.close()
+    ok_jacobi = True
+    if extended:
+        # the same set-up with the point-Jacobi inner preconditioner (diagonal summed over the ranks) and Chebyshev smoothing
+        p2 = dict(p)
+        p2["innerPreconditioner"], p2["smoother"], p2["smoothingSteps"] = "jacobi", "chebyshev", 2
+        glob = driver.HeatWaveProblem(ctx0, p2, 3, refinement, r, space_degree=k, vertices_fn=vertices)
+        it_gj = glob.step(evaluate_error=False)
+        sol_gj = glob.x.download()
+        part = driver.HeatWaveProblem(ctx, p2, 3, refinement, r, space_degree=k, vertices_fn=vertices, partition=(grid, coords))
+        it_pj = part.step(evaluate_error=False)
+        res["jacobi_iterations_global"], res["jacobi_iterations_partitioned"] = int(it_gj), int(it_pj)
+        res["jacobi_solve"] = float(np.abs(part.x.download() - brick_of(sol_gj, nb, npg, npl, off)).max() / np.abs(sol_gj).max())
+        part.close(); glob.close()
+        ok_jacobi = abs(it_gj - it_pj) <= 1 and res["jacobi_solve"] <= 1e-8
+    ctx0.close()
+    ok_practical = ok_jacobi and (res["practical_vmult"] <= 1e-12 and res["practical_diagonal"] <= 1e-12 and res["practical_vcycle"] <= 2e-3 and
                     all(abs(a - b) <= 1 for a, b in zip(it_g, it_pp)) and res["practical_solve"] <= 1e-8 and
                     res["practical_functionals"] <= 1e-8)
     ok = res["vmult"] <= 1e-12 and res["vmult_host"] <= 1e-12 and res["vcycle"] <= 2e-3 and abs(it_p - it_g0) <= 1 and res["solve"] <= 1e-8 and ok_practical
     # every rank must agree: the worst error / flag over the ranks
     keys = ["vmult", "vmult_host", "vcycle", "solve", "practical_vmult", "practical_diagonal", "practical_vcycle", "practical_solve",
-            "practical_functionals"]
+            "practical_functionals"] + (["jacobi_solve"] if extended else [])
     worst = allreduce(ctx, [res[kk] for kk in keys] + [0.0 if ok else 1.0], "max")
     for kk, w in zip(keys, worst):
         res[kk] = float(w)

@@ -33,7 +33,7 @@ def bcast(b):
 ctx = st.Context(local)
 st.dist.init_comm(ctx, rank, world, bcast)
 torch.cuda.synchronize()
-res = st.dist.parity_check(ctx, local, rank, world, refinement=ref)
+res = st.dist.parity_check(ctx, local, rank, world, refinement=ref, extended=True)
 if rank == 0:
     print("parity_multi_gpu " + json.dumps(res), flush=True)
 print("rank %d: %s" % (rank, "ok" if res["ok"] else "FAIL"), flush=True)
