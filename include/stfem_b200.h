@@ -93,14 +93,21 @@ typedef struct stfem_op_desc {
   const double *laplace_coeff_q;    /* host pointer, n_cells * (degree+1)^dim values (cell-major, q-points
                                        lexicographic) = the reference's Table [cell][q]
                                        (operators.h:1060-1087, 1185-1186); may be NULL */
-  int kernel_variant;               /* 0 = default.  Tuning / cross-check selectors (all produce the same operator):
-                                       1 generic q-point kernel; 2 (level operators) dense Vanka patches instead of the
-                                       Kronecker form; 11-19, 26-28 launch-bound configurations of the Cartesian kernel;
+  int kernel_variant;               /* 0 = default: the brick kernel (st_vmult_brick.cuh) on 3D Cartesian constant-coefficient
+                                       meshes with >= 2 time blocks, the per-cell kernels elsewhere; general geometry: stored
+                                       metric where it fits, else geometry on the fly.  Tuning / cross-check selectors (all
+                                       produce the same operator): 1 generic q-point kernel; 2 (level operators) dense Vanka
+                                       patches instead of the Kronecker form; 3 per-cell Cartesian kernel of round 1 instead of
+                                       the brick kernel; 5 / 6 general geometry with the stored metric / on the fly from the
+                                       cell vertices; 11-19, 26-28 launch-bound configurations of the per-cell Cartesian kernel;
                                        17 largest-CTA rule; 18, 20-25 software-pipelined persistent kernel; 31-34 ablation
-                                       experiments (WRONG results, timing only; rejected unless STFEM_ALLOW_ABLATION is set); 40-42 cp.async.bulk + mbarrier gather;
-                                       51 two 8-byte exchange fields instead of 16-byte pairs; 60 EXPERIMENTAL
-                                       fast-diagonalisation form (st_vmult_cart_fd.cuh; written after the last GPU call of
-                                       round 1, its parity test has not run yet) */
+                                       experiments (WRONG results, timing only; rejected unless STFEM_ALLOW_ABLATION is set);
+                                       40-42 cp.async.bulk + mbarrier gather; 51 two 8-byte exchange fields instead of 16-byte
+                                       pairs; 60 fast-diagonalisation form of the per-cell kernel (st_vmult_cart_fd.cuh,
+                                       verified on the GPU in round 2: tests/test_cart_fd_gpu.py); brick kernel: 70 plain loads
+                                       instead of TMA, 72 no size threshold, 77 X and Y+Z phases on separate warps, 79 barrier
+                                       pipeline instead of CTA barriers, 80-89 forced number of z chunks, 90 per-SM alternation
+                                       of the X warps */
 } stfem_op_desc;
 
 int stfem_op_create(stfem_mesh_t mesh, const stfem_op_desc *desc, stfem_op_t *out);
@@ -117,9 +124,10 @@ int stfem_op_vmult_slice_add(stfem_op_t op, void *const *dst, const void *src0);
 /* get_matrix_diagonal (operators.h:613-625): diag_i = Alpha(i,i) diag K + Beta(i,i) diag M */
 int stfem_op_diagonal(stfem_op_t op, void *const *diag);
 
-/* kernel_variant 60 — EXPERIMENTAL, not verified on a GPU in round 1: the Cartesian operator in fast-diagonalisation form
- * (csrc/st_vmult_cart_fd.cuh).  This host-only helper returns the modes it is built on: V (n1 x n1, row-major) and lam (n1)
- * with  Mh = V^T V,  Kh = V^T diag(lam) V  for the 1D reference matrices of FE_Q(degree) / QGauss(degree+1). */
+/* kernel_variant 60: the Cartesian operator in fast-diagonalisation form (csrc/st_vmult_cart_fd.cuh; parity-tested on the GPU,
+ * not the default: 1.01 ms against 0.90 ms of the brick kernel on configs[1]).  This host-only helper returns the modes it is
+ * built on: V (n1 x n1, row-major) and lam (n1) with  Mh = V^T V,  Kh = V^T diag(lam) V  for the 1D reference matrices of
+ * FE_Q(degree) / QGauss(degree+1). */
 int stfem_cart_fd_modes(int degree, double *V, double *lam);
 
 /* Same call with HOST buffers (nb arrays of N numbers of the operator's number type):
