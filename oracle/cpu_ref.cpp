@@ -9,9 +9,6 @@
 // what the GPU kernel is compared with in bench.py's cpu_baseline.  deal.II's FEEvaluation is restated
 // as straightforward sum factorisation (S = GLL->Gauss values, D = GLL->Gauss derivatives).
 // Threading: OpenMP over cells with an 2^dim colouring (deal.II uses MPI ranks / partition_partition).
-// Vectorisation: like deal.II's VectorizedArray the cell kernel works on a BATCH of W = 8 cells of one colour at a time
-// (arrays [entry][W], innermost loops over the batch lane marked `omp simd`), so that every sweep and every
-// quadrature-point operation is unit-stride SIMD; gather and scatter stay scalar per lane.
 // Parity of this file itself is pinned against oracle/spatial.py in tests/test_oracle_cpu_ref.py.
 #include <cmath>
 #include <cstdlib>
@@ -49,11 +46,9 @@ namespace
     return false;
   }
 
-  constexpr int W = 8; // cells per batch (one AVX-512 register of doubles, two AVX2 ones)
-
-  // y[q][w] = sum_i M[q*n+i] x[i][w] along direction `dir` of an n^DIM tensor, for all W lanes (TR: transpose of M)
+  // y[q] = sum_i M[q*n+i] x[i] along direction `dir` of an n^DIM tensor (TR: transpose of M)
   template <int DIM, int N, bool TR, bool ADD>
-  inline void sweep(const double *M, const double (*in)[W], double (*out)[W], int dir)
+  inline void sweep(const double *M, const double *in, double *out, int dir)
   {
     constexpr int NT     = (DIM == 3) ? N * N * N : N * N;
     const int     stride = dir == 0 ? 1 : (dir == 1 ? N : N * N);
@@ -63,27 +58,12 @@ namespace
           const int base = outer * N * stride + inner;
           for (int q = 0; q < N; ++q)
             {
-              double s[W];
-#pragma omp simd
-              for (int w = 0; w < W; ++w) s[w] = 0;
-              for (int i = 0; i < N; ++i)
-                {
-                  const double  m  = TR ? M[i * N + q] : M[q * N + i];
-                  const double *xi = in[base + i * stride];
-#pragma omp simd
-                  for (int w = 0; w < W; ++w) s[w] += m * xi[w];
-                }
-              double *o = out[base + q * stride];
+              double s = 0;
+              for (int i = 0; i < N; ++i) s += (TR ? M[i * N + q] : M[q * N + i]) * in[base + i * stride];
               if (ADD)
-                {
-#pragma omp simd
-                  for (int w = 0; w < W; ++w) o[w] += s[w];
-                }
+                out[base + q * stride] += s;
               else
-                {
-#pragma omp simd
-                  for (int w = 0; w < W; ++w) o[w] = s[w];
-                }
+                out[base + q * stride] = s;
             }
         }
   }
@@ -96,65 +76,43 @@ namespace
     constexpr int NSYM = DIM * (DIM + 1) / 2;
     constexpr int K    = N - 1;
     std::memset(dst, 0, sizeof(double) * s.N);
-    const int    ncol = 1 << DIM;
-    const double vol  = s.h[0] * s.h[1] * (DIM == 3 ? s.h[2] : 1.0);
+    const int ncol = 1 << DIM;
     for (int colour = 0; colour < ncol; ++colour)
       {
-        // cells of this colour: cx = c0 + 2 i, cy = c1 + 2 j, cz = c2 + 2 l; batches of W consecutive cells in x
-        const int c0 = colour & 1, c1 = (colour >> 1) & 1, c2 = (colour >> 2) & 1;
-        const int m0 = (s.n[0] - c0 + 1) / 2, m1 = (s.n[1] - c1 + 1) / 2, m2 = DIM == 3 ? (s.n[2] - c2 + 1) / 2 : 1;
-        if (m0 <= 0 || m1 <= 0 || m2 <= 0) continue;
-        const int       bx        = (m0 + W - 1) / W;
-        const long long n_batches = (long long)bx * m1 * m2;
 #pragma omp parallel for schedule(static)
-        for (long long batch = 0; batch < n_batches; ++batch)
+        for (long long cell = 0; cell < s.n_cells; ++cell)
           {
-            const int ib = (int)(batch % bx), j = (int)((batch / bx) % m1), l = (int)(batch / ((long long)bx * m1));
-            const int cy = c1 + 2 * j, cz = DIM == 3 ? c2 + 2 * l : 0;
-            int       cxs[W];
-            bool      on[W];
-            long long cells[W];
-            for (int w = 0; w < W; ++w)
-              {
-                const int i = ib * W + w;
-                on[w]       = i < m0;
-                cxs[w]      = c0 + 2 * (on[w] ? i : 0);
-                cells[w]    = cxs[w] + (long long)s.n[0] * (cy + (long long)s.n[1] * cz);
-              }
-            alignas(64) double u[NT][W], t0[NT][W], t1[NT][W], g[DIM][NT][W], r[NT][W];
+            const int cx = (int)(cell % s.n[0]), cy = (int)((cell / s.n[0]) % s.n[1]);
+            const int cz = DIM == 3 ? (int)(cell / ((long long)s.n[0] * s.n[1])) : 0;
+            if (((cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2)) != colour) continue;
+            double u[NT], t0[NT], t1[NT], g[DIM][NT], r[NT];
             // gather (read_dof_values)
-            for (int ll = 0; ll < (DIM == 3 ? N : 1); ++ll)
-              for (int jj = 0; jj < N; ++jj)
-                for (int ii = 0; ii < N; ++ii)
-                  for (int w = 0; w < W; ++w)
-                    {
-                      const int       ix = cxs[w] * K + ii, iy = cy * K + jj, iz = DIM == 3 ? cz * K + ll : 0;
-                      const long long gi = ix + (long long)s.np[0] * (iy + (long long)s.np[1] * iz);
-                      u[(ll * N + jj) * N + ii][w] = (!on[w] || constrained(s, ix, iy, iz)) ? 0.0 : src[gi];
-                    }
+            for (int l = 0; l < (DIM == 3 ? N : 1); ++l)
+              for (int j = 0; j < N; ++j)
+                for (int i = 0; i < N; ++i)
+                  {
+                    const int ix = cx * K + i, iy = cy * K + j, iz = DIM == 3 ? cz * K + l : 0;
+                    const long long gi = ix + (long long)s.np[0] * (iy + (long long)s.np[1] * iz);
+                    u[(l * N + j) * N + i] = constrained(s, ix, iy, iz) ? 0.0 : src[gi];
+                  }
+            const double *mt = s.metric ? s.metric + (size_t)cell * NT * (NSYM + 1) : nullptr;
+            const double *cq = s.coeff_q ? s.coeff_q + (size_t)cell * NT : nullptr;
+            double        vol = s.h[0] * s.h[1] * (DIM == 3 ? s.h[2] : 1.0);
             if (mass)
               {
                 // evaluate(values)
                 sweep<DIM, N, false, false>(s.S, u, t0, 0);
                 sweep<DIM, N, false, false>(s.S, t0, t1, 1);
-                double(*uq)[W] = t1;
+                double *uq = t1;
                 if (DIM == 3) { sweep<DIM, N, false, false>(s.S, t1, t0, 2); uq = t0; }
                 for (int q = 0; q < NT; ++q)
                   {
                     const int qx = q % N, qy = (q / N) % N, qz = q / (N * N);
-                    if (s.metric)
-                      {
-                        for (int w = 0; w < W; ++w) uq[q][w] *= s.metric[((size_t)cells[w] * NT + q) * (NSYM + 1) + NSYM]; // submit_value
-                      }
-                    else
-                      {
-                        const double jxw = vol * s.w[qx] * s.w[qy] * (DIM == 3 ? s.w[qz] : 1.0);
-#pragma omp simd
-                        for (int w = 0; w < W; ++w) uq[q][w] *= jxw;
-                      }
+                    const double jxw = mt ? mt[q * (NSYM + 1) + NSYM] : vol * s.w[qx] * s.w[qy] * (DIM == 3 ? s.w[qz] : 1.0);
+                    uq[q] *= jxw; // submit_value
                   }
                 // integrate(values)
-                double(*a)[W] = uq, (*b)[W] = (uq == t0) ? t1 : t0;
+                double *a = uq, *b = (uq == t0) ? t1 : t0;
                 if (DIM == 3) { sweep<DIM, N, true, false>(s.S, a, b, 2); std::swap(a, b); }
                 sweep<DIM, N, true, false>(s.S, a, b, 1);
                 sweep<DIM, N, true, false>(s.S, b, r, 0);
@@ -169,55 +127,42 @@ namespace
                     if (DIM == 3)
                       sweep<DIM, N, false, false>(d == 2 ? s.D : s.S, t1, g[d], 2);
                     else
-                      std::memcpy(g[d], t1, sizeof(double) * NT * W);
+                      std::memcpy(g[d], t1, sizeof(double) * NT);
                   }
                 // submit_gradient(coef * grad u): real-space gradient folded with JxW
                 for (int q = 0; q < NT; ++q)
                   {
-                    const int qx = q % N, qy = (q / N) % N, qz = q / (N * N);
-                    if (s.metric)
+                    const int    qx = q % N, qy = (q / N) % N, qz = q / (N * N);
+                    const double c  = cq ? cq[q] : 1.0;
+                    double       gi[DIM], to[DIM];
+                    for (int d = 0; d < DIM; ++d) gi[d] = g[d][q];
+                    if (mt)
                       {
-                        for (int w = 0; w < W; ++w)
+                        const double *m = mt + q * (NSYM + 1);
+                        if (DIM == 2)
                           {
-                            const double *m = s.metric + ((size_t)cells[w] * NT + q) * (NSYM + 1);
-                            const double  c = s.coeff_q ? s.coeff_q[(size_t)cells[w] * NT + q] : 1.0;
-                            double        gi[DIM], to[DIM];
-                            for (int d = 0; d < DIM; ++d) gi[d] = g[d][q][w];
-                            if (DIM == 2)
-                              {
-                                to[0] = m[0] * gi[0] + m[1] * gi[1];
-                                to[1] = m[1] * gi[0] + m[2] * gi[1];
-                              }
-                            else
-                              {
-                                to[0] = m[0] * gi[0] + m[1] * gi[1] + m[2] * gi[2];
-                                to[1] = m[1] * gi[0] + m[3] * gi[1] + m[4] * gi[2];
-                                to[2] = m[2] * gi[0] + m[4] * gi[1] + m[5] * gi[2];
-                              }
-                            for (int d = 0; d < DIM; ++d) g[d][q][w] = c * to[d];
+                            to[0] = m[0] * gi[0] + m[1] * gi[1];
+                            to[1] = m[1] * gi[0] + m[2] * gi[1];
+                          }
+                        else
+                          {
+                            to[0] = m[0] * gi[0] + m[1] * gi[1] + m[2] * gi[2];
+                            to[1] = m[1] * gi[0] + m[3] * gi[1] + m[4] * gi[2];
+                            to[2] = m[2] * gi[0] + m[4] * gi[1] + m[5] * gi[2];
                           }
                       }
                     else
                       {
                         const double wq = vol * s.w[qx] * s.w[qy] * (DIM == 3 ? s.w[qz] : 1.0);
-                        for (int d = 0; d < DIM; ++d)
-                          {
-                            const double f = wq / (s.h[d] * s.h[d]);
-                            if (s.coeff_q)
-                              for (int w = 0; w < W; ++w) g[d][q][w] = s.coeff_q[(size_t)cells[w] * NT + q] * (f * g[d][q][w]);
-                            else
-                              {
-#pragma omp simd
-                                for (int w = 0; w < W; ++w) g[d][q][w] = f * g[d][q][w];
-                              }
-                          }
+                        for (int d = 0; d < DIM; ++d) to[d] = wq / (s.h[d] * s.h[d]) * gi[d];
                       }
+                    for (int d = 0; d < DIM; ++d) g[d][q] = c * to[d];
                   }
                 // integrate(gradients)
                 std::memset(r, 0, sizeof(r));
                 for (int d = 0; d < DIM; ++d)
                   {
-                    const double(*a)[W] = g[d];
+                    const double *a = g[d];
                     if (DIM == 3)
                       {
                         sweep<DIM, N, true, false>(d == 2 ? s.D : s.S, a, t0, 2);
@@ -227,18 +172,16 @@ namespace
                     sweep<DIM, N, true, true>(d == 0 ? s.D : s.S, t1, r, 0);
                   }
               }
-            // scatter (distribute_local_to_global): the cells of a batch share no DoF (same colour)
-            for (int ll = 0; ll < (DIM == 3 ? N : 1); ++ll)
-              for (int jj = 0; jj < N; ++jj)
-                for (int ii = 0; ii < N; ++ii)
-                  for (int w = 0; w < W; ++w)
-                    {
-                      if (!on[w]) continue;
-                      const int ix = cxs[w] * K + ii, iy = cy * K + jj, iz = DIM == 3 ? cz * K + ll : 0;
-                      if (constrained(s, ix, iy, iz)) continue;
-                      const long long gi = ix + (long long)s.np[0] * (iy + (long long)s.np[1] * iz);
-                      dst[gi] += r[(ll * N + jj) * N + ii][w];
-                    }
+            // scatter (distribute_local_to_global)
+            for (int l = 0; l < (DIM == 3 ? N : 1); ++l)
+              for (int j = 0; j < N; ++j)
+                for (int i = 0; i < N; ++i)
+                  {
+                    const int ix = cx * K + i, iy = cy * K + j, iz = DIM == 3 ? cz * K + l : 0;
+                    if (constrained(s, ix, iy, iz)) continue;
+                    const long long gi = ix + (long long)s.np[0] * (iy + (long long)s.np[1] * iz);
+                    dst[gi] += r[(l * N + j) * N + i];
+                  }
           }
       }
   }
